@@ -1,0 +1,148 @@
+/*
+ * tn_b200.h -- C ABI of libtn_b200.so: the thermal-nerfacto per-ray hot path as sm_100a CUDA kernels.
+ *
+ * The reference (yvette256/nerfstudio-thermal, a nerfstudio 1.0.2 fork) contains no native code; on this
+ * path it either runs torch ops (`implementation="torch"`, the parity target) or calls tiny-cuda-nn.  Each
+ * entry point below replaces the torch-op sequence of one reference function; the citation after "replaces:"
+ * is relative to /root/reference/nerfstudio/.  INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions (every function):
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers owned by the caller
+ *     (PyTorch's caching allocator in the shipped host code) unless the name ends in `_host`;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); nothing allocates, synchronises or
+ *     keeps global mutable state, so calls are re-entrant, one-process-per-GPU safe and CUDA-graph capturable;
+ *   - returns 0 on success, a negative TN_E* code otherwise; tn_last_error_string() describes the last
+ *     failure on the calling thread;
+ *   - all floating-point tensors are float32, row-major, densely packed; "rows" R = rays, S = samples
+ *     per ray, N = points.
+ */
+#ifndef TN_B200_H
+#define TN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TN_OK 0
+#define TN_EINVAL (-1)   /* bad shape / unsupported size / null pointer */
+#define TN_EALIGN (-2)   /* pointer not aligned as required */
+#define TN_ECUDA (-3)    /* a CUDA launch failed; see tn_last_error_string() */
+
+#define TN_MAX_LEVELS 32
+
+/* library identification */
+int tn_version(void);                     /* 100 * major + minor */
+const char* tn_last_error_string(void);   /* thread-local, never NULL */
+const char* tn_build_arch(void);          /* "sm_100a" */
+
+/* ------------------------------------------------------------------------------------------------
+ * Multiresolution hash grid.      replaces: field_components/encodings.py:401-461
+ *   (HashEncoding.hash_fn + pytorch_fwd) and its autograd backward.
+ * x[N,3] in [0,1]; table[L*T, F] with T = 1<<log2_T; scales_host[L] = HashEncoding.scalings (host
+ * floats, L <= TN_MAX_LEVELS); out[N, L*F] level-major.  F in {1,2,4,8}.
+ * table_dtype: 0 = float32, 1 = float16 (derived cache of the fp32 parameter; out stays float32).
+ * idx_out: NULL, or int32[N,L,8] receiving the eight table rows per (point, level) in the reference's
+ *   corner order hashed_0..hashed_7 (encodings.py:431-438) -- the bit-exactness test hook.
+ * ------------------------------------------------------------------------------------------------ */
+int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
+                       int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, void* stream);
+
+/* dy[N, L*F].  dtable[L*T, F] float32 is ACCUMULATED into (caller zero-fills for a fresh gradient).
+ * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; needs `table`. */
+int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
+                       const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sample positions -> normalised grid coordinates.
+ *   replaces: cameras/rays.py:49-58 (Frustums.get_positions), field_components/spatial_distortions.py:66-69
+ *   (SceneContraction, L-inf) and fields/nerfacto_field.py:207-215 == fields/density_fields.py:96-103
+ *   ((p+2)/4, selector, zeroing).
+ * origins/directions [R,3]; ebins[R,S+1] euclidean bin edges (sample s spans ebins[s]..ebins[s+1]).
+ * x_out[R*S,3]; selector_out[R*S] float (1.0 inside, 0.0 outside).
+ * ------------------------------------------------------------------------------------------------ */
+int tn_sample_positions_fwd(const float* origins, const float* directions, const float* ebins, int64_t R,
+                            int S, float* x_out, float* selector_out, void* stream);
+/* dx[R*S,3] -> d_origins[R,3], d_directions[R,3] (overwritten).  Bins carry no gradient
+ * (model_components/ray_samplers.py:360). */
+int tn_sample_positions_bwd(const float* origins, const float* directions, const float* ebins,
+                            const float* dx, int64_t R, int S, float* d_origins, float* d_directions,
+                            void* stream);
+/* The same normalisation for free-standing points p[N,3] (Field.density_fn, fields/base_field.py:48-69). */
+int tn_contract_points_fwd(const float* p, int64_t N, float* x_out, float* selector_out, void* stream);
+int tn_contract_points_bwd(const float* p, const float* dx, int64_t N, float* dp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fully fused small MLPs.          replaces: field_components/mlp.py:159-178 (MLP.pytorch_fwd)
+ * ReLU between layers; out_act: 0 none, 1 sigmoid, 2 trunc_exp (field_components/activations.py:28-42).
+ * n_layers in {2,3}; weights w[i] are nn.Linear layout [out_i, in_i] row-major, biases b[i][out_i].
+ * Supported shapes: in_dim <= 64, width in {16, 64}, out_dim <= 16.
+ * x[N,in_dim] -> y[N,out_dim].  Hidden activations never leave the SM.
+ * ------------------------------------------------------------------------------------------------ */
+int tn_mlp_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
+               const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
+               void* stream);
+/* dy[N,out_dim] = gradient w.r.t. the ACTIVATED output.  The forward activations are recomputed from x
+ * on chip (nothing was saved).  dx: NULL or [N,in_dim] (overwritten).  dw[i]/db[i] (nn.Linear layout)
+ * are ACCUMULATED into with atomics: the caller zero-fills them for a fresh gradient. */
+int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width, int out_dim, int n_layers,
+               const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
+               float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
+
+/* Real spherical-harmonics basis, 4 levels (16 components).
+ *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */
+int tn_sh4(const float* d, int64_t N, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Samplers.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: model_components/ray_samplers.py:78-128 with the UniformLinDispPiecewise spacing (:244-245).
+ * unit_bins[S+1] = torch.linspace(0,1,S+1) (device copy of the host-computed values, so the bin edges
+ * are the reference's to the bit); nears/fars [R]; jitter NULL (eval), [R] (the reference's
+ * torch.rand((R,1)) draw, single_jitter; jitter_per_sample = 0) or [R,S+1] (jitter_per_sample = 1).
+ * sbins_out/ebins_out [R,S+1]: normalised ("spacing") and euclidean bin edges. */
+int tn_piecewise_bins(const float* unit_bins, const float* nears, const float* fars, const float* jitter,
+                      int jitter_per_sample, int64_t R, int S, float* sbins_out, float* ebins_out, void* stream);
+/* replaces: model_components/ray_samplers.py:301-372 (PDFSampler, include_original=False).
+ * weights[R,S_old] (already annealed), sbins_old[R,S_old+1].
+ * u_base[S_new+1]: eval (jitter == NULL): linspace(0, 1-1/nb, nb) + 1/(2 nb), nb = S_new+1 (:328-329);
+ *                  train (jitter given: [R], or [R,nb] with jitter_per_sample = 1): linspace(0, 1-1/nb, nb),
+ *                  the kernel adds jitter/nb (:319-325).
+ * Outputs sbins_new/ebins_new [R,S_new+1].  S_old <= 1024. */
+int tn_pdf_sample(const float* weights, const float* sbins_old, const float* nears, const float* fars,
+                  const float* u_base, const float* jitter, int jitter_per_sample, int64_t R, int S_old,
+                  int S_new, float histogram_padding, float eps, float* sbins_new, float* ebins_new,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Volume rendering.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: cameras/rays.py:128-150 (RaySamples.get_weights).  sigma, deltas [R,S] -> weights [R,S]. */
+int tn_weights_fwd(const float* sigma, const float* deltas, int64_t R, int S, float* weights, void* stream);
+/* dw[R,S] -> dsigma[R,S] (overwritten). */
+int tn_weights_bwd(const float* sigma, const float* deltas, const float* dw, int64_t R, int S,
+                   float* dsigma, void* stream);
+
+/* replaces: model_components/renderers.py:118-133 (+:292-307 RGBT), :509 (accumulation), :547-557 (median
+ * depth), :558-572 (expected depth before the batch-global clip of :574).
+ * weights[R,S], colour[R,S,C] (C <= 4), starts/ends [R,S].
+ * bg_mode: 0 none ("random": no blending), 1 last_sample, 2 constant bg_host[C].
+ * eval_mode != 0 applies nan_to_num to colour and clamps the composite to [0,1] (renderers.py:238-245).
+ * Any output pointer may be NULL.  steps_minmax_out: float[2] updated with atomic min/max of
+ * (starts+ends)/2 over the launch (caller initialises to +inf/-inf) for the :574 clip. */
+int tn_render_fwd(const float* weights, const float* colour, const float* starts, const float* ends,
+                  int64_t R, int S, int C, int bg_mode, const float* bg_host, int eval_mode,
+                  float* rgb_out, float* acc_out, float* depth_median_out, float* depth_expected_out,
+                  float* steps_minmax_out, void* stream);
+/* Gradients of rgb_out / acc_out / unclipped expected depth -> dweights[R,S], dcolour[R,S,C]
+ * (overwritten).  d_rgb/d_acc/d_depth may each be NULL (= zero). */
+int tn_render_bwd(const float* weights, const float* colour, const float* starts, const float* ends,
+                  const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S, int C,
+                  int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TN_B200_H */

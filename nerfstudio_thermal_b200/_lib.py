@@ -1,0 +1,103 @@
+"""ctypes binding of libtn_b200.so (C ABI declared in include/tn_b200.h).
+
+There is no CPU fallback and no alternative backend: if the shared library is missing, every product
+entry point raises `TnLibraryError`.  Build it with `python -c "import __graft_entry__ as g; g.build()"`
+(or `nerfstudio_thermal_b200/csrc/build.sh`).
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtn_b200.so")
+
+
+class TnLibraryError(RuntimeError):
+    pass
+
+
+class TnKernelError(RuntimeError):
+    pass
+
+
+_P = c_void_p  # device pointers travel as integers
+_FPP = POINTER(c_void_p)  # host array of device pointers
+
+# name -> (argtypes); restype is int unless listed in _RESTYPES
+_SIGNATURES = {
+    "tn_version": [],
+    "tn_last_error_string": [],
+    "tn_build_arch": [],
+    "tn_hash_encode_fwd": [_P, _P, c_int, POINTER(c_float), c_int64, c_int, c_int, c_int, _P, _P, _P],
+    "tn_hash_encode_bwd": [_P, _P, c_int, POINTER(c_float), _P, c_int64, c_int, c_int, c_int, _P, _P, _P],
+    "tn_sample_positions_fwd": [_P, _P, _P, c_int64, c_int, _P, _P, _P],
+    "tn_sample_positions_bwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
+    "tn_contract_points_fwd": [_P, c_int64, _P, _P, _P],
+    "tn_contract_points_bwd": [_P, _P, c_int64, _P, _P],
+    "tn_mlp_fwd": [_P, c_int64, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _P],
+    "tn_mlp_bwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _FPP, _FPP, _P],
+    "tn_sh4": [_P, c_int64, _P, _P],
+    "tn_piecewise_bins": [_P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, _P],
+    "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],
+    "tn_weights_fwd": [_P, _P, c_int64, c_int, _P, _P],
+    "tn_weights_bwd": [_P, _P, _P, c_int64, c_int, _P, _P],
+    "tn_render_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int, _P, _P, _P, _P, _P, _P],
+    "tn_render_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), _P, _P, _P],
+}
+_RESTYPES = {"tn_last_error_string": c_char_p, "tn_build_arch": c_char_p}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises TnLibraryError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TnLibraryError(
+            f"{LIB_PATH} not found: the sm_100a CUDA library is required (there is no CPU fallback). "
+            "Build it with nerfstudio_thermal_b200/csrc/build.sh or __graft_entry__.build().")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; map non-zero codes to TnKernelError."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise TnKernelError(f"{name} failed ({rc}): {lib.tn_last_error_string().decode()}")
+
+
+def ptr(t):
+    """Device pointer of a CUDA float32/int32 contiguous tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TnKernelError("libtn_b200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise TnKernelError("libtn_b200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def float_array(values):
+    arr = (c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def ptr_array(tensors):
+    return (c_void_p * len(tensors))(*[ptr(t) for t in tensors])

@@ -1,0 +1,382 @@
+// Multiresolution hash-grid encoding, forward and backward (sm_100a).
+//
+// Semantics follow the reference's torch branch, field_components/encodings.py:401-461: every level is
+// hashed, T rows per level, corners are ceil/floor of x*scale, the interpolation weight sits on the CEIL
+// corner.  This file is compiled with -fmad=false: every product/sum below is individually rounded exactly
+// like the reference's chain of separate torch ops, which makes corner indices AND interpolated features
+// bit-identical to the reference for identical inputs.
+//
+// Mapping: one thread per point, 128 points per CTA, levels looped inside the thread (unrolled by two so
+// sixteen independent 8-byte gathers are in flight per thread).  The [128 x L*F] output tile is staged in
+// shared memory (rows rotated to dodge bank conflicts) and leaves the SM as one contiguous, fully
+// coalesced 128*L*F*4-byte run.  Tables live in L2 (64 MB fp32 / 32 MB fp16 at T=2^19 vs 126 MB of L2).
+//
+// Backward: the same index math, then one vectorised RED (red.global.add.v2.f32) per corner.  On coarse
+// levels, where the consecutive samples of a ray sit in the same cell, lanes holding the same cell form
+// contiguous runs; a segmented shuffle reduction folds each run into its head lane so that one RED per
+// corner per run is issued instead of one per lane (warp-aggregated atomics).
+#include "tn_common.cuh"
+
+namespace tn {
+
+struct LevelScales {
+  float s[TN_MAX_LEVELS];
+};
+
+constexpr uint32_t kPrimeY = 2654435761u;  // encodings.py:413
+constexpr uint32_t kPrimeZ = 805459861u;
+constexpr int kPts = 128;                  // points per CTA
+
+template <int F, bool HALF>
+__device__ __forceinline__ void load_row(const void* __restrict__ table, uint32_t row, float (&f)[F]) {
+  if constexpr (!HALF) {
+    const float* t = reinterpret_cast<const float*>(table) + (size_t)row * F;
+    if constexpr (F == 1) {
+      f[0] = __ldg(t);
+    } else if constexpr (F == 2) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(t));
+      f[0] = v.x; f[1] = v.y;
+    } else {
+#pragma unroll
+      for (int i = 0; i < F; i += 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(t + i));
+        f[i] = v.x; f[i + 1] = v.y; f[i + 2] = v.z; f[i + 3] = v.w;
+      }
+    }
+  } else {
+    const __half* t = reinterpret_cast<const __half*>(table) + (size_t)row * F;
+    if constexpr (F == 1) {
+      f[0] = __half2float(__ldg(t));
+    } else {
+#pragma unroll
+      for (int i = 0; i < F; i += 2) {
+        float2 v = __half22float2(__ldg(reinterpret_cast<const __half2*>(t + i)));
+        f[i] = v.x; f[i + 1] = v.y;
+      }
+    }
+  }
+}
+
+// Corner rows in the reference order hashed_0..hashed_7 (encodings.py:431-438) and the three offsets.
+struct Cell {
+  uint32_t idx[8];
+  float ox, oy, oz;
+  uint64_t key;  // identifies (floor, ceil) triple: equal keys <=> identical eight rows
+};
+
+__device__ __forceinline__ Cell locate(float x0, float x1, float x2, float scale, uint32_t mask, uint32_t base) {
+  Cell c;
+  const float s0 = x0 * scale, s1 = x1 * scale, s2 = x2 * scale;  // encodings.py:425
+  const int lo0 = (int)floorf(s0), lo1 = (int)floorf(s1), lo2 = (int)floorf(s2);  // :427
+  const int hi0 = (int)ceilf(s0), hi1 = (int)ceilf(s1), hi2 = (int)ceilf(s2);     // :426
+  c.ox = s0 - (float)lo0;  // :429
+  c.oy = s1 - (float)lo1;
+  c.oz = s2 - (float)lo2;
+  // int32 * int64 primes, xor, mod 2^k (:413-417)  ==  uint32 wrap-around arithmetic, masked
+  const uint32_t xc = (uint32_t)hi0, xf = (uint32_t)lo0;
+  const uint32_t yc = (uint32_t)hi1 * kPrimeY, yf = (uint32_t)lo1 * kPrimeY;
+  const uint32_t zc = (uint32_t)hi2 * kPrimeZ, zf = (uint32_t)lo2 * kPrimeZ;
+  c.idx[0] = ((xc ^ yc ^ zc) & mask) + base;
+  c.idx[1] = ((xc ^ yf ^ zc) & mask) + base;
+  c.idx[2] = ((xf ^ yf ^ zc) & mask) + base;
+  c.idx[3] = ((xf ^ yc ^ zc) & mask) + base;
+  c.idx[4] = ((xc ^ yc ^ zf) & mask) + base;
+  c.idx[5] = ((xc ^ yf ^ zf) & mask) + base;
+  c.idx[6] = ((xf ^ yf ^ zf) & mask) + base;
+  c.idx[7] = ((xf ^ yc ^ zf) & mask) + base;
+  c.key = (uint64_t)(uint32_t)(lo0 & 0xFFFFF) | ((uint64_t)(uint32_t)(lo1 & 0xFFFFF) << 20) |
+          ((uint64_t)(uint32_t)(lo2 & 0xFFFFF) << 40) | ((uint64_t)(hi0 != lo0) << 60) |
+          ((uint64_t)(hi1 != lo1) << 61) | ((uint64_t)(hi2 != lo2) << 62);
+  return c;
+}
+
+// position of (row, level) inside the rotated tile
+__device__ __forceinline__ int tile_pos(int row, int l, int L, int F) {
+  int r = l + row % L;
+  if (r >= L) r -= L;
+  return (row * L + r) * F;
+}
+
+template <int F, bool HALF, bool WRITE_IDX>
+__global__ void __launch_bounds__(kPts) hash_fwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
+                                                        LevelScales sc, int64_t N, int L, int log2T,
+                                                        float* __restrict__ out, int32_t* __restrict__ idx_out) {
+  extern __shared__ float4 smem4[];
+  float* tile = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x;
+  const int64_t base_pt = (int64_t)blockIdx.x * kPts;
+  const int64_t p = base_pt + tid;
+  const bool valid = p < N;
+  const uint32_t T = 1u << log2T, mask = T - 1u;
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+  if (valid) {
+    x0 = __ldg(x + 3 * p); x1 = __ldg(x + 3 * p + 1); x2 = __ldg(x + 3 * p + 2);
+  }
+  const int rowmod = tid % L;
+#pragma unroll 2
+  for (int l = 0; l < L; ++l) {
+    const Cell c = locate(x0, x1, x2, sc.s[l], mask, (uint32_t)l * T);
+    float f[8][F];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
+    if constexpr (WRITE_IDX) {
+      if (valid) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) idx_out[(p * L + l) * 8 + k] = (int32_t)c.idx[k];
+      }
+    }
+    const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+    int r = l + rowmod;
+    if (r >= L) r -= L;
+    float* dst = tile + (tid * L + r) * F;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      // encodings.py:449-459, same association
+      const float f03 = f[0][j] * c.ox + f[3][j] * mx;
+      const float f12 = f[1][j] * c.ox + f[2][j] * mx;
+      const float f56 = f[5][j] * c.ox + f[6][j] * mx;
+      const float f47 = f[4][j] * c.ox + f[7][j] * mx;
+      const float f0312 = f03 * c.oy + f12 * my;
+      const float f4756 = f47 * c.oy + f56 * my;
+      dst[j] = f0312 * c.oz + f4756 * mz;
+    }
+  }
+  __syncthreads();
+  // contiguous, coalesced write-out of the tile (rows base_pt .. base_pt+rows-1 are adjacent in `out`)
+  const int rows = (int)min((int64_t)kPts, N - base_pt);
+  float* gout = out + base_pt * (int64_t)(L * F);
+  for (int i = tid; i < rows * L; i += kPts) {
+    const int row = i / L, l = i - row * L;
+    const float* src = tile + tile_pos(row, l, L, F);
+    if constexpr (F == 2) {
+      *reinterpret_cast<float2*>(gout + (size_t)i * 2) = *reinterpret_cast<const float2*>(src);
+    } else if constexpr (F == 4 || F == 8) {
+#pragma unroll
+      for (int j = 0; j < F; j += 4)
+        *reinterpret_cast<float4*>(gout + (size_t)i * F + j) = *reinterpret_cast<const float4*>(src + j);
+    } else {
+      gout[i] = src[0];
+    }
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void red_row(float* __restrict__ dtable, uint32_t row, const float (&g)[F]) {
+  float* a = dtable + (size_t)row * F;
+  if constexpr (F == 1) {
+    atomicAdd(a, g[0]);
+  } else if constexpr (F == 2) {
+    red_add_v2(a, g[0], g[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < F; i += 4) red_add_v4(a + i, g[i], g[i + 1], g[i + 2], g[i + 3]);
+  }
+}
+
+template <int F, bool HALF, bool NEED_DX>
+__global__ void __launch_bounds__(kPts) hash_bwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
+                                                        LevelScales sc, const float* __restrict__ dy, int64_t N, int L,
+                                                        int log2T, int n_coarse, float* __restrict__ dtable,
+                                                        float* __restrict__ dx) {
+  extern __shared__ float4 smem4[];
+  float* tile = reinterpret_cast<float*>(smem4);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t base_pt = (int64_t)blockIdx.x * kPts;
+  const int64_t p = base_pt + tid;
+  const bool valid = p < N;
+  const uint32_t T = 1u << log2T, mask = T - 1u;
+  // coalesced load of the dy tile into the rotated layout
+  const int rows = (int)min((int64_t)kPts, N - base_pt);
+  const float* gdy = dy + base_pt * (int64_t)(L * F);
+  for (int i = tid; i < rows * L; i += kPts) {
+    const int row = i / L, l = i - row * L;
+    float* dst = tile + tile_pos(row, l, L, F);
+    if constexpr (F == 2) {
+      *reinterpret_cast<float2*>(dst) = __ldg(reinterpret_cast<const float2*>(gdy + (size_t)i * 2));
+    } else if constexpr (F == 4 || F == 8) {
+#pragma unroll
+      for (int j = 0; j < F; j += 4)
+        *reinterpret_cast<float4*>(dst + j) = __ldg(reinterpret_cast<const float4*>(gdy + (size_t)i * F + j));
+    } else {
+      dst[0] = __ldg(gdy + i);
+    }
+  }
+  float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+  if (valid) {
+    x0 = __ldg(x + 3 * p); x1 = __ldg(x + 3 * p + 1); x2 = __ldg(x + 3 * p + 2);
+  }
+  __syncthreads();
+  const int rowmod = tid % L;
+  float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+#pragma unroll 1
+  for (int l = 0; l < L; ++l) {
+    const float scale = sc.s[l];
+    const Cell c = locate(x0, x1, x2, scale, mask, (uint32_t)l * T);
+    int r = l + rowmod;
+    if (r >= L) r -= L;
+    float g[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) g[j] = valid ? tile[(tid * L + r) * F + j] : 0.f;
+    const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
+    float gc[8][F];
+    float f[8][F];
+    if constexpr (NEED_DX) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
+    }
+    float dox = 0.f, doy = 0.f, doz = 0.f;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      const float g0312 = g[j] * c.oz, g4756 = g[j] * mz;
+      const float g03 = g0312 * c.oy, g12 = g0312 * my;
+      const float g47 = g4756 * c.oy, g56 = g4756 * my;
+      gc[0][j] = g03 * c.ox; gc[3][j] = g03 * mx;
+      gc[1][j] = g12 * c.ox; gc[2][j] = g12 * mx;
+      gc[5][j] = g56 * c.ox; gc[6][j] = g56 * mx;
+      gc[4][j] = g47 * c.ox; gc[7][j] = g47 * mx;
+      if constexpr (NEED_DX) {
+        const float f03 = f[0][j] * c.ox + f[3][j] * mx;
+        const float f12 = f[1][j] * c.ox + f[2][j] * mx;
+        const float f56 = f[5][j] * c.ox + f[6][j] * mx;
+        const float f47 = f[4][j] * c.ox + f[7][j] * mx;
+        const float f0312 = f03 * c.oy + f12 * my;
+        const float f4756 = f47 * c.oy + f56 * my;
+        dox += g03 * (f[0][j] - f[3][j]) + g12 * (f[1][j] - f[2][j]) + g56 * (f[5][j] - f[6][j]) +
+               g47 * (f[4][j] - f[7][j]);
+        doy += g0312 * (f03 - f12) + g4756 * (f47 - f56);
+        doz += g[j] * (f0312 - f4756);
+      }
+    }
+    if constexpr (NEED_DX) {
+      dx0 += dox * scale; dx1 += doy * scale; dx2 += doz * scale;
+    }
+    bool issue = valid;
+    if (l < n_coarse) {  // warp-uniform branch: segmented reduction over runs of equal cells
+      const uint64_t key = valid ? c.key : ~0ull;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t okey = __shfl_down_sync(0xffffffffu, key, d);
+        const bool take = (lane + d < 32) && (okey == key);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int j = 0; j < F; ++j) {
+            const float o = __shfl_down_sync(0xffffffffu, gc[k][j], d);
+            if (take) gc[k][j] += o;
+          }
+      }
+      const uint64_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
+      issue = valid && (lane == 0 || pkey != key);
+    }
+    if (issue) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red_row<F>(dtable, c.idx[k], gc[k]);
+    }
+  }
+  if constexpr (NEED_DX) {
+    if (valid) {
+      dx[3 * p] = dx0; dx[3 * p + 1] = dx1; dx[3 * p + 2] = dx2;
+    }
+  }
+}
+
+static int check_common(const float* x, const void* table, const float* scales_host, int64_t N, int L, int F,
+                        int log2_T, int table_dtype) {
+  TN_REQUIRE(x && table && scales_host, TN_EINVAL, "hash_encode: null pointer");
+  TN_REQUIRE(N >= 0 && N < (int64_t(1) << 40), TN_EINVAL, "hash_encode: bad N=%lld", (long long)N);
+  TN_REQUIRE(L >= 1 && L <= TN_MAX_LEVELS, TN_EINVAL, "hash_encode: L=%d out of range [1,%d]", L, TN_MAX_LEVELS);
+  TN_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, TN_EINVAL, "hash_encode: F=%d not in {1,2,4,8}", F);
+  TN_REQUIRE(log2_T >= 1 && log2_T <= 26 && ((int64_t)L << log2_T) < (int64_t(1) << 32), TN_EINVAL,
+             "hash_encode: log2_T=%d unsupported", log2_T);
+  TN_REQUIRE(table_dtype == 0 || table_dtype == 1, TN_EINVAL, "hash_encode: table_dtype=%d", table_dtype);
+  TN_REQUIRE(aligned(table, 16) && aligned(x, 4), TN_EALIGN, "hash_encode: table must be 16-byte aligned");
+  return TN_OK;
+}
+
+template <int F>
+static int launch_fwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, int64_t N, int L,
+                      int log2_T, float* out, int32_t* idx_out, cudaStream_t st) {
+  const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
+  const size_t smem = (size_t)kPts * L * F * sizeof(float);
+#define TN_FWD(H, W)                                                                                         \
+  do {                                                                                                       \
+    auto k = hash_fwd_kernel<F, H, W>;                                                                       \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, idx_out);                                    \
+  } while (0)
+  if (table_dtype == 0) {
+    if (idx_out) TN_FWD(false, true); else TN_FWD(false, false);
+  } else {
+    if (idx_out) TN_FWD(true, true); else TN_FWD(true, false);
+  }
+#undef TN_FWD
+  return check_launch("hash_fwd_kernel");
+}
+
+template <int F>
+static int launch_bwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, const float* dy,
+                      int64_t N, int L, int log2_T, int n_coarse, float* dtable, float* dx, cudaStream_t st) {
+  const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
+  const size_t smem = (size_t)kPts * L * F * sizeof(float);
+#define TN_BWD(H, D)                                                                                         \
+  do {                                                                                                       \
+    auto k = hash_bwd_kernel<F, H, D>;                                                                       \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx);                        \
+  } while (0)
+  if (table_dtype == 0) {
+    if (dx) TN_BWD(false, true); else TN_BWD(false, false);
+  } else {
+    if (dx) TN_BWD(true, true); else TN_BWD(true, false);
+  }
+#undef TN_BWD
+  return check_launch("hash_bwd_kernel");
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+extern "C" int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
+                                  int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, void* stream) {
+  int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
+  if (rc) return rc;
+  TN_REQUIRE(out, TN_EINVAL, "hash_encode_fwd: out is null");
+  TN_REQUIRE(aligned(out, 16), TN_EALIGN, "hash_encode_fwd: out must be 16-byte aligned");
+  TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_fwd: L*F=%d too large", L * F);
+  if (N == 0) return TN_OK;
+  LevelScales sc;
+  for (int l = 0; l < TN_MAX_LEVELS; ++l) sc.s[l] = l < L ? scales_host[l] : 0.f;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (F) {
+    case 1: return launch_fwd<1>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
+    case 2: return launch_fwd<2>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
+    case 4: return launch_fwd<4>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
+    default: return launch_fwd<8>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
+  }
+}
+
+extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
+                                  const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
+                                  void* stream) {
+  int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
+  if (rc) return rc;
+  TN_REQUIRE(dy && dtable, TN_EINVAL, "hash_encode_bwd: null pointer");
+  TN_REQUIRE(aligned(dy, 16) && aligned(dtable, 16), TN_EALIGN, "hash_encode_bwd: dy/dtable must be 16-byte aligned");
+  TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_bwd: L*F=%d too large", L * F);
+  if (N == 0) return TN_OK;
+  LevelScales sc;
+  int n_coarse = 0;
+  for (int l = 0; l < TN_MAX_LEVELS; ++l) {
+    sc.s[l] = l < L ? scales_host[l] : 0.f;
+    // cells of coarse levels hold long runs of consecutive samples: aggregate there
+    if (l < L && l == n_coarse && scales_host[l] <= 96.f) ++n_coarse;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (F) {
+    case 1: return launch_bwd<1>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
+    case 2: return launch_bwd<2>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
+    case 4: return launch_bwd<4>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
+    default: return launch_bwd<8>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
+  }
+}

@@ -1,0 +1,228 @@
+"""Fields: density + outputs, with the reference's class names, signatures and state_dict keys.
+
+Mirrors `nerfstudio/fields/{base_field,nerfacto_field,thermal_nerfacto_field,density_fields}.py`.
+"""
+from enum import Enum
+from typing import Dict, Literal, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import ops
+from .field_components import (
+    MLP,
+    Embedding,
+    HashEncoding,
+    MLPWithHashEncoding,
+    SceneContraction,
+    SHEncoding,
+    SpatialDistortion,
+    trunc_exp,
+)
+from .rays import Frustums, RaySamples
+
+
+class FieldHeadNames(Enum):
+    """field_components/field_heads.py (names the path uses)."""
+
+    RGB = "rgb"
+    DENSITY = "density"
+    NORMALS = "normals"
+    PRED_NORMALS = "pred_normals"
+
+
+def get_normalized_directions(directions: Tensor) -> Tensor:
+    """fields/base_field.py:136-142."""
+    return (directions + 1.0) / 2.0
+
+
+def _is_linf_contraction(sd: Optional[SpatialDistortion]) -> bool:
+    return isinstance(sd, SceneContraction) and sd.order == float("inf")
+
+
+class Field(nn.Module):
+    """fields/base_field.py:40-133."""
+
+    def __init__(self) -> None:
+        super().__init__()
+        self._sample_locations = None
+        self._density_before_activation = None
+
+    def _grid_coordinates(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
+        """(x [N,3] in [0,1] zeroed outside the box, selector [N]) for the samples; the steps of
+        fields/nerfacto_field.py:207-215 == fields/density_fields.py:96-103."""
+        lay = ray_samples._layout
+        if _is_linf_contraction(self.spatial_distortion):
+            if lay is not None:
+                return ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+            return ops.contract_points(ray_samples.frustums.get_positions().reshape(-1, 3))
+        positions = ray_samples.frustums.get_positions()
+        if self.spatial_distortion is not None:
+            positions = (self.spatial_distortion(positions) + 2.0) / 4.0
+        else:  # SceneBox.get_normalized_positions, data/scene_box.py
+            positions = (positions - self.aabb[0]) / (self.aabb[1] - self.aabb[0])
+        selector = ((positions > 0.0) & (positions < 1.0)).all(dim=-1)
+        positions = positions * selector[..., None]
+        return positions.reshape(-1, 3), selector.reshape(-1).to(positions.dtype)
+
+    def density_fn(self, positions: Tensor, times: Optional[Tensor] = None) -> Tensor:
+        """fields/base_field.py:48-69."""
+        del times
+        ray_samples = RaySamples(
+            frustums=Frustums(origins=positions, directions=torch.ones_like(positions),
+                              starts=torch.zeros_like(positions[..., :1]), ends=torch.zeros_like(positions[..., :1]),
+                              pixel_area=torch.ones_like(positions[..., :1])))
+        density, _ = self.get_density(ray_samples)
+        return density
+
+    def get_density(self, ray_samples: RaySamples):
+        raise NotImplementedError
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None):
+        raise NotImplementedError
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
+        """fields/base_field.py:114-133."""
+        if compute_normals:
+            raise NotImplementedError("analytic normals (predict_normals) are outside the thermal-nerfacto hot path")
+        density, density_embedding = self.get_density(ray_samples)
+        field_outputs = self.get_outputs(ray_samples, density_embedding=density_embedding)
+        field_outputs[FieldHeadNames.DENSITY] = density
+        return field_outputs
+
+
+class NerfactoField(Field):
+    """fields/nerfacto_field.py:47-348 (the north star's `TCNNNerfactoField` is this class's legacy name).
+
+    Unsupported reference options raise at construction: transient embedding, semantics, predicted normals.
+    """
+
+    aabb: Tensor
+
+    def __init__(self, aabb: Tensor, num_images: int, num_layers: int = 2, hidden_dim: int = 64, geo_feat_dim: int = 15,
+                 num_levels: int = 16, base_res: int = 16, max_res: int = 2048, log2_hashmap_size: int = 19,
+                 num_layers_color: int = 3, num_layers_transient: int = 2, features_per_level: int = 2,
+                 hidden_dim_color: int = 64, hidden_dim_transient: int = 64, appearance_embedding_dim: int = 32,
+                 transient_embedding_dim: int = 16, use_transient_embedding: bool = False, use_semantics: bool = False,
+                 num_semantic_classes: int = 100, pass_semantic_gradients: bool = False, use_pred_normals: bool = False,
+                 use_average_appearance_embedding: bool = False,
+                 spatial_distortion: Optional[SpatialDistortion] = None, average_init_density: float = 1.0,
+                 implementation: Literal["tcnn", "torch", "b200"] = "b200", num_channels: int = 3) -> None:
+        super().__init__()
+        if use_transient_embedding or use_semantics or use_pred_normals:
+            raise NotImplementedError("transient/semantic/pred-normal heads are not part of thermal-nerfacto")
+        self.register_buffer("aabb", aabb)
+        self.geo_feat_dim = geo_feat_dim
+        self.register_buffer("max_res", torch.tensor(max_res))
+        self.register_buffer("num_levels", torch.tensor(num_levels))
+        self.register_buffer("log2_hashmap_size", torch.tensor(log2_hashmap_size))
+        self.spatial_distortion = spatial_distortion
+        self.num_images = num_images
+        self.appearance_embedding_dim = appearance_embedding_dim
+        self.embedding_appearance = Embedding(num_images, appearance_embedding_dim) if appearance_embedding_dim > 0 \
+            else None
+        self.use_average_appearance_embedding = use_average_appearance_embedding
+        self.use_transient_embedding = self.use_semantics = self.use_pred_normals = False
+        self.base_res = base_res
+        self.average_init_density = average_init_density
+        self.step = 0
+        self.direction_encoding = SHEncoding(levels=4, implementation=implementation)
+        self.mlp_base = MLPWithHashEncoding(
+            num_levels=num_levels, min_res=base_res, max_res=max_res, log2_hashmap_size=log2_hashmap_size,
+            features_per_level=features_per_level, num_layers=num_layers, layer_width=hidden_dim,
+            out_dim=1 + geo_feat_dim, activation=nn.ReLU(), out_activation=None, implementation=implementation)
+        self.mlp_head = MLP(
+            in_dim=self.direction_encoding.get_out_dim() + geo_feat_dim + appearance_embedding_dim,
+            num_layers=num_layers_color, layer_width=hidden_dim_color, out_dim=num_channels, activation=nn.ReLU(),
+            out_activation=nn.Sigmoid(), implementation=implementation)
+
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
+        """fields/nerfacto_field.py:205-229."""
+        x, selector = self._grid_coordinates(ray_samples)
+        shape = ray_samples.frustums.shape
+        self._sample_locations = x.view(*shape, 3)
+        h = self.mlp_base(x).view(*shape, -1)
+        density_before_activation, base_mlp_out = torch.split(h, [1, self.geo_feat_dim], dim=-1)
+        self._density_before_activation = density_before_activation
+        density = self.average_init_density * trunc_exp(density_before_activation)
+        density = density * selector.view(*shape, 1)
+        return density, base_mlp_out
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None):
+        """fields/nerfacto_field.py:272-348."""
+        assert density_embedding is not None
+        if ray_samples.camera_indices is None:
+            raise AttributeError("Camera indices are not provided.")
+        shape = ray_samples.frustums.directions.shape[:-1]
+        lay = ray_samples._layout
+        if lay is not None:  # SH once per ray, broadcast over the samples
+            d = self.direction_encoding(get_normalized_directions(lay.directions))
+            d = d[:, None, :].expand(*shape, d.shape[-1])
+        else:
+            d = self.direction_encoding(get_normalized_directions(ray_samples.frustums.directions).reshape(-1, 3))
+            d = d.view(*shape, -1)
+        parts = [d.reshape(-1, d.shape[-1]), density_embedding.reshape(-1, self.geo_feat_dim)]
+        if self.embedding_appearance is not None:
+            if self.training:
+                emb = self.embedding_appearance(ray_samples.camera_indices.squeeze(-1))
+            elif self.use_average_appearance_embedding:
+                emb = torch.ones((*shape, self.appearance_embedding_dim), device=d.device) \
+                    * self.embedding_appearance.mean(dim=0)
+            else:
+                emb = torch.zeros((*shape, self.appearance_embedding_dim), device=d.device)
+            parts.append(emb.reshape(-1, self.appearance_embedding_dim))
+        h = torch.cat(parts, dim=-1)
+        rgb = self.mlp_head(h).view(*shape, -1)
+        return {FieldHeadNames.RGB: rgb}
+
+
+class ThermalNerfactoField(NerfactoField):
+    """fields/thermal_nerfacto_field.py:10-99: NerfactoField whose colour head has `num_channels` outputs
+    (3 RGB, 4 RGBT shared, 1 thermal)."""
+
+    def __init__(self, aabb: Tensor, num_images: int, num_channels: int = 4, **kwargs) -> None:
+        super().__init__(aabb, num_images, num_channels=num_channels, **kwargs)
+
+
+class HashMLPDensityField(Field):
+    """fields/density_fields.py:34-121.  `encoding.hash_table` and `mlp_base.0.hash_table` are the same
+    Parameter under two state_dict keys, as in the reference."""
+
+    aabb: Tensor
+
+    def __init__(self, aabb: Tensor, num_layers: int = 2, hidden_dim: int = 64,
+                 spatial_distortion: Optional[SpatialDistortion] = None, use_linear: bool = False, num_levels: int = 8,
+                 max_res: int = 1024, base_res: int = 16, log2_hashmap_size: int = 18, features_per_level: int = 2,
+                 average_init_density: float = 1.0, implementation: Literal["tcnn", "torch", "b200"] = "b200") -> None:
+        super().__init__()
+        self.register_buffer("aabb", aabb)
+        self.spatial_distortion = spatial_distortion
+        self.use_linear = use_linear
+        self.average_init_density = average_init_density
+        self.register_buffer("max_res", torch.tensor(max_res))
+        self.register_buffer("num_levels", torch.tensor(num_levels))
+        self.register_buffer("log2_hashmap_size", torch.tensor(log2_hashmap_size))
+        self.encoding = HashEncoding(num_levels=num_levels, min_res=base_res, max_res=max_res,
+                                     log2_hashmap_size=log2_hashmap_size, features_per_level=features_per_level,
+                                     implementation=implementation)
+        if not self.use_linear:
+            network = MLP(in_dim=self.encoding.get_out_dim(), num_layers=num_layers, layer_width=hidden_dim, out_dim=1,
+                          activation=nn.ReLU(), out_activation=None, implementation=implementation)
+            self.mlp_base = torch.nn.Sequential(self.encoding, network)
+        else:
+            self.linear = torch.nn.Linear(self.encoding.get_out_dim(), 1)
+
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+        """fields/density_fields.py:95-118."""
+        x, selector = self._grid_coordinates(ray_samples)
+        shape = ray_samples.frustums.shape
+        if not self.use_linear:
+            raw = self.mlp_base(x).view(*shape, -1)
+        else:
+            raw = self.linear(self.encoding(x)).view(*shape, -1)
+        density = self.average_init_density * trunc_exp(raw)
+        density = density * selector.view(*shape, 1)
+        return density, None
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:
+        return {}

@@ -1,0 +1,100 @@
+"""Per-ray losses of thermal-nerfacto (the row after the hot path).
+
+Mirrors `nerfstudio/model_components/losses.py:57-158` (interlevel / distortion) and `:593-651`
+(tv_pixel / cross_channel).  Round 1: torch expressions over the kernel outputs (same formulas as the
+reference, so loss values and gradients agree); fusing them into the compositing kernel is the next step.
+"""
+import torch
+from torch import Tensor
+
+EPS = 1.0e-7  # losses.py:39
+
+L1Loss = torch.nn.L1Loss
+MSELoss = torch.nn.MSELoss
+
+
+def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
+    """losses.py:57-84."""
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
+    return cy1_hi - cy1_lo
+
+
+def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    """losses.py:87-103."""
+    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + EPS)
+
+
+def ray_samples_to_sdist(ray_samples) -> Tensor:
+    """losses.py:106-111."""
+    if getattr(ray_samples, "_layout", None) is not None:
+        return ray_samples._layout.sbins
+    starts, ends = ray_samples.spacing_starts, ray_samples.spacing_ends
+    return torch.cat([starts[..., 0], ends[..., -1:, 0]], dim=-1)
+
+
+def interlevel_loss(weights_list, ray_samples_list) -> Tensor:
+    """losses.py:114-135."""
+    c = ray_samples_to_sdist(ray_samples_list[-1]).detach()
+    w = weights_list[-1][..., 0].detach()
+    assert len(ray_samples_list) > 0
+    loss_interlevel = 0.0
+    for ray_samples, weights in zip(ray_samples_list[:-1], weights_list[:-1]):
+        cp = ray_samples_to_sdist(ray_samples)
+        wp = weights[..., 0]
+        loss_interlevel += torch.mean(lossfun_outer(c, w, cp, wp))
+    assert isinstance(loss_interlevel, Tensor)
+    return loss_interlevel
+
+
+def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
+    """losses.py:139-150."""
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return loss_inter + loss_intra
+
+
+def distortion_loss(weights_list, ray_samples_list) -> Tensor:
+    """losses.py:153-158."""
+    c = ray_samples_to_sdist(ray_samples_list[-1])
+    w = weights_list[-1][..., 0]
+    return torch.mean(lossfun_distortion(c, w))
+
+
+def _rgb_patch_mask(is_thermal: Tensor) -> Tensor:
+    """[R/4] float mask of the 2x2 patches that belong to RGB cameras.  The reference selects the RGB rays
+    with a boolean index (a device->host sync) and views them as patches; with the patch-ordered batches
+    its pixel sampler produces (data/pixel_samplers.py:389-438) a per-patch mask gives the same mean."""
+    return (1 - is_thermal).view(-1, 4)[:, 0]
+
+
+def _masked_mean(values: Tensor, mask: Tensor) -> Tensor:
+    return (values * mask).sum() / mask.sum()
+
+
+def tv_pixel_loss(pred_thermal: Tensor, is_thermal: Tensor) -> Tensor:
+    """losses.py:603-620: total variation of the rendered thermal channel inside each 2x2 RGB-camera patch."""
+    q = pred_thermal.reshape(-1, 4)
+    tv = (q[:, 0] - q[:, 1]).abs() + (q[:, 0] - q[:, 2]).abs() + (q[:, 1] - q[:, 3]).abs() + (q[:, 2] - q[:, 3]).abs()
+    return 0.25 * _masked_mean(tv, _rgb_patch_mask(is_thermal))
+
+
+def pixel_grad(img: Tensor, patch_size: int = 2) -> Tensor:
+    """losses.py:623-634: the four finite differences of a 2x2 patch, stacked [4, num_patches]."""
+    assert patch_size == 2
+    q = img.reshape(-1, 4)
+    return torch.stack((q[:, 1] - q[:, 0], q[:, 2] - q[:, 0], q[:, 3] - q[:, 1], q[:, 3] - q[:, 2]))
+
+
+def cross_channel_loss(pred_thermal: Tensor, gt_rgb: Tensor, is_thermal: Tensor) -> Tensor:
+    """losses.py:637-651: L1 between patch gradients of rendered thermal and of grey-scale ground truth."""
+    diff = (pixel_grad(pred_thermal) - pixel_grad(gt_rgb.mean(-1, keepdim=True))).abs().sum(0)
+    return 0.25 * _masked_mean(diff, _rgb_patch_mask(is_thermal))

@@ -1,0 +1,498 @@
+"""ThermalNerfactoModel: the caller of the hot path, with the reference's structure, output keys,
+loss terms, parameter groups and state_dict keys.
+
+Mirrors `nerfstudio/models/thermal_nerfacto.py:32-489`, `nerfstudio/models/nerfacto.py:52-353`,
+`nerfstudio/models/base_model.py:132-206`, `nerfstudio/model_components/scene_colliders.py:169-191` and
+`nerfstudio/cameras/camera_optimizers.py:89-213` (SO3xR3 mode).  Data managers, trainers, viewers and
+metrics (PSNR/SSIM/LPIPS) are the reference's host code and are out of scope.
+"""
+from collections import defaultdict
+from dataclasses import dataclass, field
+from typing import Dict, List, Literal, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+from torch.nn import Parameter
+
+from .field_components import SceneContraction
+from .fields import FieldHeadNames, HashMLPDensityField, ThermalNerfactoField
+from .losses import L1Loss, MSELoss, cross_channel_loss, distortion_loss, interlevel_loss, tv_pixel_loss
+from .rays import RayBundle, RaySamples
+from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, RGBTRenderer
+from .samplers import ProposalNetworkSampler, UniformSampler
+
+
+# ------------------------------------------------------------------------------------------ camera optimizer
+@dataclass
+class CameraOptimizerConfig:
+    """cameras/camera_optimizers.py:39-84 (fields the model reads)."""
+
+    mode: Literal["off", "SO3xR3", "shared_SO3xR3"] = "off"
+    trans_l2_penalty: float = 1e-2
+    rot_l2_penalty: float = 1e-3
+    penalty_scale: float = 1
+
+
+def exp_map_SO3xR3(tangent_vector: Tensor) -> Tensor:
+    """[B,6] (translation, so(3) log-rotation) -> [B,3,4] = [R|t].  cameras/lie_groups.py:24-59 (Rodrigues)."""
+    t, w = tangent_vector[:, :3], tangent_vector[:, 3:]
+    theta = torch.clamp((w * w).sum(1), 1e-4).sqrt()
+    inv = 1.0 / theta
+    a = inv * theta.sin()
+    b = inv * inv * (1.0 - theta.cos())
+    zero = torch.zeros_like(w[:, 0])
+    k = torch.stack([zero, -w[:, 2], w[:, 1], w[:, 2], zero, -w[:, 0], -w[:, 1], w[:, 0], zero], dim=1).view(-1, 3, 3)
+    rot = a[:, None, None] * k + b[:, None, None] * torch.bmm(k, k) + torch.eye(3, dtype=w.dtype, device=w.device)[None]
+    return torch.cat([rot, t[:, :, None]], dim=2)
+
+
+class CameraOptimizer(nn.Module):
+    """cameras/camera_optimizers.py:89-213."""
+
+    def __init__(self, config: CameraOptimizerConfig, num_cameras: int, device="cpu",
+                 non_trainable_camera_indices: Optional[Tensor] = None, suffix: str = "") -> None:
+        super().__init__()
+        self.config = CameraOptimizerConfig(**vars(config))
+        self.num_cameras = num_cameras
+        if self.config.penalty_scale < 0:
+            self.config.mode = "off"
+        if self.config.mode == "SO3xR3":
+            self.pose_adjustment = Parameter(torch.zeros((num_cameras, 6), device=device))
+        elif self.config.mode == "shared_SO3xR3":
+            self.pose_adjustment = Parameter(torch.zeros((1, 6), device=device))
+        elif self.config.mode != "off":
+            raise NotImplementedError(f"camera optimizer mode {self.config.mode}")
+        self.suffix = suffix
+        frozen = torch.zeros(num_cameras, dtype=torch.bool)
+        if non_trainable_camera_indices is not None and len(non_trainable_camera_indices) > 0:
+            frozen[non_trainable_camera_indices.long()] = True
+        self.has_frozen = non_trainable_camera_indices is not None
+        self.register_buffer("_frozen", frozen, persistent=False)
+
+    def forward(self, indices: Tensor) -> Tensor:
+        if self.config.mode == "off":
+            return torch.eye(4, device=indices.device)[None, :3, :4].tile(indices.shape[0], 1, 1)
+        if self.config.mode == "SO3xR3":
+            out = exp_map_SO3xR3(self.pose_adjustment[indices, :])
+        else:
+            out = exp_map_SO3xR3(self.pose_adjustment).tile((indices.shape[0], 1, 1))
+        if self.has_frozen:  # non-trainable cameras get the identity (camera_optimizers.py:155-164)
+            eye = torch.eye(4, device=out.device)[:3, :4]
+            out = torch.where(self._frozen[indices][:, None, None], eye, out)
+        return out
+
+    def apply_to_raybundle(self, raybundle: RayBundle) -> None:
+        if self.config.mode != "off":
+            c = self(raybundle.camera_indices.squeeze(-1))
+            raybundle.origins = raybundle.origins + c[:, :3, 3]
+            raybundle.directions = torch.bmm(c[:, :3, :3], raybundle.directions[..., None]).squeeze(-1)
+
+    def get_loss_dict(self, loss_dict: dict) -> None:
+        if self.config.mode != "off":
+            loss_dict[f"camera_opt_regularizer{self.suffix}"] = (
+                self.pose_adjustment[:, :3].norm(dim=-1).mean() * self.config.trans_l2_penalty
+                + self.pose_adjustment[:, 3:].norm(dim=-1).mean() * self.config.rot_l2_penalty
+            ) * self.config.penalty_scale
+
+    def get_metrics_dict(self, metrics_dict: dict) -> None:
+        if self.config.mode != "off":
+            metrics_dict[f"camera_opt_translation{self.suffix}"] = self.pose_adjustment[:, :3].norm()
+            metrics_dict[f"camera_opt_rotation{self.suffix}"] = self.pose_adjustment[:, 3:].norm()
+
+    def get_param_groups(self, param_groups: dict, name: str = "camera_opt") -> None:
+        params = list(self.parameters())
+        if self.config.mode != "off":
+            assert len(params) > 0
+            param_groups[name] = params
+
+
+class NearFarCollider(nn.Module):
+    """model_components/scene_colliders.py:169-191."""
+
+    def __init__(self, near_plane: float, far_plane: float, reset_near_plane: bool = True) -> None:
+        super().__init__()
+        self.near_plane, self.far_plane, self.reset_near_plane = near_plane, far_plane, reset_near_plane
+
+    def forward(self, ray_bundle: RayBundle) -> RayBundle:
+        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
+        near_plane = self.near_plane if (self.training or not self.reset_near_plane) else 0
+        ray_bundle.nears = ones * near_plane
+        ray_bundle.fars = ones * self.far_plane
+        return ray_bundle
+
+
+# ------------------------------------------------------------------------------------------ config
+@dataclass
+class ThermalNerfactoModelConfig:
+    """models/thermal_nerfacto.py:32-64 on top of models/nerfacto.py:52-133 (same names and defaults)."""
+
+    near_plane: float = 0.05
+    far_plane: float = 1000.0
+    background_color: Literal["random", "last_sample", "black", "white"] = "last_sample"
+    hidden_dim: int = 64
+    hidden_dim_color: int = 64
+    hidden_dim_transient: int = 64
+    num_levels: int = 16
+    base_res: int = 16
+    max_res: int = 2048
+    log2_hashmap_size: int = 19
+    features_per_level: int = 2
+    num_proposal_samples_per_ray: Tuple[int, ...] = (256, 96)
+    num_nerf_samples_per_ray: int = 48
+    proposal_update_every: int = 5
+    proposal_warmup: int = 5000
+    num_proposal_iterations: int = 2
+    use_same_proposal_network: bool = False
+    proposal_net_args_list: List[Dict] = field(default_factory=lambda: [
+        {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 128, "use_linear": False},
+        {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 256, "use_linear": False},
+    ])
+    proposal_initial_sampler: Literal["piecewise", "uniform"] = "piecewise"
+    interlevel_loss_mult: float = 1.0
+    distortion_loss_mult: float = 0.002
+    use_proposal_weight_anneal: bool = True
+    use_appearance_embedding: bool = True
+    use_average_appearance_embedding: bool = True
+    proposal_weights_anneal_slope: float = 10.0
+    proposal_weights_anneal_max_num_iters: int = 1000
+    use_single_jitter: bool = True
+    predict_normals: bool = False
+    disable_scene_contraction: bool = False
+    use_gradient_scaling: bool = False
+    implementation: Literal["tcnn", "torch", "b200"] = "b200"
+    appearance_embed_dim: int = 32
+    average_init_density: float = 1.0
+    camera_optimizer: CameraOptimizerConfig = field(default_factory=lambda: CameraOptimizerConfig(mode="SO3xR3"))
+    eval_num_rays_per_chunk: int = 1 << 15  # configs/method_configs.py:270
+    # thermal
+    density_loss_mult: float = 5e-5
+    density_mode: Literal["rgb_only", "shared", "separate"] = "separate"
+    rgb_density_loss_mult: float = 0.01
+    thermal_loss_mult: float = 100.0
+    tv_rgb_loss_mult: float = 0
+    tv_thermal_loss_mult: float = 0
+    tv_pixel_loss_mult: float = 1e-6
+    cross_channel_loss_mult: float = 1e-6
+    removal_min_density_diff: float = 0.05
+    use_proposal_thermal_weight_anneal: bool = False
+    camera_optimizer_thermal: CameraOptimizerConfig = field(
+        default_factory=lambda: CameraOptimizerConfig(mode="SO3xR3", penalty_scale=10))
+    shared_camera_optimizer: CameraOptimizerConfig = field(
+        default_factory=lambda: CameraOptimizerConfig(mode="shared_SO3xR3", penalty_scale=-1))
+    shared_camera_optimizer_thermal: CameraOptimizerConfig = field(
+        default_factory=lambda: CameraOptimizerConfig(mode="shared_SO3xR3", penalty_scale=-1))
+
+    def setup(self, **kwargs) -> "ThermalNerfactoModel":
+        return ThermalNerfactoModel(self, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------ model
+class ThermalNerfactoModel(nn.Module):
+    """models/thermal_nerfacto.py:67-489 (+ the NerfactoModel / Model parts it inherits)."""
+
+    def __init__(self, config: ThermalNerfactoModelConfig, scene_box=None, num_train_data: int = 0,
+                 metadata: Optional[Dict] = None, aabb: Optional[Tensor] = None, **kwargs) -> None:
+        super().__init__()
+        if config.predict_normals or config.use_gradient_scaling or config.tv_rgb_loss_mult > 0 \
+                or config.tv_thermal_loss_mult > 0:
+            raise NotImplementedError("predict_normals / gradient scaling / density-TV are off the default path")
+        self.config = config
+        if aabb is None:
+            aabb = scene_box.aabb if scene_box is not None else torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+        self.scene_box = scene_box
+        self.num_train_data = num_train_data
+        self.kwargs = dict(metadata=metadata or {}, **kwargs)
+        self.device_indicator_param = nn.Parameter(torch.empty(0))  # models/base_model.py:85
+        self._populate(aabb)
+
+    @property
+    def device(self):
+        return self.device_indicator_param.device
+
+    def _make_field(self, aabb, contraction, num_channels):
+        c = self.config
+        return ThermalNerfactoField(
+            aabb, hidden_dim=c.hidden_dim, num_levels=c.num_levels, max_res=c.max_res, base_res=c.base_res,
+            features_per_level=c.features_per_level, log2_hashmap_size=c.log2_hashmap_size,
+            hidden_dim_color=c.hidden_dim_color, hidden_dim_transient=c.hidden_dim_transient,
+            spatial_distortion=contraction, num_images=self.num_train_data, use_pred_normals=c.predict_normals,
+            use_average_appearance_embedding=c.use_average_appearance_embedding,
+            appearance_embedding_dim=c.appearance_embed_dim if c.use_appearance_embedding else 0,
+            implementation=c.implementation, num_channels=num_channels)
+
+    def _make_proposals(self, aabb, contraction):
+        c = self.config
+        nets, fns = torch.nn.ModuleList(), []
+        if c.use_same_proposal_network:
+            assert len(c.proposal_net_args_list) == 1, "Only one proposal network is allowed."
+            net = HashMLPDensityField(aabb, spatial_distortion=contraction, **c.proposal_net_args_list[0],
+                                      average_init_density=c.average_init_density, implementation=c.implementation)
+            nets.append(net)
+            fns.extend([net.density_fn for _ in range(c.num_proposal_iterations)])
+        else:
+            for i in range(c.num_proposal_iterations):
+                args = c.proposal_net_args_list[min(i, len(c.proposal_net_args_list) - 1)]
+                nets.append(HashMLPDensityField(aabb, spatial_distortion=contraction, **args,
+                                                average_init_density=c.average_init_density,
+                                                implementation=c.implementation))
+            fns.extend([n.density_fn for n in nets])
+        return nets, fns
+
+    def _make_sampler(self):
+        c = self.config
+
+        def update_schedule(step):
+            return np.clip(np.interp(step, [0, c.proposal_warmup], [0, c.proposal_update_every]), 1,
+                           c.proposal_update_every)
+
+        initial = UniformSampler(single_jitter=c.use_single_jitter) if c.proposal_initial_sampler == "uniform" else None
+        return ProposalNetworkSampler(
+            num_nerf_samples_per_ray=c.num_nerf_samples_per_ray,
+            num_proposal_samples_per_ray=c.num_proposal_samples_per_ray,
+            num_proposal_network_iterations=c.num_proposal_iterations, single_jitter=c.use_single_jitter,
+            update_sched=update_schedule, initial_sampler=initial)
+
+    def _populate(self, aabb: Tensor) -> None:
+        """populate_modules: models/nerfacto.py:145-254 then models/thermal_nerfacto.py:79-216 (the modules
+        the thermal subclass overwrites -- field, camera_optimizer -- are built once)."""
+        c = self.config
+        contraction = None if c.disable_scene_contraction else SceneContraction(order=float("inf"))
+        is_thermal = list(self.kwargs["metadata"].get("is_thermal", [0] * self.num_train_data))
+        thermal_idx = torch.tensor([i for i, x in enumerate(is_thermal) if x != 0], dtype=torch.long)
+        rgb_idx = torch.tensor([i for i, x in enumerate(is_thermal) if x == 0], dtype=torch.long)
+        # --- NerfactoModel.populate_modules
+        self.proposal_networks, self.density_fns = self._make_proposals(aabb, contraction)
+        self.proposal_sampler = self._make_sampler()
+        self.collider = NearFarCollider(near_plane=c.near_plane, far_plane=c.far_plane)
+        self.renderer_rgb = RGBRenderer(background_color=c.background_color)
+        self.renderer_accumulation = AccumulationRenderer()
+        self.renderer_depth = DepthRenderer(method="median")
+        self.renderer_expected_depth = DepthRenderer(method="expected")
+        self.rgb_loss = MSELoss()
+        self.step = 0
+        # --- ThermalNerfactoModel.populate_modules
+        self.output_suffixes = ("", "_thermal") if c.density_mode == "separate" else ("",)
+        self.field = self._make_field(aabb, contraction, 3 + (c.density_mode == "shared"))
+        if c.density_mode == "separate":
+            self.field_thermal = self._make_field(aabb, contraction, 1)
+        self.camera_optimizer = CameraOptimizer(c.camera_optimizer, self.num_train_data,
+                                                non_trainable_camera_indices=thermal_idx)
+        self.camera_optimizer_thermal = CameraOptimizer(c.camera_optimizer_thermal, self.num_train_data,
+                                                        non_trainable_camera_indices=rgb_idx, suffix="_thermal")
+        self.shared_camera_optimizer = CameraOptimizer(c.shared_camera_optimizer, self.num_train_data,
+                                                       non_trainable_camera_indices=thermal_idx, suffix="_shared")
+        self.shared_camera_optimizer_thermal = CameraOptimizer(
+            c.shared_camera_optimizer_thermal, self.num_train_data, non_trainable_camera_indices=rgb_idx,
+            suffix="_shared_thermal")
+        self.proposal_networks_thermal, self.density_fns_thermal = self._make_proposals(aabb, contraction)
+        self.proposal_sampler_thermal = self._make_sampler()
+        self.renderer_rgbt = RGBTRenderer(background_color=c.background_color)
+        self.renderer_thermal = RGBRenderer(background_color=c.background_color, num_channels=1)
+        self.density_loss = L1Loss()
+
+    # -------------------------------------------------------------------------------------- optimisation glue
+    def get_param_groups(self) -> Dict[str, List[Parameter]]:
+        """models/nerfacto.py:256-261 + models/thermal_nerfacto.py:390-401."""
+        groups: Dict[str, List[Parameter]] = {}
+        groups["proposal_networks"] = list(self.proposal_networks.parameters())
+        groups["fields"] = list(self.field.parameters())
+        self.camera_optimizer.get_param_groups(param_groups=groups)
+        self.shared_camera_optimizer.get_param_groups(param_groups=groups, name="shared_camera_opt")
+        if self.config.density_mode == "separate":
+            groups["proposal_networks_thermal"] = list(self.proposal_networks_thermal.parameters())
+            groups["fields_thermal"] = list(self.field_thermal.parameters())
+            self.camera_optimizer_thermal.get_param_groups(param_groups=groups, name="camera_opt_thermal")
+            self.shared_camera_optimizer_thermal.get_param_groups(param_groups=groups,
+                                                                  name="shared_camera_opt_thermal")
+        return groups
+
+    def set_anneal_step(self, step: int) -> None:
+        """The BEFORE_TRAIN_ITERATION callback body, models/nerfacto.py:271-281."""
+        c = self.config
+        self.step = step
+        if c.use_proposal_weight_anneal:
+            frac = np.clip(step / c.proposal_weights_anneal_max_num_iters, 0, 1)
+            b = c.proposal_weights_anneal_slope
+            anneal = b * frac / ((b - 1) * frac + 1)
+            self.proposal_sampler.set_anneal(anneal)
+            if c.use_proposal_thermal_weight_anneal:
+                self.proposal_sampler_thermal.set_anneal(anneal)
+
+    # -------------------------------------------------------------------------------------- forward
+    def forward(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                jitters_thermal: Optional[List[Tensor]] = None) -> Dict[str, Tensor]:
+        """Model.forward, models/base_model.py:132-143: collider, then get_outputs."""
+        ray_bundle = self.collider(ray_bundle)
+        return self.get_outputs(ray_bundle, jitters=jitters, jitters_thermal=jitters_thermal)
+
+    def _get_outputs(self, ray_bundle: RayBundle, field_: ThermalNerfactoField, renderer: nn.Module,
+                     ray_samples: RaySamples, weights_list: List, ray_samples_list: List) -> Dict:
+        """NerfactoModel._get_outputs, models/nerfacto.py:299-353."""
+        field_outputs = field_.forward(ray_samples, compute_normals=self.config.predict_normals)
+        weights = ray_samples.get_weights(field_outputs[FieldHeadNames.DENSITY])
+        weights_list.append(weights)
+        ray_samples_list.append(ray_samples)
+        rgb = renderer(rgb=field_outputs[FieldHeadNames.RGB], weights=weights)
+        with torch.no_grad():
+            depth = self.renderer_depth(weights=weights, ray_samples=ray_samples)
+        expected_depth = self.renderer_expected_depth(weights=weights, ray_samples=ray_samples)
+        accumulation = self.renderer_accumulation(weights=weights)
+        outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "expected_depth": expected_depth,
+                   "density": field_outputs[FieldHeadNames.DENSITY]}
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+        with torch.no_grad():
+            for i in range(self.config.num_proposal_iterations):
+                outputs[f"prop_depth_{i}"] = self.renderer_depth(weights=weights_list[i],
+                                                                 ray_samples=ray_samples_list[i])
+        outputs["_field_rgb"] = field_outputs[FieldHeadNames.RGB]
+        return outputs
+
+    def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                    jitters_thermal: Optional[List[Tensor]] = None) -> Dict:
+        """ThermalNerfactoModel.get_outputs, models/thermal_nerfacto.py:403-489."""
+        c = self.config
+        # the reference deep-copies the bundle so that each path applies its own pose corrections (:407)
+        ray_bundle_thermal = RayBundle(origins=ray_bundle.origins, directions=ray_bundle.directions,
+                                       pixel_area=ray_bundle.pixel_area, camera_indices=ray_bundle.camera_indices,
+                                       nears=ray_bundle.nears, fars=ray_bundle.fars, metadata=ray_bundle.metadata,
+                                       times=ray_bundle.times)
+        self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
+        if self.training:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
+                                                                            jitters=jitters)
+        renderer_rgb = self.renderer_rgbt if c.density_mode == "shared" else self.renderer_rgb
+        outputs = self._get_outputs(ray_bundle, self.field, renderer_rgb, ray_samples, weights_list, ray_samples_list)
+        field_rgb = outputs.pop("_field_rgb")
+
+        if c.density_mode == "shared":
+            rgbt = outputs["rgb"]
+            outputs["rgbt"] = rgbt
+            outputs["rgb"] = rgbt[..., :3]
+            outputs["rgb_thermal"] = rgbt[..., 3:]
+        elif c.density_mode == "separate":
+            self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
+            if self.training:
+                self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
+            ray_samples_thermal, weights_list_thermal, ray_samples_list_thermal = self.proposal_sampler_thermal(
+                ray_bundle_thermal, density_fns=self.density_fns_thermal, jitters=jitters_thermal)
+            thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
+                                                ray_samples_thermal, weights_list_thermal, ray_samples_list_thermal)
+            field_rgb_thermal = thermal_outputs.pop("_field_rgb")
+            for k, v in thermal_outputs.items():
+                outputs[f"{k}_thermal"] = v
+
+            if c.density_loss_mult > 0 or not self.training:
+                # cross-field densities for the density regulariser (:447-458).  The reference runs the full
+                # field forward here and throws the colour away; only the density is evaluated.
+                outputs["density2"] = self.field.get_density(ray_samples_thermal)[0]
+                outputs["density2_thermal"] = self.field_thermal.get_density(ray_samples)[0]
+
+            if not self.training:
+                # "removal" renders (:460-487).  The reference recomputes both field forwards on the very same
+                # samples (identical values in eval); the colours from above are reused instead.
+                thr = c.removal_min_density_diff
+                mask_rgb = (outputs["density"] / outputs["density"]
+                            - outputs["density2_thermal"] / outputs["density"]).abs() < thr
+                w_rm = ray_samples.get_weights(outputs["density"] * mask_rgb)
+                outputs["removal"] = self.renderer_rgb(rgb=field_rgb, weights=w_rm)
+                mask_th = (outputs["density_thermal"] / outputs["density_thermal"]
+                           - outputs["density2"] / outputs["density_thermal"]).abs() < thr
+                # reference quirk kept: thermal densities composited with the RGB samples' deltas (:485)
+                w_rm_th = ray_samples.get_weights(outputs["density_thermal"] * mask_th)
+                outputs["removal_thermal"] = self.renderer_thermal(rgb=field_rgb_thermal, weights=w_rm_th)
+        return outputs
+
+    @torch.no_grad()
+    def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:
+        """models/base_model.py:177-206: chunked full-frame render (chunk size kept, the expected-depth clip is
+        chunk-global in the reference)."""
+        input_device = camera_ray_bundle.directions.device
+        chunk = self.config.eval_num_rays_per_chunk
+        image_height, image_width = camera_ray_bundle.origins.shape[:2]
+        num_rays = len(camera_ray_bundle)
+        flat = camera_ray_bundle.flatten()
+        outputs_lists = defaultdict(list)
+        for i in range(0, num_rays, chunk):
+            ray_bundle = flat[i:i + chunk].to(self.device)
+            outputs = self.forward(ray_bundle=ray_bundle)
+            for name, out in outputs.items():
+                if torch.is_tensor(out):
+                    outputs_lists[name].append(out.to(input_device))
+        return {name: torch.cat(lst).view(image_height, image_width, -1) for name, lst in outputs_lists.items()}
+
+    # -------------------------------------------------------------------------------------- losses
+    def get_metrics_dict(self, outputs, batch) -> Dict:
+        """models/thermal_nerfacto.py:253-282 without the PSNR entries (torchmetrics is the reference's
+        reporting code, not part of the loss)."""
+        metrics_dict = {}
+        if self.training:
+            metrics_dict["distortion"] = 0
+            for s in self.output_suffixes:
+                metrics_dict["distortion"] += distortion_loss(outputs[f"weights_list{s}"],
+                                                              outputs[f"ray_samples_list{s}"])
+        self.camera_optimizer.get_metrics_dict(metrics_dict)
+        self.shared_camera_optimizer.get_metrics_dict(metrics_dict)
+        if self.config.density_mode == "separate":
+            self.camera_optimizer_thermal.get_metrics_dict(metrics_dict)
+            self.shared_camera_optimizer_thermal.get_metrics_dict(metrics_dict)
+        return metrics_dict
+
+    def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
+        """models/thermal_nerfacto.py:284-388."""
+        c = self.config
+        loss_dict = {}
+        image = batch["image"].to(self.device)
+        is_thermal = batch["is_thermal"].to(self.device)
+        if c.density_mode != "rgb_only":
+            pred = torch.cat((outputs["rgb"], outputs["rgb_thermal"]), dim=1)
+        else:
+            pred = torch.cat((outputs["rgb"], torch.zeros(outputs["rgb"].shape[0], 1, device=self.device)), dim=1)
+        pred_rgb, gt_rgb = self.renderer_rgbt.blend_background_for_loss_computation(
+            pred_image=pred, pred_accumulation=outputs["accumulation"], gt_image=image, is_thermal=is_thermal)
+        is_rgb = (1 - is_thermal)[:, None]
+        loss_dict["rgb_loss"] = self.rgb_loss(gt_rgb[..., :3] * is_rgb, pred_rgb[..., :3] * is_rgb)
+        if c.density_mode != "rgb_only":
+            th = is_thermal[:, None]
+            loss_dict["thermal_loss"] = c.thermal_loss_mult * self.rgb_loss(gt_rgb[..., 3:] * th, pred_rgb[..., 3:] * th)
+        if c.density_mode == "separate" and c.density_loss_mult > 0:
+            m, r = c.density_loss_mult, c.rgb_density_loss_mult
+            d, d2, dt, d2t = (outputs["density"], outputs["density2"], outputs["density_thermal"],
+                              outputs["density2_thermal"])
+            if r == 1:
+                loss_dict["density_loss"] = m * self.density_loss(d2, dt) + m * self.density_loss(d, d2t)
+            else:  # asymmetric stop-gradient pattern, :336-344
+                loss_dict["density_loss"] = (m * self.density_loss(d2.detach(), dt)
+                                             + m * self.density_loss(d.detach(), d2t)
+                                             + r * m * self.density_loss(d2, dt.detach())
+                                             + r * m * self.density_loss(d, d2t.detach()))
+        if c.density_mode != "rgb_only" and c.tv_pixel_loss_mult > 0:
+            loss_dict["tv_pixel_loss"] = c.tv_pixel_loss_mult * tv_pixel_loss(pred_rgb[..., 3:], is_thermal)
+        if c.density_mode != "rgb_only" and c.cross_channel_loss_mult > 0:
+            loss_dict["cross_channel_loss"] = c.cross_channel_loss_mult * cross_channel_loss(
+                pred_rgb[..., 3:], gt_rgb[..., :3], is_thermal)
+        if self.training:
+            loss_dict["interlevel_loss"] = 0
+            loss_dict["distortion_loss"] = 0
+            assert metrics_dict is not None and "distortion" in metrics_dict
+            for s in self.output_suffixes:
+                loss_dict["interlevel_loss"] += c.interlevel_loss_mult * interlevel_loss(
+                    outputs[f"weights_list{s}"], outputs[f"ray_samples_list{s}"])
+                # reference quirk kept: the SUMMED distortion metric is added once per suffix (:368)
+                loss_dict["distortion_loss"] += c.distortion_loss_mult * metrics_dict["distortion"]
+            self.camera_optimizer.get_loss_dict(loss_dict)
+            if c.density_mode == "separate":
+                self.camera_optimizer_thermal.get_loss_dict(loss_dict)
+        self.shared_camera_optimizer.get_loss_dict(loss_dict)
+        if c.density_mode == "separate":
+            self.shared_camera_optimizer_thermal.get_loss_dict(loss_dict)
+        return loss_dict
+
+    def get_train_loss_dict(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], **fw):
+        """VanillaPipeline.get_train_loss_dict body, pipelines/base_pipeline.py:291-304."""
+        outputs = self(ray_bundle, **fw)
+        metrics = self.get_metrics_dict(outputs, batch)
+        return outputs, self.get_loss_dict(outputs, batch, metrics), metrics

@@ -1,0 +1,339 @@
+"""torch.autograd bindings of the libtn_b200 kernels (thin: shape checks, allocation, launch).
+
+All tensors are CUDA float32; every launch goes to torch's current stream so the ops compose with
+torch code, CUDA graphs and one-process-per-GPU data parallelism.  No op here has a CPU path.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import call, float_array, ptr, ptr_array, stream
+
+ACT_NONE, ACT_SIGMOID, ACT_TRUNC_EXP = 0, 1, 2
+BG_NONE, BG_LAST_SAMPLE, BG_CONSTANT = 0, 1, 2
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------- hash grid
+class HashGridSpec:
+    """Static description of one grid: per-level scales (host floats), L, F, log2 T."""
+
+    def __init__(self, scalings: Sequence[float], features_per_level: int, log2_hashmap_size: int):
+        self.scalings = [float(s) for s in scalings]
+        self.num_levels = len(self.scalings)
+        self.features = int(features_per_level)
+        self.log2_T = int(log2_hashmap_size)
+        self._c_scales = float_array(self.scalings)
+
+    @property
+    def out_dim(self) -> int:
+        return self.num_levels * self.features
+
+    @property
+    def rows(self) -> int:
+        return self.num_levels << self.log2_T
+
+
+def hash_encode_indices(x: Tensor, spec: HashGridSpec) -> Tensor:
+    """int32 [N, L, 8] table rows in the reference's corner order (test hook for bit-exactness)."""
+    x = _f32c(x)
+    n = x.shape[0]
+    dummy = torch.zeros((spec.rows, spec.features), device=x.device)
+    out = torch.empty((n, spec.out_dim), device=x.device)
+    idx = torch.empty((n, spec.num_levels, 8), device=x.device, dtype=torch.int32)
+    call("tn_hash_encode_fwd", ptr(x), ptr(dummy), 0, spec._c_scales, n, spec.num_levels, spec.features, spec.log2_T,
+         ptr(out), ptr(idx), stream())
+    return idx
+
+
+class _HashEncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, table, spec: HashGridSpec, table_f16):
+        x = _f32c(x)
+        n = x.shape[0]
+        out = torch.empty((n, spec.out_dim), device=x.device, dtype=torch.float32)
+        src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
+        call("tn_hash_encode_fwd", ptr(x), ptr(src), dtype, spec._c_scales, n, spec.num_levels, spec.features,
+             spec.log2_T, ptr(out), None, stream())
+        ctx.spec = spec
+        ctx.save_for_backward(x, table, table_f16)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, table, table_f16 = ctx.saved_tensors
+        spec = ctx.spec
+        dy = _f32c(dy)
+        n = x.shape[0]
+        dtable = torch.zeros_like(table, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        if dtable is None and dx is None:
+            return None, None, None, None
+        if dtable is None:  # kernel always scatters; give it a scratch target
+            dtable = torch.zeros_like(table, dtype=torch.float32)
+        src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
+        call("tn_hash_encode_bwd", ptr(x), ptr(src), dtype, spec._c_scales, ptr(dy), n, spec.num_levels, spec.features,
+             spec.log2_T, ptr(dtable), ptr(dx), stream())
+        return dx, (dtable if ctx.needs_input_grad[1] else None), None, None
+
+
+def hash_encode(x: Tensor, table: Tensor, spec: HashGridSpec, table_f16: Optional[Tensor] = None) -> Tensor:
+    """x[N,3] in [0,1], table[L*T,F] -> [N, L*F].  field_components/encodings.py:420-461."""
+    return _HashEncodeFn.apply(x, table, spec, table_f16)
+
+
+# ----------------------------------------------------------------------------------- positions
+class _SamplePositionsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, origins, directions, ebins):
+        origins, directions, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
+        r, s = ebins.shape[0], ebins.shape[1] - 1
+        x = torch.empty((r * s, 3), device=ebins.device)
+        sel = torch.empty((r * s,), device=ebins.device)
+        call("tn_sample_positions_fwd", ptr(origins), ptr(directions), ptr(ebins), r, s, ptr(x), ptr(sel), stream())
+        ctx.save_for_backward(origins, directions, ebins)
+        ctx.mark_non_differentiable(sel)
+        return x, sel
+
+    @staticmethod
+    def backward(ctx, dx, _dsel):
+        origins, directions, ebins = ctx.saved_tensors
+        r, s = ebins.shape[0], ebins.shape[1] - 1
+        do = torch.empty_like(origins)
+        dd = torch.empty_like(directions)
+        call("tn_sample_positions_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(_f32c(dx)), r, s, ptr(do),
+             ptr(dd), stream())
+        return do, dd, None
+
+
+def sample_positions(origins: Tensor, directions: Tensor, ebins: Tensor) -> Tuple[Tensor, Tensor]:
+    """Ray samples -> contracted, normalised grid coordinates x[R*S,3] and selector[R*S]."""
+    return _SamplePositionsFn.apply(origins, directions, ebins)
+
+
+class _ContractPointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p):
+        p = _f32c(p)
+        n = p.shape[0]
+        x = torch.empty_like(p)
+        sel = torch.empty((n,), device=p.device)
+        call("tn_contract_points_fwd", ptr(p), n, ptr(x), ptr(sel), stream())
+        ctx.save_for_backward(p)
+        ctx.mark_non_differentiable(sel)
+        return x, sel
+
+    @staticmethod
+    def backward(ctx, dx, _dsel):
+        (p,) = ctx.saved_tensors
+        dp = torch.empty_like(p)
+        call("tn_contract_points_bwd", ptr(p), ptr(_f32c(dx)), p.shape[0], ptr(dp), stream())
+        return dp
+
+
+def contract_points(p: Tensor) -> Tuple[Tensor, Tensor]:
+    """World positions p[N,3] -> (x[N,3], selector[N])."""
+    return _ContractPointsFn.apply(p)
+
+
+# ----------------------------------------------------------------------------------- MLP
+class _MlpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, out_act, *wb):
+        x = _f32c(x)
+        ws = [_f32c(t) for t in wb[0::2]]
+        bs = [_f32c(t) for t in wb[1::2]]
+        n, in_dim = x.shape
+        width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
+        y = torch.empty((n, out_dim), device=x.device)
+        call("tn_mlp_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
+             stream())
+        ctx.out_act = out_act
+        ctx.save_for_backward(x, *ws, *bs)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x = saved[0]
+        nl = (len(saved) - 1) // 2
+        ws, bs = list(saved[1:1 + nl]), list(saved[1 + nl:])
+        n, in_dim = x.shape
+        width, out_dim = ws[0].shape[0], ws[-1].shape[0]
+        dws = [torch.zeros_like(w) for w in ws]
+        dbs = [torch.zeros_like(b) for b in bs]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        call("tn_mlp_bwd", ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
+             ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream())
+        grads = []
+        for dw, db in zip(dws, dbs):
+            grads += [dw, db]
+        return (dx, None, *grads)
+
+
+def mlp(x: Tensor, weights: List[Tensor], biases: List[Tensor], out_act: int = ACT_NONE) -> Tensor:
+    """Fully fused MLP (ReLU hidden activations).  field_components/mlp.py:159-178."""
+    wb = []
+    for w, b in zip(weights, biases):
+        wb += [w, b]
+    return _MlpFn.apply(x, out_act, *wb)
+
+
+def mlp_shape_supported(in_dim: int, width: int, out_dim: int, n_layers: int) -> bool:
+    return n_layers in (2, 3) and 1 <= in_dim <= 64 and width in (16, 64) and 1 <= out_dim <= 16
+
+
+def sh4(directions: Tensor) -> Tensor:
+    """16 SH components of d[N,3] (no gradient, as in the reference: encodings.py:792 is @torch.no_grad)."""
+    d = _f32c(directions.detach())
+    out = torch.empty((d.shape[0], 16), device=d.device)
+    call("tn_sh4", ptr(d), d.shape[0], ptr(out), stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------- samplers
+_LINSPACE_CACHE = {}
+
+
+def _host_linspace(key, make, device):
+    """Constants the reference computes with torch.linspace on the fly; computed once on the HOST
+    (bit-identical to the reference's values) and cached per device."""
+    k = (key, str(device))
+    if k not in _LINSPACE_CACHE:
+        _LINSPACE_CACHE[k] = make().to(device)
+    return _LINSPACE_CACHE[k]
+
+
+def _jitter_arg(jitter: Optional[Tensor], rays: int, per_ray: int):
+    """jitter None | [R,1] (single jitter) | [R,per_ray] -> (contiguous tensor | None, per-sample flag)."""
+    if jitter is None:
+        return None, 0
+    j = _f32c(jitter)
+    if j.numel() == rays:
+        return j.view(-1), 0
+    if j.numel() == rays * per_ray:
+        return j.view(-1), 1
+    raise ValueError(f"jitter has {j.numel()} elements; expected {rays} or {rays * per_ray}")
+
+
+def piecewise_bins(nears: Tensor, fars: Tensor, num_samples: int, jitter: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
+    """UniformLinDispPiecewiseSampler bins: (spacing bins, euclidean bins), both [R, S+1]."""
+    nears, fars = _f32c(nears).view(-1), _f32c(fars).view(-1)
+    r = nears.shape[0]
+    unit = _host_linspace(("unit", num_samples), lambda: torch.linspace(0.0, 1.0, num_samples + 1), nears.device)
+    sb = torch.empty((r, num_samples + 1), device=nears.device)
+    eb = torch.empty_like(sb)
+    jit, per_sample = _jitter_arg(jitter, r, num_samples + 1)
+    call("tn_piecewise_bins", ptr(unit), ptr(nears), ptr(fars), ptr(jit), per_sample, r, num_samples, ptr(sb), ptr(eb),
+         stream())
+    return sb, eb
+
+
+def pdf_sample(weights: Tensor, sbins_old: Tensor, nears: Tensor, fars: Tensor, num_samples: int,
+               jitter: Optional[Tensor], histogram_padding: float = 0.01, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
+    """PDFSampler (include_original=False): new (spacing bins, euclidean bins) [R, S_new+1]."""
+    w = _f32c(weights.detach())
+    r, s_old = w.shape
+    nb = num_samples + 1
+    if jitter is None:
+        u = _host_linspace(("u_eval", nb), lambda: torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb),
+                           w.device)
+    else:
+        u = _host_linspace(("u_train", nb), lambda: torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb), w.device)
+    sb = torch.empty((r, nb), device=w.device)
+    eb = torch.empty_like(sb)
+    jit, per_sample = _jitter_arg(jitter, r, nb)
+    call("tn_pdf_sample", ptr(w), ptr(_f32c(sbins_old)), ptr(_f32c(nears).view(-1)), ptr(_f32c(fars).view(-1)), ptr(u),
+         ptr(jit), per_sample, r, s_old, num_samples, histogram_padding, eps, ptr(sb), ptr(eb), stream())
+    return sb, eb
+
+
+# ----------------------------------------------------------------------------------- rendering
+class _WeightsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sigma, deltas):
+        sigma, deltas = _f32c(sigma), _f32c(deltas)
+        r, s = sigma.shape
+        w = torch.empty_like(sigma)
+        call("tn_weights_fwd", ptr(sigma), ptr(deltas), r, s, ptr(w), stream())
+        ctx.save_for_backward(sigma, deltas)
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        sigma, deltas = ctx.saved_tensors
+        r, s = sigma.shape
+        ds = torch.empty_like(sigma)
+        call("tn_weights_bwd", ptr(sigma), ptr(deltas), ptr(_f32c(dw)), r, s, ptr(ds), stream())
+        return ds, None
+
+
+def sample_weights(sigma: Tensor, deltas: Tensor) -> Tensor:
+    """sigma, deltas [R,S] -> weights [R,S].  cameras/rays.py:128-150.  (deltas carry no gradient.)"""
+    return _WeightsFn.apply(sigma, deltas.detach())
+
+
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, weights, colour, starts, ends, bg_mode, bg, eval_mode, want_depth):
+        weights = _f32c(weights)
+        r, s = weights.shape
+        c = 0 if colour is None else colour.shape[-1]
+        dev = weights.device
+        colour_c = None if colour is None else _f32c(colour).view(r, s, c)
+        starts_c = None if starts is None else _f32c(starts).view(r, s)
+        ends_c = None if ends is None else _f32c(ends).view(r, s)
+        rgb = torch.empty((r, c), device=dev) if c else None
+        acc = torch.empty((r, 1), device=dev)
+        med = exp = minmax = None
+        if want_depth:
+            med = torch.empty((r, 1), device=dev)
+            exp = torch.empty((r, 1), device=dev)
+            minmax = torch.tensor([float("inf"), float("-inf")], device=dev)
+        bg_arr = float_array(bg) if bg is not None else None
+        call("tn_render_fwd", ptr(weights), ptr(colour_c), ptr(starts_c), ptr(ends_c), r, s, c, bg_mode, bg_arr,
+             int(eval_mode), ptr(rgb), ptr(acc), ptr(med), ptr(exp), ptr(minmax), stream())
+        ctx.bg_mode, ctx.bg, ctx.c = bg_mode, bg, c
+        ctx.save_for_backward(weights, colour_c, starts_c, ends_c)
+        outs = (rgb, acc, med, exp, minmax)
+        ctx.mark_non_differentiable(*[o for o in (med, minmax) if o is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, _d_med, d_exp, _d_mm):
+        weights, colour, starts, ends = ctx.saved_tensors
+        r, s = weights.shape
+        c = ctx.c
+        dw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
+        dcol = torch.empty_like(colour) if (c and ctx.needs_input_grad[1]) else None
+        bg_arr = float_array(ctx.bg) if ctx.bg is not None else None
+        d_rgb = None if (d_rgb is None or not c) else _f32c(d_rgb)
+        d_acc = None if d_acc is None else _f32c(d_acc)
+        d_exp = None if d_exp is None else _f32c(d_exp)
+        call("tn_render_bwd", ptr(weights), ptr(colour), ptr(starts), ptr(ends), ptr(d_rgb), ptr(d_acc), ptr(d_exp), r,
+             s, c, ctx.bg_mode, bg_arr, ptr(dw), ptr(dcol), stream())
+        return dw, dcol, None, None, None, None, None, None
+
+
+def render(weights: Tensor, colour: Optional[Tensor], starts: Optional[Tensor], ends: Optional[Tensor], *,
+           bg_mode: int = BG_NONE, bg: Optional[Sequence[float]] = None, eval_mode: bool = False,
+           want_depth: bool = False):
+    """Fused renderer reductions over one launch.
+
+    Returns (rgb [R,C] | None, accumulation [R,1], median depth [R,1] | None,
+             UNCLIPPED expected depth [R,1] | None, (min,max) of sample midpoints [2] | None).
+    """
+    return _RenderFn.apply(weights, colour, starts, ends, bg_mode, None if bg is None else tuple(bg), eval_mode,
+                           want_depth)
+
+
+def library_info() -> str:
+    lib = _lib.load()
+    return f"libtn_b200 v{lib.tn_version()} ({lib.tn_build_arch().decode()}) at {_lib.LIB_PATH}"

@@ -1,0 +1,83 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, `torch.distributed` (NCCL over NVLink/NVSwitch).
+
+Replaces, for this path, the reference's only parallel strategy: `DistributedDataParallel(model,
+find_unused_parameters=True)` in `nerfstudio/pipelines/base_pipeline.py:280-283` (process groups are created in
+`nerfstudio/scripts/train.py:138-157`).
+
+* Training: rays are independent, every rank holds full replicas; the single exchange step is the average of
+  all parameter gradients.  DDP does it with ~7 buckets of 25 MB plus an autograd-graph walk for unused
+  parameters; here all gradients live in ONE flat, zero-initialised fp32 buffer (parameters' `.grad` are views
+  into it) and one all-reduce moves it.  Unused parameters (proposal networks on non-"updated" steps,
+  ray_samplers.py:604-611) simply contribute zeros.
+* Rendering: rows of the frame are sharded on chunk boundaries with no communication
+  (`shard_chunks`); chunk boundaries are the reference's (`eval_num_rays_per_chunk`), so the chunk-global
+  expected-depth clip (renderers.py:574) sees the same chunks.
+"""
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor, nn
+
+
+class FlatGradBuffer:
+    """All gradients of a module in one contiguous fp32 buffer, laid out group by group."""
+
+    def __init__(self, params: Iterable[nn.Parameter], device=None):
+        seen, self.params = set(), []
+        for p in params:
+            if p.requires_grad and p.numel() > 0 and id(p) not in seen:
+                seen.add(id(p))
+                self.params.append(p)
+        device = device if device is not None else (self.params[0].device if self.params else "cpu")
+        # 16-byte aligned offsets: the scatter kernels use vector reductions on table gradients
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+
+    @classmethod
+    def from_param_groups(cls, groups: Dict[str, List[nn.Parameter]], order: Optional[List[str]] = None, device=None):
+        names = order if order is not None else list(groups)
+        return cls([p for n in names for p in groups[n]], device=device)
+
+    def zero_(self) -> None:
+        self.flat.zero_()
+
+    def numel(self) -> int:
+        return self.flat.numel()
+
+    def check_views(self) -> bool:
+        """True when every parameter's .grad still aliases the flat buffer (optimizers that set grads to None
+        break the aliasing; call `zero_()` instead of `zero_grad(set_to_none=True)`)."""
+        base = self.flat.untyped_storage().data_ptr()
+        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
+
+    def all_reduce_mean(self, group=None, async_op: bool = False):
+        """Average the gradients over the ranks of `group` (DDP semantics, base_pipeline.py:282)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        world = dist.get_world_size(group)
+        if dist.get_backend(group) == "nccl":
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
+        self.flat.div_(world)
+        return work
+
+
+def shard_chunks(num_rays: int, chunk: int, rank: int, world: int) -> List[Tuple[int, int]]:
+    """[start, end) ray ranges (whole chunks of the reference's chunk loop, models/base_model.py:187-190) that
+    `rank` renders; contiguous blocks of chunks per rank, earlier ranks take the remainder."""
+    n_chunks = (num_rays + chunk - 1) // chunk
+    base, rem = divmod(n_chunks, world)
+    first = rank * base + min(rank, rem)
+    count = base + (1 if rank < rem else 0)
+    return [(c * chunk, min((c + 1) * chunk, num_rays)) for c in range(first, first + count)]
+
+
+def rank_seed(base_seed: int, rank: int) -> int:
+    """scripts/train.py:82-97: every rank seeds with config.machine.seed + global_rank."""
+    return base_seed + rank

@@ -1,0 +1,339 @@
+"""GPU parity tests, kernel level: libtn_b200 (through the C ABI) vs the CPU oracle and the reference goldens.
+
+Tolerances: integer results (hash rows, sample counts) bit-exact; hash features bit-exact (the encode kernel
+rounds every op like the reference); everything downstream of an exp()/sum within 1e-5 abs/rel unless noted
+(north-star bar: 1e-3 rendered outputs, 1e-3 relative gradients).
+"""
+import pytest
+import torch
+
+import oracle
+from oracle import sampling as osamp
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import ops
+
+DEV = "cuda"
+
+
+def close(a, b, atol=1e-5, rtol=1e-5):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), atol=atol, rtol=rtol)
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+# ----------------------------------------------------------------------------------------- hash grid
+@pytest.mark.parametrize("tag,L,lo,hi,log2T", [("main19", 16, 16, 2048, 19), ("main21", 16, 16, 2048, 21),
+                                               ("prop128", 5, 16, 128, 17), ("prop256", 5, 16, 256, 17)])
+def test_hash_rows_bit_exact_vs_reference(golden, tag, L, lo, hi, log2T):
+    g = golden("hash_indices.npz")
+    enc = tn.HashEncoding(num_levels=L, min_res=lo, max_res=hi, log2_hashmap_size=log2T, features_per_level=1)
+    assert torch.equal(enc.scalings, g[f"{tag}_scalings"])
+    idx = enc.corner_indices(g["x"].to(DEV))
+    assert torch.equal(idx.cpu(), g[f"{tag}_idx"])
+
+
+@pytest.mark.parametrize("name,L,hi", [("hash_small.npz", 16, 2048), ("hash_small_prop.npz", 5, 128)])
+def test_hash_encode_golden_fwd_bwd(golden, name, L, hi):
+    g = golden(name)
+    enc = tn.HashEncoding(num_levels=L, min_res=16, max_res=hi, log2_hashmap_size=int(g["log2T"])).to(DEV)
+    with torch.no_grad():
+        enc.hash_table.copy_(g["table"])
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = enc(x)
+    assert torch.equal(y.cpu(), g["y"]), f"max diff {(y.cpu() - g['y']).abs().max()}"
+    (y * g["dy"].to(DEV)).sum().backward()
+    close(enc.hash_table.grad, g["dtable"], 1e-5, 1e-5)
+    close(x.grad, g["dx"], 2e-4, 1e-4)
+
+
+@pytest.mark.parametrize("F", [1, 2, 4, 8])
+def test_hash_encode_features_per_level(F):
+    torch.manual_seed(5)
+    scal = oracle.hash_scalings(6, 16, 512)
+    table = (torch.rand(6 << 10, F) - 0.5)
+    x = torch.rand(1000, 3)
+    enc = tn.HashEncoding(num_levels=6, min_res=16, max_res=512, log2_hashmap_size=10, features_per_level=F).to(DEV)
+    with torch.no_grad():
+        enc.hash_table.copy_(table)
+    xg = x.to(DEV).requires_grad_(True)
+    y = enc(xg)
+    xo = x.clone().requires_grad_(True)
+    to = table.clone().requires_grad_(True)
+    yo = oracle.hash_encode(xo, to, scal, 10)
+    assert torch.equal(y.cpu(), yo)
+    g = torch.randn_like(yo)
+    (yo * g).sum().backward()
+    (y * g.to(DEV)).sum().backward()
+    close(enc.hash_table.grad, to.grad)
+    close(xg.grad, xo.grad, 2e-4, 1e-4)
+
+
+def test_hash_encode_full_size_properties():
+    """BASELINE size (T=2^19, 16 levels, 4096*48 points): oracle on a slice + size-independent properties."""
+    torch.manual_seed(6)
+    enc = tn.HashEncoding(num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=19).to(DEV)
+    with torch.no_grad():
+        enc.hash_table.uniform_(-0.5, 0.5)
+    n = 4096 * 48
+    x = torch.rand(n, 3, device=DEV)
+    x[:7] = torch.tensor([[0.0, 0, 0], [1, 1, 1], [0.5, 0.5, 0.5], [0, 1, 0.25], [1e-7, 1 - 1e-7, 0.3],
+                          [1 / 2047, 2046 / 2047, 1.0], [0.999999, 0.0, 0.5]], device=DEV)
+    y = enc(x)
+    sl = slice(0, 2048)
+    yo = oracle.hash_encode(x[sl].cpu(), enc.hash_table.detach().cpu(), enc.scalings, 19)
+    assert torch.equal(y[sl].cpu(), yo)
+    # (1) interpolation weights sum to one: a constant table encodes to that constant
+    const = tn.HashEncoding(num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=19).to(DEV)
+    with torch.no_grad():
+        const.hash_table.fill_(0.75)
+    close(const(x), torch.full((n, 32), 0.75), 1e-6, 0)
+    # (2) linearity in the table
+    other = torch.rand_like(enc.hash_table) - 0.5
+    with torch.no_grad():
+        const.hash_table.copy_(2.0 * enc.hash_table + other)
+        y2 = const(x)
+        const.hash_table.copy_(other)
+        y3 = const(x)
+    close(y2, 2.0 * y + y3, 2e-6, 1e-5)
+    # (3) checksum of the scatter: sum of the table gradient == sum of the output gradient, per level & feature
+    dy = torch.randn_like(y)
+    enc.hash_table.grad = None
+    y.backward(dy)
+    got = enc.hash_table.grad.view(16, -1, 2).sum(1).double().cpu()
+    want = dy.view(n, 16, 2).double().sum(0).cpu()
+    torch.testing.assert_close(got, want, atol=5e-2, rtol=1e-4)
+
+
+def test_hash_encode_half_table():
+    torch.manual_seed(7)
+    enc = tn.HashEncoding(num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=12).to(DEV)
+    with torch.no_grad():
+        enc.hash_table.uniform_(-0.5, 0.5)
+    x = torch.rand(5000, 3, device=DEV)
+    y32 = enc(x)
+    enc.use_half_table = True
+    y16 = enc(x)
+    assert (y16 - y32).abs().max().item() < 5e-4  # fp16 table rounding: 2^-11 * 0.5
+    yo = oracle.hash_encode(x.cpu(), enc.hash_table.detach().half().float().cpu(), enc.scalings, 12)
+    assert torch.equal(y16.cpu(), yo)
+
+
+def test_hash_encode_empty_and_ragged():
+    enc = tn.HashEncoding(num_levels=5, min_res=16, max_res=128, log2_hashmap_size=8).to(DEV)
+    assert enc(torch.zeros(0, 3, device=DEV)).shape == (0, 10)
+    for n in (1, 31, 127, 129, 1000):
+        x = torch.rand(n, 3, device=DEV)
+        yo = oracle.hash_encode(x.cpu(), enc.hash_table.detach().cpu(), enc.scalings, 8)
+        assert torch.equal(enc(x).cpu(), yo)
+    assert enc(torch.rand(4, 6, 3, device=DEV)).shape == (4, 6, 10)
+
+
+# ----------------------------------------------------------------------------------------- MLP / SH / contraction
+@pytest.mark.parametrize("tag,i,n,w,o,act", [("density", 32, 2, 64, 16, None), ("head3", 63, 3, 64, 3, "sigmoid"),
+                                             ("head4", 63, 3, 64, 4, "sigmoid"), ("head1", 63, 3, 64, 1, "sigmoid"),
+                                             ("prop", 10, 2, 16, 1, None)])
+def test_mlp_golden_fwd_bwd(golden, tag, i, n, w, o, act):
+    g = golden("components.npz")
+    mlp = tn.MLP(in_dim=i, num_layers=n, layer_width=w, out_dim=o,
+                 out_activation=torch.nn.Sigmoid() if act else None).to(DEV)
+    with torch.no_grad():
+        for li, layer in enumerate(mlp.layers):
+            layer.weight.copy_(g[f"mlp_{tag}_w{li}"])
+            layer.bias.copy_(g[f"mlp_{tag}_b{li}"])
+    x = g[f"mlp_{tag}_x"].to(DEV).requires_grad_(True)
+    y = mlp(x)
+    close(y, g[f"mlp_{tag}_y"], 2e-6, 1e-5)
+    (y * g[f"mlp_{tag}_dy"].to(DEV)).sum().backward()
+    close(x.grad, g[f"mlp_{tag}_dx"], 1e-5, 1e-4)
+    for li, layer in enumerate(mlp.layers):
+        close(layer.weight.grad, g[f"mlp_{tag}_dw{li}"], 2e-5, 1e-4)
+        close(layer.bias.grad, g[f"mlp_{tag}_db{li}"], 2e-5, 1e-4)
+
+
+@pytest.mark.parametrize("n", [0, 1, 63, 64, 65, 5000])
+def test_mlp_ragged_sizes(n):
+    torch.manual_seed(8)
+    mlp = tn.MLP(in_dim=32, num_layers=2, layer_width=64, out_dim=16).to(DEV)
+    x = torch.randn(n, 32, device=DEV)
+    y = mlp(x)
+    ws = [l.weight.detach().cpu() for l in mlp.layers]
+    bs = [l.bias.detach().cpu() for l in mlp.layers]
+    close(y, oracle.mlp_forward(x.cpu(), ws, bs), 2e-6, 1e-5)
+
+
+def test_mlp_weight_grads_large_batch():
+    """many tiles / persistent CTAs: gradient reduction across the grid"""
+    torch.manual_seed(9)
+    mlp = tn.MLP(in_dim=63, num_layers=3, layer_width=64, out_dim=3, out_activation=torch.nn.Sigmoid()).to(DEV)
+    x = torch.randn(100_003, 63, device=DEV, requires_grad=True)
+    y = mlp(x)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xo = x.detach().cpu().requires_grad_(True)
+    ws = [l.weight.detach().cpu().requires_grad_(True) for l in mlp.layers]
+    bs = [l.bias.detach().cpu().requires_grad_(True) for l in mlp.layers]
+    yo = oracle.mlp_forward(xo, ws, bs, "sigmoid")
+    yo.backward(g.cpu())
+    close(y, yo, 2e-6, 1e-5)
+    assert rel_err(x.grad, xo.grad) < 1e-5
+    for l, w, b in zip(mlp.layers, ws, bs):
+        assert rel_err(l.weight.grad, w.grad) < 1e-4
+        assert rel_err(l.bias.grad, b.grad) < 1e-4
+
+
+def test_unsupported_mlp_shape_raises():
+    with pytest.raises(NotImplementedError):
+        tn.MLP(in_dim=100, num_layers=2, layer_width=64, out_dim=3)
+    with pytest.raises(NotImplementedError):
+        tn.MLP(in_dim=32, num_layers=2, layer_width=48, out_dim=3)
+
+
+def test_sh_and_contraction_golden(golden):
+    g = golden("components.npz")
+    sh = tn.SHEncoding(levels=4)(g["sh_in"].to(DEV))
+    assert torch.equal(sh.cpu(), g["sh_out"])
+    p = g["contract_in"].to(DEV).requires_grad_(True)
+    x, sel = ops.contract_points(p)
+    want = (g["contract_out"] + 2.0) / 4.0
+    want_sel = ((want > 0) & (want < 1)).all(-1)
+    assert torch.equal(x.cpu(), want * want_sel[:, None])
+    assert torch.equal(sel.cpu(), want_sel.float())
+    # backward against autograd of the oracle composition
+    po = g["contract_in"].clone().requires_grad_(True)
+    xo, _ = oracle.normalize_positions(po)
+    gy = g["contract_dy"]
+    (xo * gy).sum().backward()
+    (x * gy.to(DEV)).sum().backward()
+    close(p.grad, po.grad, 1e-6, 1e-5)
+
+
+def test_sample_positions_fwd_bwd():
+    torch.manual_seed(10)
+    R, S = 37, 48
+    o = (torch.randn(R, 3) * 0.5).requires_grad_(True)
+    d = torch.nn.functional.normalize(torch.randn(R, 3), dim=-1).requires_grad_(True)
+    eb = torch.sort(torch.rand(R, S + 1) * 6, dim=-1).values
+    og, dg = o.detach().to(DEV).requires_grad_(True), d.detach().to(DEV).requires_grad_(True)
+    x, sel = ops.sample_positions(og, dg, eb.to(DEV))
+    pos = o[:, None, :] + d[:, None, :] * (eb[:, :-1, None] + eb[:, 1:, None]) / 2
+    xo, so = oracle.normalize_positions(pos)
+    assert torch.equal(x.cpu().view(R, S, 3), xo)
+    assert torch.equal(sel.cpu().view(R, S), so.float())
+    gy = torch.randn(R, S, 3)
+    (xo * gy).sum().backward()
+    (x.view(R, S, 3) * gy.to(DEV)).sum().backward()
+    close(og.grad, o.grad, 1e-5, 1e-4)
+    close(dg.grad, d.grad, 1e-5, 1e-4)
+
+
+# ----------------------------------------------------------------------------------------- samplers / weights / renderers
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_sampling_chain_golden(golden, mode):
+    g = golden("sampling.npz")
+    tr = mode == "train"
+    rb = tn.RayBundle(origins=g[f"{mode}_origins"].to(DEV), directions=g[f"{mode}_directions"].to(DEV),
+                      pixel_area=torch.ones(24, 1, device=DEV), nears=g[f"{mode}_nears"].to(DEV),
+                      fars=g[f"{mode}_fars"].to(DEV))
+    jit = [g[f"{mode}_jit{i}"].to(DEV) if tr else None for i in range(3)]
+    init = tn.UniformLinDispPiecewiseSampler(single_jitter=True).train(tr)
+    pdf = tn.PDFSampler(include_original=False, single_jitter=True).train(tr)
+    s0 = init(rb, num_samples=256, jitter=jit[0])
+    assert torch.equal(s0.frustums.starts.cpu(), g[f"{mode}_s0_starts"])
+    assert torch.equal(s0.frustums.ends.cpu(), g[f"{mode}_s0_ends"])
+    assert torch.equal(s0.spacing_starts.cpu(), g[f"{mode}_s0_spacing_starts"])
+    assert torch.equal(s0.deltas.cpu(), g[f"{mode}_s0_deltas"])
+    close(s0.frustums.get_positions(), g[f"{mode}_s0_positions"], 1e-6, 1e-6)
+    w0 = s0.get_weights(g[f"{mode}_dens0"].to(DEV))
+    close(w0, g[f"{mode}_w0"], 1e-6, 1e-5)
+    # PDF resampling on the reference's own weights (isolates the sampler from exp() differences)
+    s1 = pdf(rb, s0, g[f"{mode}_w0"].to(DEV), num_samples=96, jitter=jit[1])
+    assert s1.frustums.starts.shape == (24, 96, 1)
+    close(s1.spacing_starts, g[f"{mode}_s1_spacing_starts"], 2e-6, 0)
+    close(s1.frustums.starts, g[f"{mode}_s1_starts"], 0, 2e-5)
+    close(s1.frustums.ends, g[f"{mode}_s1_ends"], 0, 2e-5)
+    w1 = s1.get_weights(g[f"{mode}_dens1"].to(DEV))
+    close(w1, g[f"{mode}_w1"], 2e-5, 1e-4)
+    s2 = pdf(rb, s1, g[f"{mode}_w1"].to(DEV), num_samples=48, jitter=jit[2])
+    assert s2.frustums.starts.shape == (24, 48, 1)
+    close(s2.spacing_starts, g[f"{mode}_s2_spacing_starts"], 2e-6, 0)
+    close(s2.frustums.starts, g[f"{mode}_s2_starts"], 0, 5e-5)
+
+
+def _s2_samples(g, mode):
+    st, en = g[f"{mode}_s2_starts"].to(DEV), g[f"{mode}_s2_ends"].to(DEV)
+    fr = tn.Frustums(origins=torch.zeros(24, 48, 3, device=DEV), directions=torch.ones(24, 48, 3, device=DEV), starts=st,
+                     ends=en, pixel_area=torch.ones(24, 48, 1, device=DEV))
+    return tn.RaySamples(frustums=fr, deltas=g[f"{mode}_s2_deltas"].to(DEV))
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_weights_and_renderers_golden(golden, mode):
+    g = golden("sampling.npz")
+    tr = mode == "train"
+    rs = _s2_samples(g, mode)
+    dens = g[f"{mode}_dens2"].to(DEV).requires_grad_(True)
+    w = rs.get_weights(dens)
+    close(w, g[f"{mode}_w2"], 1e-6, 1e-5)
+    (w * g[f"{mode}_dw2"].to(DEV)).sum().backward()
+    close(dens.grad, g[f"{mode}_ddens2"], 1e-5, 1e-4)
+    w2 = g[f"{mode}_w2"].to(DEV)
+    for C, rend in ((3, tn.RGBRenderer(background_color="last_sample")),
+                    (1, tn.RGBRenderer(background_color="last_sample", num_channels=1)),
+                    (4, tn.RGBTRenderer(background_color="last_sample"))):
+        rend.train(tr)
+        col = g[f"{mode}_col{C}"].to(DEV).requires_grad_(True)
+        wv = w2.clone().requires_grad_(True)
+        img = rend(rgb=col, weights=wv)
+        close(img, g[f"{mode}_img{C}"], 1e-6, 1e-5)
+        if tr:  # eval clamps in place; gradients are a training-time concern
+            (img * g[f"{mode}_dimg{C}"].to(DEV)).sum().backward()
+            close(col.grad, g[f"{mode}_dcol{C}"], 1e-6, 1e-5)
+            close(wv.grad, g[f"{mode}_dw_from_img{C}"], 1e-5, 1e-5)
+    for bg in ("black", "white", "random"):
+        rend = tn.RGBRenderer(background_color=bg).train(tr)
+        close(rend(rgb=g[f"{mode}_col3"].to(DEV), weights=w2), g[f"{mode}_img3_{bg}"], 1e-6, 1e-5)
+    close(tn.AccumulationRenderer()(weights=w2), g[f"{mode}_acc"], 1e-6, 1e-6)
+    assert torch.equal(tn.DepthRenderer("median")(weights=w2, ray_samples=rs).cpu(), g[f"{mode}_depth_median"])
+    close(tn.DepthRenderer("expected")(weights=w2, ray_samples=rs), g[f"{mode}_depth_expected"], 1e-5, 1e-5)
+
+
+def test_expected_depth_gradient():
+    torch.manual_seed(11)
+    R, S = 19, 48
+    eb = torch.sort(torch.rand(R, S + 1) * 5, dim=-1).values
+    w = (torch.rand(R, S, 1) * 0.03).requires_grad_(True)
+    st, en = eb[:, :-1, None], eb[:, 1:, None]
+    want = oracle.render_depth_expected(w, st, en)
+    gi = torch.randn_like(want)
+    (want * gi).sum().backward()
+    fr = tn.Frustums(origins=torch.zeros(R, S, 3, device=DEV), directions=torch.ones(R, S, 3, device=DEV),
+                     starts=st.to(DEV), ends=en.to(DEV), pixel_area=torch.ones(R, S, 1, device=DEV))
+    wg = w.detach().to(DEV).requires_grad_(True)
+    got = tn.DepthRenderer("expected")(weights=wg, ray_samples=tn.RaySamples(frustums=fr))
+    close(got, want, 1e-5, 1e-5)
+    (got * gi.to(DEV)).sum().backward()
+    close(wg.grad, w.grad, 1e-4, 1e-4)
+
+
+def test_weights_edge_cases():
+    """zero density, opaque wall, inf/nan products (nan_to_num), S not a multiple of 32, S = 1"""
+    for S in (1, 31, 48, 96, 256, 257):
+        torch.manual_seed(S)
+        R = 9
+        sig = torch.rand(R, S) * 20
+        sig[0] = 0
+        sig[1, S // 2:] = 1e9
+        dl = torch.rand(R, S) * 0.1
+        dl[2, -1] = float("inf")
+        sig[3, 0] = float("inf")
+        dl[3, 0] = 0.0  # inf * 0 = nan
+        want = osamp.sample_weights(dl[..., None], sig[..., None])[..., 0]
+        got = ops.sample_weights(sig.to(DEV), dl.to(DEV))
+        close(got, want, 1e-6, 1e-5)

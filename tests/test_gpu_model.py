@@ -1,0 +1,167 @@
+"""GPU parity tests, model level: ThermalNerfactoModel (CUDA kernels) vs the reference goldens and the oracle.
+
+North-star tolerances, written out: rendered rgb / thermal / depth / accumulation <= 1e-3 max abs (fp32),
+<= 5e-3 with fp16 hash tables; gradients <= 1e-3 relative (L2 over each parameter tensor); sample counts
+exact.  Median depth is a searchsorted over an fp32 prefix sum: a 1-ulp difference may pick the neighbouring
+sample, so it is compared with a small mismatch budget.
+"""
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import nerfstudio_thermal_b200 as tn
+
+DEV = "cuda"
+SMALL_PROPS = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False},
+               {"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 256, "use_linear": False}]
+
+
+def build(golden, mode, **over):
+    g = golden(f"model_{mode}.npz")
+    cfg = tn.ThermalNerfactoModelConfig(density_mode=mode, log2_hashmap_size=9, proposal_net_args_list=SMALL_PROPS,
+                                        **over)
+    model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    sd["device_indicator_param"] = torch.empty(0)
+    model.load_state_dict(sd, strict=True)  # reference checkpoint keys load unchanged
+    return g, model.to(DEV)
+
+
+def bundle(g):
+    R = g["origins"].shape[0]
+    return tn.RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV),
+                        pixel_area=torch.full((R, 1), 1e-6, device=DEV), camera_indices=g["camera_indices"].to(DEV))
+
+
+def max_abs(a, b):
+    return (a.detach().cpu() - b).abs().max().item()
+
+
+def frac_mismatch(a, b, tol):
+    return ((a.detach().cpu() - b).abs() > tol).float().mean().item()
+
+
+@pytest.mark.parametrize("mode", ["separate", "shared", "rgb_only"])
+def test_eval_outputs_match_reference(golden, mode):
+    g, model = build(golden, mode)
+    model.eval()
+    with torch.no_grad():
+        out = model(bundle(g))
+    ref_keys = sorted(k[5:] for k in g if k.startswith("eval/"))
+    assert sorted(k for k, v in out.items() if torch.is_tensor(v)) == ref_keys
+    for k in ref_keys:
+        ref = g[f"eval/{k}"]
+        assert out[k].shape == ref.shape, k
+        if "depth" in k and "expected" not in k:  # median depths
+            assert frac_mismatch(out[k], ref, 1e-3) <= 0.07, k
+        elif k.startswith("density"):
+            torch.testing.assert_close(out[k].cpu(), ref, atol=1e-3, rtol=1e-3)
+        else:
+            assert max_abs(out[k], ref) <= 1e-3, (k, max_abs(out[k], ref))
+
+
+@pytest.mark.parametrize("mode", ["separate", "shared", "rgb_only"])
+def test_train_outputs_losses_and_gradients_match_reference(golden, mode):
+    g, model = build(golden, mode)
+    model.train()
+    jit = [g[f"jitter{i}"].to(DEV) for i in range(3)]
+    jit_t = [g[f"jitter{i}"].to(DEV) for i in range(3, 6)] if mode == "separate" else None
+    out = model(bundle(g), jitters=jit, jitters_thermal=jit_t)
+    for k in [k[6:] for k in g if k.startswith("train/")]:
+        if k.startswith("weights") or k.startswith("sdist"):
+            continue
+        ref = g[f"train/{k}"]
+        if "depth" in k and "expected" not in k:
+            assert frac_mismatch(out[k], ref, 1e-3) <= 0.07, k
+        elif k.startswith("density"):
+            torch.testing.assert_close(out[k].cpu(), ref, atol=1e-3, rtol=1e-3)
+        else:
+            assert max_abs(out[k], ref) <= 1e-3, (k, max_abs(out[k], ref))
+    for sfx in (("", "_thermal") if mode == "separate" else ("",)):
+        for i, S in enumerate((256, 96, 48)):
+            w = out[f"weights_list{sfx}"][i]
+            assert w.shape == (32, S, 1)  # sample counts exact
+            assert max_abs(w, g[f"train/weights{sfx}_{i}"]) <= 1e-4
+            sd_ = out[f"ray_samples_list{sfx}"][i]._layout.sbins
+            assert max_abs(sd_, g[f"train/sdist{sfx}_{i}"]) <= 1e-5
+    if mode == "rgb_only":
+        return
+    batch = {"image": g["image"].to(DEV), "is_thermal": g["is_thermal"].to(DEV)}
+    metrics = model.get_metrics_dict(out, batch)
+    losses = model.get_loss_dict(out, batch, metrics)
+    ref_keys = sorted(k[5:] for k in g if k.startswith("loss/"))
+    assert sorted(losses) == ref_keys
+    total = 0
+    for k in ref_keys:
+        torch.testing.assert_close(torch.as_tensor(losses[k]).detach().cpu().float(), g[f"loss/{k}"], atol=1e-6,
+                                   rtol=1e-3)
+        total = total + losses[k]
+    total.backward()
+    params = dict(model.named_parameters())
+    checked = 0
+    for k in [k[5:] for k in g if k.startswith("grad/")]:
+        ref = g[f"grad/{k}"]
+        kk = k.replace("mlp_base.0.hash_table", "encoding.hash_table") if k not in params else k
+        got = params[kk].grad
+        assert got is not None, k
+        rel = ((got.cpu().double() - ref.double()).norm() / (ref.double().norm() + 1e-30)).item()
+        assert rel <= 1e-3 or ref.abs().max() < 1e-9, (k, rel)
+        checked += 1
+    assert checked >= 10
+
+
+def test_full_frame_render_chunks_and_keys(golden):
+    g, model = build(golden, "separate", eval_num_rays_per_chunk=16)
+    model.eval()
+    R = g["origins"].shape[0]
+    rb = tn.RayBundle(origins=g["origins"].view(4, 8, 3).to(DEV), directions=g["directions"].view(4, 8, 3).to(DEV),
+                      pixel_area=torch.full((4, 8, 1), 1e-6, device=DEV),
+                      camera_indices=g["camera_indices"].view(4, 8, 1).to(DEV))
+    out = model.get_outputs_for_camera_ray_bundle(rb)
+    assert out["rgb"].shape == (4, 8, 3) and out["rgb_thermal"].shape == (4, 8, 1)
+    assert out["depth"].shape == (4, 8, 1) and out["accumulation_thermal"].shape == (4, 8, 1)
+    # per-ray outputs do not depend on the chunking (expected depth's clip is chunk-global by design)
+    assert max_abs(out["rgb"].view(R, 3), g["eval/rgb"]) <= 1e-3
+    assert max_abs(out["accumulation"].view(R, 1), g["eval/accumulation"]) <= 1e-3
+
+
+def test_half_table_mode_within_5e3(golden):
+    g, model = build(golden, "separate")
+    for m in model.modules():
+        if isinstance(m, tn.HashEncoding):
+            m.use_half_table = True
+    model.eval()
+    with torch.no_grad():
+        out = model(bundle(g))
+    for k in ("rgb", "rgb_thermal", "accumulation", "accumulation_thermal"):
+        assert max_abs(out[k], g[f"eval/{k}"]) <= 5e-3, (k, max_abs(out[k], g[f"eval/{k}"]))
+
+
+def test_model_vs_oracle_fresh_seed_default_sizes():
+    """default thermal-nerfacto sizes (T=2^19 main, 2^17 proposals), fresh weights, 64 rays, eval + train loss"""
+    torch.manual_seed(123)
+    cfg = tn.ThermalNerfactoModelConfig(density_mode="separate")
+    model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.endswith("hash_table"):
+                p.mul_(300.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV)
+    R = 64
+    gen = torch.Generator().manual_seed(5)
+    cams = (torch.arange(R // 4) * 8 // (R // 4)).repeat_interleave(4)[:, None]
+    o = torch.randn(R, 3, generator=gen) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=-1)
+    ocfg = oracle.OracleConfig(density_mode="separate", is_thermal_cameras=(0, 0, 0, 0, 1, 1, 1, 1))
+    model.eval()
+    with torch.no_grad():
+        out = model(tn.RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                                 camera_indices=cams.to(DEV)))
+        ref = oracle.thermal_nerfacto_forward(sd, ocfg, o, d, cams, training=False)
+    for k in ("rgb", "rgb_thermal", "accumulation", "accumulation_thermal", "expected_depth", "removal"):
+        assert max_abs(out[k], ref[k]) <= 1e-3, (k, max_abs(out[k], ref[k]))
