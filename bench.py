@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- thermal-nerfacto per-ray hot path: train rays/s (fwd+bwd) on B200, beside the CPU reference path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (N>1: launched by torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1]): ThermalNerfactoModel, density_mode=separate, default sizes
+(main grids 16 levels x 2^19 x 2, proposal grids 5 x 2^17 x 2, 256/96 proposal + 48 field samples), 4096 rays per GPU
+as 2x2 patches from 64 cameras (32 RGB + 32 thermal), seed 42 + rank.  One step = model forward, metrics + loss
+dict, backward (and, for N > 1, ONE flat NCCL all-reduce of all gradients).  `value` is measured with the batch
+already in HBM; `e2e` copies the batch from pinned host memory every step and reads the loss back.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_CAMERAS = 64
+RAYS_PER_GPU = 4096
+METRIC = "train rays/s (fwd+bwd), thermal-nerfacto"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--density-mode", default="separate", choices=["separate", "shared", "rgb_only"])
+    ap.add_argument("--log2-hashmap-size", type=int, default=19)
+    ap.add_argument("--init", choices=["trained", "reference"], default="trained",
+                    help="'trained': tables U(-0.5,0.5), density bias +2 (non-degenerate weights); 'reference': initialisers")
+    ap.add_argument("--half-tables", action="store_true", help="fp16 gather caches of the hash tables")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel time table to stderr")
+    return ap.parse_args()
+
+
+def make_batch(rays, seed, num_cams=NUM_CAMERAS):
+    """Patch-structured synthetic batch: groups of four rays = one 2x2 patch of one camera,
+    RGB cameras first."""
+    g = torch.Generator().manual_seed(seed)
+    patches = rays // 4
+    cam_of_patch = (torch.arange(patches) * num_cams) // patches
+    cams = cam_of_patch.repeat_interleave(4)[:, None]
+    centre = torch.randn(patches, 3, generator=g) * 0.3
+    origins = centre.repeat_interleave(4, 0) + torch.randn(rays, 3, generator=g) * 0.002
+    dirs = torch.nn.functional.normalize(torch.randn(patches, 3, generator=g), dim=-1).repeat_interleave(4, 0)
+    directions = torch.nn.functional.normalize(dirs + torch.randn(rays, 3, generator=g) * 0.002, dim=-1)
+    image = torch.rand(rays, 3, generator=g)
+    is_thermal = (cams[:, 0] >= num_cams // 2).float()
+    pixel_area = torch.full((rays, 1), 1e-6)
+    return dict(origins=origins, directions=directions, pixel_area=pixel_area, camera_indices=cams, image=image,
+                is_thermal=is_thermal)
+
+
+def build_model(args):
+    import nerfstudio_thermal_b200 as tn
+
+    torch.manual_seed(1234)  # identical replicas on every rank
+    cfg = tn.ThermalNerfactoModelConfig(density_mode=args.density_mode, log2_hashmap_size=args.log2_hashmap_size)
+    model = cfg.setup(num_train_data=NUM_CAMERAS, metadata={"is_thermal": [0] * (NUM_CAMERAS // 2) + [1] * (NUM_CAMERAS // 2)})
+    if args.init == "trained":
+        with torch.no_grad():
+            for k, p in model.named_parameters():
+                if k.endswith("hash_table"):
+                    p.uniform_(-0.5, 0.5)
+            for f in [model.field] + ([model.field_thermal] if args.density_mode == "separate" else []):
+                f.mlp_base.model[1].layers[-1].bias[0] += 2.0
+    return model
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def algorithmic_bytes_per_point(L, F=2, table_bytes=4, bwd=False, dx=False):
+    """encode fwd = 12 + L*8*F*b_t + L*F*4 ; bwd = 12 + L*F*4 + L*8*F*4 (+12 with dL/dx)."""
+    if not bwd:
+        return 12 + L * 8 * F * table_bytes + L * F * 4
+    return 12 + L * F * 4 + L * 8 * F * 4 + (12 if dx else 0)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def oracle_step(sd, cfg, batch, jit):
+    import oracle
+
+    for v in sd.values():
+        if v.requires_grad:
+            v.grad = None
+    out = oracle.thermal_nerfacto_forward(sd, cfg, batch["origins"], batch["directions"], batch["camera_indices"],
+                                          training=True, jitters=jit[:3], jitters_thermal=jit[3:])
+    losses = oracle.thermal_nerfacto_losses(sd, cfg, out, batch["image"], batch["is_thermal"], training=True)
+    total = sum(losses.values())
+    total.backward()
+    return float(total)
+
+
+def oracle_setup(args):
+    import oracle
+
+    model = build_model(args)
+    sd = {}
+    for k, v in model.state_dict().items():
+        v = v.detach().clone()
+        if v.dtype == torch.float32 and v.numel() > 6 and not k.endswith("aabb"):
+            v.requires_grad_(True)
+        sd[k] = v
+    for k in list(sd):  # the aliased proposal table is one tensor
+        if k.endswith("encoding.hash_table"):
+            sd[k] = sd[k.replace("encoding.hash_table", "mlp_base.0.hash_table")]
+    half = NUM_CAMERAS // 2
+    cfg = oracle.OracleConfig(density_mode=args.density_mode, log2_hashmap_size=args.log2_hashmap_size,
+                              is_thermal_cameras=tuple([0] * half + [1] * half))
+    return sd, cfg
+
+
+def time_oracle(args, rays, steps, warmup):
+    torch.set_num_threads(os.cpu_count())
+    sd, cfg = oracle_setup(args)
+    times = []
+    for i in range(warmup + steps):
+        batch = make_batch(rays, 42 + i)
+        jit = [torch.rand(rays, 1) for _ in range(6)]
+        t0 = time.perf_counter()
+        oracle_step(sd, cfg, batch, jit)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    # bounded sample: a first full-size step decides how many rays fit the time budget of the whole run
+    t_probe = time_oracle(args, args.rays, 1, 0)
+    budget = 150.0
+    total_steps = args.steps + args.warmup
+    rays = args.rays
+    if t_probe * total_steps > budget:
+        rays = max(256, int(args.rays * budget / (t_probe * total_steps)) // 64 * 64)
+    sec = time_oracle(args, rays, args.steps, args.warmup)
+    value = rays / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"thermal-nerfacto train step fwd+loss+bwd, density_mode={args.density_mode}, "
+                               f"T=2^{args.log2_hashmap_size}, CPU torch ops (oracle port of implementation='torch')",
+                   "rays_per_step": rays, "init": args.init},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps of {rays} rays (full batch is {args.rays}); probe step of "
+                                   f"{args.rays} rays took {t_probe:.2f} s"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import _lib, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
+
+    model = build_model(args).to(dev).train()
+    if args.half_tables:
+        for m in model.modules():
+            if isinstance(m, tn.HashEncoding):
+                m.use_half_table = True
+    grads = parallel.FlatGradBuffer.from_param_groups(model.get_param_groups(), device=dev)
+    grads.attach_sinks(model)
+    R = args.rays
+    host = {k: v.pin_memory() for k, v in make_batch(R, parallel.rank_seed(42, rank)).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def step(batch):
+        grads.zero_()
+        rb = tn.RayBundle(origins=batch["origins"], directions=batch["directions"], pixel_area=batch["pixel_area"],
+                          camera_indices=batch["camera_indices"])
+        _, losses, _ = model.get_train_loss_dict(rb, batch)
+        total = sum(losses.values())
+        total.backward()
+        grads.all_reduce_mean()
+        return total
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    _lib.STATS.reset()
+    ms_total = timed(lambda: step(resident), args.steps)
+    launches = _lib.STATS.count
+    # end to end: pinned host batch -> device every step, loss read back every step
+    def e2e_step():
+        batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(step(batch))  # .item(): device->host read of the loss
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks.stop_flag = True
+    clocks.join()
+
+    # instrumented pass of the same steps: per-kernel CUDA-event durations (roofline of the dominant kernel)
+    _lib.STATS.reset(timing=True)
+    for _ in range(args.steps):
+        step(resident)
+    torch.cuda.synchronize()
+    table = _lib.STATS.summary()
+    _lib.STATS.reset()
+
+    ms_step = ms_total / args.steps
+    value = world * R / (ms_step * 1e-3)
+    e2e_value = world * R / (ms_e2e / args.steps * 1e-3)
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        kern_ms = sum(ms for _, ms in table.values()) / args.steps
+        enc = {k: v for k, v in table.items() if k.startswith("tn_hash_encode")}
+        dom_tag, (dom_n, dom_ms) = max(enc.items(), key=lambda kv: kv[1][1])
+        L = 16 if "[L16" in dom_tag else 5
+        bwd = "bwd" in dom_tag
+        tb = 2 if (args.half_tables and not bwd) else 4
+        pts = {16: R * 48, 5: R * 256}  # points per launch (proposal level 0: 256, level 1: 96 -> weighted below)
+        n_per_step = dom_n / args.steps
+        if L == 16:
+            pts_per_launch = R * 48
+        else:
+            pts_per_launch = R * (256 + 96) / 2.0  # the two proposal levels share the tag; average launch
+        alg = algorithmic_bytes_per_point(L, 2, tb, bwd, dx="dx" in dom_tag) * pts_per_launch
+        avg_ms = dom_ms / dom_n
+        achieved = alg / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom_tag, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "launches_per_step": n_per_step, "avg_launch_ms": avg_ms,
+                    "algorithmic_bytes_per_launch": alg, "share_of_kernel_time": dom_ms / args.steps / kern_ms}
+        if args.profile_kernels:
+            for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+                print(f"{k:58s} {n / args.steps:6.1f} launches/step {ms / args.steps:8.3f} ms/step", file=sys.stderr)
+            print(f"sum of libtn_b200 kernels {kern_ms:.3f} ms/step; step {ms_step:.3f} ms", file=sys.stderr)
+        line = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if not args.half_tables else "f32 (f16 table gathers)",
+            "data": "synthetic",
+            "config": {"workload": f"thermal-nerfacto train step (fwd + loss + bwd), density_mode={args.density_mode}, "
+                                   f"{R} rays/GPU, main grids 16x2^{args.log2_hashmap_size}x2, proposal grids 5x2^17x2, "
+                                   "samples 256/96+48",
+                       "rays_per_gpu": R, "init": args.init, "parallelism": f"dp{world}",
+                       "l2": "no explicit flush: tables + gradient buffers touched every step (~310 MB) exceed the 126 MB L2",
+                       "optimizer_step": "not in the timed region (metric is fwd+bwd)"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+            "kernel_ms_per_step": kern_ms, "roofline": roofline, "clocks": clocks.result(),
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            t0 = time.perf_counter()
+            t_small = time_oracle(args, 1024, 1, 0)  # page in / warm allocator
+            sec = time_oracle(args, R, 1, 0)
+            line["cpu_baseline"] = {"value": R / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"1 step of the full {R}-ray batch ({sec:.2f} s) after a 1024-ray warm-up "
+                                              f"step ({t_small:.2f} s); total {time.perf_counter() - t0:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -71,10 +71,45 @@ def load():
     return lib
 
 
-def call(name, *args):
+class LaunchStats:
+    """Launch counter and optional per-launch CUDA-event timing of the C-ABI calls (bench.py / profiling).
+
+    `count` always counts launches.  With `timing=True` every call is bracketed by two events on the current
+    stream; `summary()` (after a synchronize) returns {tag: (launches, total_ms)} where tag = entry point name
+    plus the caller-supplied shape tag."""
+
+    def __init__(self):
+        self.count = 0
+        self.timing = False
+        self.events = []
+        self.tag = ""
+
+    def reset(self, timing=False):
+        self.count, self.timing, self.events = 0, timing, []
+
+    def summary(self):
+        out = {}
+        for tag, e0, e1 in self.events:
+            n, ms = out.get(tag, (0, 0.0))
+            out[tag] = (n + 1, ms + e0.elapsed_time(e1))
+        return out
+
+
+STATS = LaunchStats()
+
+
+def call(name, *args, tag=""):
     """Invoke an int-returning entry point; map non-zero codes to TnKernelError."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    STATS.count += 1
+    if STATS.timing:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        STATS.events.append((f"{name}{tag}", e0, e1))
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise TnKernelError(f"{name} failed ({rc}): {lib.tn_last_error_string().decode()}")
 

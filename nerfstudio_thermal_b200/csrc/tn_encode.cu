@@ -253,10 +253,16 @@ __global__ void __launch_bounds__(kPts) hash_bwd_kernel(const float* __restrict_
     bool issue = valid;
     if (l < n_coarse) {  // warp-uniform branch: segmented reduction over runs of equal cells
       const uint64_t key = valid ? c.key : ~0ull;
+      // run id = number of run heads at or below this lane: monotone, so equal ids at distance d mean the
+      // whole span is one run (equal KEYS would not: a ray can leave and re-enter a cell, and callers may
+      // pass unordered points)
+      const uint64_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = (lane == 0) || (pkey != key);
+      const int run = __popc(__ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane)));
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t okey = __shfl_down_sync(0xffffffffu, key, d);
-        const bool take = (lane + d < 32) && (okey == key);
+        const int orun = __shfl_down_sync(0xffffffffu, run, d);
+        const bool take = (lane + d < 32) && (orun == run);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
 #pragma unroll
@@ -265,8 +271,7 @@ __global__ void __launch_bounds__(kPts) hash_bwd_kernel(const float* __restrict_
             if (take) gc[k][j] += o;
           }
       }
-      const uint64_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
-      issue = valid && (lane == 0 || pkey != key);
+      issue = valid && head;
     }
     if (issue) {
 #pragma unroll
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(kPts) hash_bwd_kernel(const float* __restrict_
 
 static int check_common(const float* x, const void* table, const float* scales_host, int64_t N, int L, int F,
                         int log2_T, int table_dtype) {
-  TN_REQUIRE(x && table && scales_host, TN_EINVAL, "hash_encode: null pointer");
+  TN_REQUIRE((x || N == 0) && table && scales_host, TN_EINVAL, "hash_encode: null pointer");
   TN_REQUIRE(N >= 0 && N < (int64_t(1) << 40), TN_EINVAL, "hash_encode: bad N=%lld", (long long)N);
   TN_REQUIRE(L >= 1 && L <= TN_MAX_LEVELS, TN_EINVAL, "hash_encode: L=%d out of range [1,%d]", L, TN_MAX_LEVELS);
   TN_REQUIRE(F == 1 || F == 2 || F == 4 || F == 8, TN_EINVAL, "hash_encode: F=%d not in {1,2,4,8}", F);
@@ -341,7 +346,7 @@ extern "C" int tn_hash_encode_fwd(const float* x, const void* table, int table_d
                                   int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
-  TN_REQUIRE(out, TN_EINVAL, "hash_encode_fwd: out is null");
+  TN_REQUIRE(out || N == 0, TN_EINVAL, "hash_encode_fwd: out is null");
   TN_REQUIRE(aligned(out, 16), TN_EALIGN, "hash_encode_fwd: out must be 16-byte aligned");
   TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_fwd: L*F=%d too large", L * F);
   if (N == 0) return TN_OK;
@@ -361,7 +366,7 @@ extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_d
                                   void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
-  TN_REQUIRE(dy && dtable, TN_EINVAL, "hash_encode_bwd: null pointer");
+  TN_REQUIRE((dy || N == 0) && dtable, TN_EINVAL, "hash_encode_bwd: null pointer");
   TN_REQUIRE(aligned(dy, 16) && aligned(dtable, 16), TN_EALIGN, "hash_encode_bwd: dy/dtable must be 16-byte aligned");
   TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_bwd: L*F=%d too large", L * F);
   if (N == 0) return TN_OK;

@@ -429,8 +429,8 @@ extern "C" int tn_mlp_fwd(const float* x, int64_t N, int in_dim, int width, int 
   MlpParams prm = {};
   int rc = fill_params(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
-  TN_REQUIRE(x && y && N >= 0, TN_EINVAL, "mlp_fwd: bad x/y/N");
   if (N == 0) return TN_OK;
+  TN_REQUIRE(x && y && N > 0, TN_EINVAL, "mlp_fwd: bad x/y/N");
   cudaStream_t st = (cudaStream_t)stream;
   TN_DISPATCH(launch_fwd, x, N, prm, y, st);
 }
@@ -441,7 +441,8 @@ extern "C" int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim
   MlpParams prm = {};
   int rc = fill_params(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
-  TN_REQUIRE(x && dy && N >= 0 && dw_host_ptrs && db_host_ptrs, TN_EINVAL, "mlp_bwd: bad x/dy/N/grad tables");
+  if (N == 0) return TN_OK;
+  TN_REQUIRE(x && dy && N > 0 && dw_host_ptrs && db_host_ptrs, TN_EINVAL, "mlp_bwd: bad x/dy/N/grad tables");
   for (int i = 0; i < n_layers; ++i) {
     TN_REQUIRE(dw_host_ptrs[i] && db_host_ptrs[i], TN_EINVAL, "mlp_bwd: null grad pointer for layer %d", i);
     prm.dw[i] = dw_host_ptrs[i];

@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) weights_fwd_kernel(const fl
     const int s = base + lane;
     const float dd = s < S ? __ldg(deltas + r * S + s) * __ldg(sigma + r * S + s) : 0.f;
     const double incl = warp_incl_scan((double)dd, lane) + carry;
-    // exclusive cumsum, rounded to float like torch.cumsum's output, then exp(-.)
-    const float excl = (float)(incl - (double)dd);
+    // exclusive cumsum (shifted inclusive scan: subtracting dd back would turn inf into nan), rounded to
+    // float like torch.cumsum's output, then exp(-.)
+    const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    const float excl = (float)(lane == 0 ? carry : prev);
     if (s < S) {
       const float alpha = 1.f - expf(-dd);
       const float trans = expf(-excl);
@@ -65,7 +67,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) weights_bwd_kernel(const fl
     const int s = base + lane;
     const float dd = s < S ? __ldg(deltas + r * S + s) * __ldg(sigma + r * S + s) : 0.f;
     const double incl = warp_incl_scan((double)dd, lane) + carry;
-    if (s < S) tr[s] = expf(-(float)(incl - (double)dd));
+    const double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (s < S) tr[s] = expf(-(float)(lane == 0 ? carry : prev));
     carry = __shfl_sync(0xffffffffu, incl, 31);
   }
   __syncwarp();

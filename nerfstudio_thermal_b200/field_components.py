@@ -61,6 +61,8 @@ class HashEncoding(Encoding):
         self.use_half_table = False
         self._half_cache: Optional[Tensor] = None
         self._half_version = -1
+        # optional accumulation target for the table gradient (set by parallel.FlatGradBuffer.attach_sinks)
+        self.grad_sink: Optional[Tensor] = None
 
     def get_out_dim(self) -> int:
         return self.num_levels * self.features_per_level
@@ -93,7 +95,7 @@ class HashEncoding(Encoding):
     def forward(self, in_tensor: Tensor) -> Tensor:
         assert in_tensor.shape[-1] == 3
         flat = in_tensor.reshape(-1, 3)
-        out = ops.hash_encode(flat, self.hash_table, self.spec, self._half())
+        out = ops.hash_encode(flat, self.hash_table, self.spec, self._half(), self.grad_sink)
         return out.view(*in_tensor.shape[:-1], self.get_out_dim())
 
 

