@@ -91,6 +91,19 @@ int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width
                const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
                float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
 
+/* The same MLPs on the tcgen05 tensor cores: 128-point tiles (UMMA M=128), accumulators in TMEM, operands as
+ * bf16 hi+lo pairs (three MMAs per product, fp32 accumulate: ~2e-5 relative error).  Same arguments and
+ * semantics as tn_mlp_fwd. */
+int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
+                  const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
+                  void* stream);
+/* Backward on the tensor cores as well (same arguments and semantics as tn_mlp_bwd): forward recomputed per
+ * tile, dH = dZ.W and dW^T += A^T.dZ as tcgen05 MMAs, dW/db accumulators resident in TMEM across the tiles of
+ * a persistent CTA and flushed once with atomics. */
+int tn_mlp_tc_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width, int out_dim, int n_layers,
+                  const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
+                  float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
+
 /* Real spherical-harmonics basis, 4 levels (16 components).
  *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */
 int tn_sh4(const float* d, int64_t N, float* out, void* stream);

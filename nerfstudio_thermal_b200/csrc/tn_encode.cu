@@ -97,13 +97,17 @@ __device__ __forceinline__ int tile_pos(int row, int l, int L, int F) {
   return (row * L + r) * F;
 }
 
+constexpr int kLevelBatch = 2;  // levels whose 8-corner gathers are issued back to back (16 loads in flight/thread)
+
 template <int F, bool HALF, bool WRITE_IDX>
-__global__ void __launch_bounds__(kPts) hash_fwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
-                                                        LevelScales sc, int64_t N, int L, int log2T,
-                                                        float* __restrict__ out, int32_t* __restrict__ idx_out) {
+__global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
+                                                           LevelScales sc, int64_t N, int L, int log2T,
+                                                           float* __restrict__ out, int32_t* __restrict__ idx_out) {
   extern __shared__ float4 smem4[];
+  __shared__ float s_scale[TN_MAX_LEVELS];
   float* tile = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x;
+  if (tid < TN_MAX_LEVELS) s_scale[tid] = sc.s[tid];
   const int64_t base_pt = (int64_t)blockIdx.x * kPts;
   const int64_t p = base_pt + tid;
   const bool valid = p < N;
@@ -113,32 +117,49 @@ __global__ void __launch_bounds__(kPts) hash_fwd_kernel(const float* __restrict_
     x0 = __ldg(x + 3 * p); x1 = __ldg(x + 3 * p + 1); x2 = __ldg(x + 3 * p + 2);
   }
   const int rowmod = tid % L;
-#pragma unroll 2
-  for (int l = 0; l < L; ++l) {
-    const Cell c = locate(x0, x1, x2, sc.s[l], mask, (uint32_t)l * T);
-    float f[8][F];
+  __syncthreads();
+#pragma unroll 1
+  for (int l0 = 0; l0 < L; l0 += kLevelBatch) {
+    // phase 1: all corner rows of the batch, phase 2: all gathers, phase 3: blends.  Keeping the phases apart
+    // is what puts 8*kLevelBatch independent loads in flight per thread (the gathers are latency-bound).
+    Cell c[kLevelBatch];
+    float f[kLevelBatch][8][F];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
-    if constexpr (WRITE_IDX) {
-      if (valid) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) idx_out[(p * L + l) * 8 + k] = (int32_t)c.idx[k];
-      }
+    for (int b = 0; b < kLevelBatch; ++b) {
+      const int l = min(l0 + b, L - 1);
+      c[b] = locate(x0, x1, x2, s_scale[l], mask, (uint32_t)l * T);
     }
-    const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
-    int r = l + rowmod;
-    if (r >= L) r -= L;
-    float* dst = tile + (tid * L + r) * F;
 #pragma unroll
-    for (int j = 0; j < F; ++j) {
-      // encodings.py:449-459, same association
-      const float f03 = f[0][j] * c.ox + f[3][j] * mx;
-      const float f12 = f[1][j] * c.ox + f[2][j] * mx;
-      const float f56 = f[5][j] * c.ox + f[6][j] * mx;
-      const float f47 = f[4][j] * c.ox + f[7][j] * mx;
-      const float f0312 = f03 * c.oy + f12 * my;
-      const float f4756 = f47 * c.oy + f56 * my;
-      dst[j] = f0312 * c.oz + f4756 * mz;
+    for (int b = 0; b < kLevelBatch; ++b)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c[b].idx[k], f[b][k]);
+#pragma unroll
+    for (int b = 0; b < kLevelBatch; ++b) {
+      const int l = l0 + b;
+      if (l < L) {
+        if constexpr (WRITE_IDX) {
+          if (valid) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx_out[(p * L + l) * 8 + k] = (int32_t)c[b].idx[k];
+          }
+        }
+        const float ox = c[b].ox, oy = c[b].oy, oz = c[b].oz;
+        const float mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
+        int r = l + rowmod;
+        if (r >= L) r -= L;
+        float* dst = tile + (tid * L + r) * F;
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+          // encodings.py:449-459, same association
+          const float f03 = f[b][0][j] * ox + f[b][3][j] * mx;
+          const float f12 = f[b][1][j] * ox + f[b][2][j] * mx;
+          const float f56 = f[b][5][j] * ox + f[b][6][j] * mx;
+          const float f47 = f[b][4][j] * ox + f[b][7][j] * mx;
+          const float f0312 = f03 * oy + f12 * my;
+          const float f4756 = f47 * oy + f56 * my;
+          dst[j] = f0312 * oz + f4756 * mz;
+        }
+      }
     }
   }
   __syncthreads();
@@ -174,7 +195,7 @@ __device__ __forceinline__ void red_row(float* __restrict__ dtable, uint32_t row
 }
 
 template <int F, bool HALF, bool NEED_DX>
-__global__ void __launch_bounds__(kPts) hash_bwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
+__global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
                                                         LevelScales sc, const float* __restrict__ dy, int64_t N, int L,
                                                         int log2T, int n_coarse, float* __restrict__ dtable,
                                                         float* __restrict__ dx) {

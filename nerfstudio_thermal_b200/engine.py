@@ -1,0 +1,99 @@
+"""Step runners for the hot path: a CUDA-graph-captured train step and a sharded full-frame renderer.
+
+The per-step work of thermal-nerfacto at 4096 rays is ~150 small launches (kernels of this library plus
+torch's elementwise glue and autograd bookkeeping); issued eagerly the GPU idles between them.  On B200 the
+idiomatic fix is a CUDA graph: the whole forward + loss + backward is captured once on static input buffers
+and replayed with one launch per step.  Everything on the path is capture-safe by construction -- the C ABI
+never allocates or synchronises, jitter comes from torch's graph-safe Philox generator, and the per-ray
+losses avoid boolean indexing.
+
+Mirrors what `Trainer.train_iteration` + `VanillaPipeline.get_train_loss_dict` drive in the reference
+(engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304), minus optimizer/scheduler/GradScaler (unchanged
+host code in the reference; the optimizer reads the gradients from `grads.flat` / `param.grad`).
+"""
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+
+from . import parallel
+from .model import ThermalNerfactoModel
+from .rays import RayBundle
+
+BATCH_KEYS = ("origins", "directions", "pixel_area", "camera_indices", "image", "is_thermal")
+
+
+class GraphedTrainStep:
+    """forward + metrics + loss dict + backward (+ flat gradient all-reduce) for a fixed batch shape.
+
+    step(batch) copies the batch (host or device tensors) into static device buffers, replays the captured
+    graph and returns the scalar total loss tensor (device).  `losses` holds the per-term loss tensors of the
+    last step; gradients are in `grads.flat` (parameters' .grad are views into it).
+    """
+
+    def __init__(self, model: ThermalNerfactoModel, example_batch: Dict[str, Tensor], use_graph: bool = True,
+                 warmup: int = 3, group=None):
+        self.model = model
+        self.device = model.device
+        assert self.device.type == "cuda", "the hot path runs on CUDA only (no CPU fallback)"
+        self.group = group
+        self.grads = parallel.FlatGradBuffer.from_param_groups(model.get_param_groups(), device=self.device)
+        self.grads.attach_sinks(model)
+        self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
+        self._load(example_batch)
+        self.losses: Dict[str, Tensor] = {}
+        self.total: Optional[Tensor] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        model.train()
+        if use_graph:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(max(warmup, 2)):  # allocator / cudaFuncSetAttribute / host-constant caches warm
+                    self._eager()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._eager()
+            torch.cuda.synchronize(self.device)
+
+    def _load(self, batch: Dict[str, Tensor]) -> None:
+        for k in BATCH_KEYS:
+            self.static[k].copy_(batch[k], non_blocking=True)
+
+    def _eager(self) -> None:
+        s = self.static
+        self.grads.zero_()
+        bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
+                           camera_indices=s["camera_indices"])
+        _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
+        self.total = sum(self.losses.values())
+        self.total.backward()
+
+    def step(self, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
+        if batch is not None:
+            self._load(batch)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._eager()
+        self.grads.all_reduce_mean(self.group)
+        return self.total
+
+
+@torch.no_grad()
+def render_rays_sharded(model: ThermalNerfactoModel, bundle: RayBundle, rank: int = 0, world: int = 1,
+                        keys: Optional[List[str]] = None) -> Dict[str, Tensor]:
+    """Zero-communication full-frame render: this rank evaluates its contiguous block of the reference's chunks
+    (models/base_model.py:177-206) of a flattened ray bundle and returns the outputs for those rays only
+    (the caller concatenates rank outputs in rank order)."""
+    model.eval()
+    flat = bundle.flatten()
+    outs: Dict[str, List[Tensor]] = {}
+    for start, end in parallel.shard_chunks(len(flat), model.config.eval_num_rays_per_chunk, rank, world):
+        res = model(flat[start:end].to(model.device))
+        for k, v in res.items():
+            if torch.is_tensor(v) and (keys is None or k in keys):
+                outs.setdefault(k, []).append(v)
+    return {k: torch.cat(v) for k, v in outs.items()}

@@ -153,6 +153,10 @@ def contract_points(p: Tensor) -> Tuple[Tensor, Tensor]:
 
 
 # ----------------------------------------------------------------------------------- MLP
+# "tc": tcgen05 tensor-core kernels (bf16x3 split precision, fp32 accumulate);  "simt": exact-fp32 FFMA kernels
+MLP_BACKEND = {"fwd": "tc", "bwd": "tc"}
+
+
 class _MlpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, out_act, *wb):
@@ -162,7 +166,8 @@ class _MlpFn(torch.autograd.Function):
         n, in_dim = x.shape
         width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
         y = torch.empty((n, out_dim), device=x.device)
-        call("tn_mlp_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
+        fwd = "tn_mlp_tc_fwd" if MLP_BACKEND["fwd"] == "tc" else "tn_mlp_fwd"
+        call(fwd, ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
              stream(), tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
         ctx.out_act = out_act
         ctx.save_for_backward(x, *ws, *bs)
@@ -179,7 +184,8 @@ class _MlpFn(torch.autograd.Function):
         dws = [torch.zeros_like(w) for w in ws]
         dbs = [torch.zeros_like(b) for b in bs]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        call("tn_mlp_bwd", ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
+        bwd = "tn_mlp_tc_bwd" if MLP_BACKEND["bwd"] == "tc" else "tn_mlp_bwd"
+        call(bwd, ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
              ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(),
              tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
         grads = []
@@ -306,7 +312,8 @@ class _RenderFn(torch.autograd.Function):
         if want_depth:
             med = torch.empty((r, 1), device=dev)
             exp = torch.empty((r, 1), device=dev)
-            minmax = torch.tensor([float("inf"), float("-inf")], device=dev)
+            # cached device constant + clone: no host->device copy at call time (CUDA-graph capture safe)
+            minmax = _host_linspace(("minmax",), lambda: torch.tensor([float("inf"), float("-inf")]), dev).clone()
         bg_arr = float_array(bg) if bg is not None else None
         call("tn_render_fwd", ptr(weights), ptr(colour_c), ptr(starts_c), ptr(ends_c), r, s, c, bg_mode, bg_arr,
              int(eval_mode), ptr(rgb), ptr(acc), ptr(med), ptr(exp), ptr(minmax), stream())
