@@ -91,18 +91,20 @@ int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width
                const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
                float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
 
-/* The same MLPs on the tcgen05 tensor cores: 128-point tiles (UMMA M=128), accumulators in TMEM, operands as
- * bf16 hi+lo pairs (three MMAs per product, fp32 accumulate: ~2e-5 relative error).  Same arguments and
- * semantics as tn_mlp_fwd. */
+/* The same MLPs on the tcgen05 tensor cores: 128-point tiles (UMMA M=128), accumulators in TMEM.  Operands
+ * are sums of bf16 terms, products a few MMAs accumulated in fp32: three terms / six MMAs in the forward
+ * (fp32-faithful pre-activations, so ReLU masks agree with the fp32 reference), two terms / three MMAs in the
+ * backward (~2e-5 relative).  Arguments as tn_mlp_fwd, plus:
+ * relu_mask_out: NULL, or uint32[N, n_layers-1, max(1,width/32)] receiving bit j of hidden layer l = (z_lj > 0). */
 int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
                   const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
-                  void* stream);
-/* Backward on the tensor cores as well (same arguments and semantics as tn_mlp_bwd): forward recomputed per
- * tile, dH = dZ.W and dW^T += A^T.dZ as tcgen05 MMAs, dW/db accumulators resident in TMEM across the tiles of
- * a persistent CTA and flushed once with atomics. */
-int tn_mlp_tc_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width, int out_dim, int n_layers,
-                  const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
-                  float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
+                  uint32_t* relu_mask_out, void* stream);
+/* Backward on the tensor cores as well (arguments as tn_mlp_bwd): activations recomputed per tile, dH = dZ.W
+ * and dW^T += A^T.dZ as tcgen05 MMAs, dW/db accumulators resident in TMEM across the tiles of a persistent CTA
+ * and flushed once with atomics.  relu_mask: the forward's masks (NULL: gate on the recomputed activations). */
+int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim, int width,
+                  int out_dim, int n_layers, const float* const* w_host_ptrs, const float* const* b_host_ptrs,
+                  int out_act, float* dx, float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
 
 /* Real spherical-harmonics basis, 4 levels (16 components).
  *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */

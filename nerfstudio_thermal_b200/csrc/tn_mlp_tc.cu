@@ -5,10 +5,15 @@
 // thread-per-point loop over the row that `tcgen05.ld.32x32b` hands to that thread.  Hidden activations go
 // TMEM -> registers -> shared memory (as the next layer's A operand) and never reach HBM.
 //
-// Precision: operands are bf16 PAIRS (hi + lo, tn_tc.cuh) and each product is three MMAs (hi*hi + lo*hi +
-// hi*lo) accumulated in fp32, i.e. ~16 mantissa bits per factor (relative error ~2e-5) -- this keeps the
-// "fp32" parity bar (1e-3) with a wide margin while running on the bf16 tensor pipe; the MLPs are <1 % of the
-// step's time either way, the point of the tensor cores here is that hidden layers cost no SIMT issue slots.
+// Precision.  Operands are sums of bf16 terms and a product is a few MMAs accumulated in fp32 by the tensor core:
+//   * forward: THREE terms per operand (x = x1+x2+x3, 24 mantissa bits), six MMAs per product (all term pairs
+//     down to 2^-16): pre-activations are fp32-faithful, so the ReLU masks agree with the fp32 reference (a
+//     2^-16 forward flips enough units at the kink to push gradients past the 1e-3 parity bar).  The forward
+//     optionally stores the ReLU masks (W bits per point and hidden layer);
+//   * backward: two terms, three MMAs (hi*hi + lo*hi + hi*lo, ~2e-5 relative) for the recomputed activations,
+//     dH = dZ.W and dW^T += A^T.dZ; ReLU gating uses the forward's masks.
+// The MLPs are a few per cent of the step either way; what the tensor cores buy is that hidden layers cost no
+// SIMT issue slots and no shared-memory operand traffic.
 //
 // The reference math: field_components/mlp.py:159-178 (nn.Linear stack, ReLU, optional Sigmoid).
 #include "tn_tc.cuh"
@@ -19,6 +24,7 @@ using namespace tc;
 
 constexpr int TP = 128;      // points per tile == threads per CTA == UMMA M
 constexpr int OUTP = 16;     // padded width of the output layer (UMMA N must be a multiple of 16 at M = 128)
+constexpr int CH = TP * 16;  // bytes of one chunk column of an activation tile (8 features x 128 rows)
 
 struct TcParams {
   const float* w[3];
@@ -28,58 +34,73 @@ struct TcParams {
   int in_dim, out_dim, out_act;
 };
 
-// nn.Linear weight [n_real][k_real] (row-major fp32) -> hi/lo operand tiles with NP rows, KP features
-template <int NP, int KP>
-__device__ __forceinline__ void load_weight_split(const float* __restrict__ w, int n_real, int k_real, uint8_t* hi,
-                                                  uint8_t* lo) {
+// x = t[0] + t[1] + ... (bf16 terms, each the rounding of what the previous ones left)
+template <int NT>
+__device__ __forceinline__ void split_terms(float x, __nv_bfloat16 (&t)[NT]) {
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    t[i] = __float2bfloat16_rn(x);
+    x -= __bfloat162float(t[i]);
+  }
+}
+
+// 8 consecutive features (one 16-byte chunk) of row r into the NT term tiles of an operand with `rows` rows
+template <int NT>
+__device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride, int rows, int chunk, int r,
+                                                  const float (&v)[8]) {
+  __nv_bfloat16 t[NT][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat16 s[NT];
+    split_terms<NT>(v[i], s);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) t[k][i] = s[k];
+  }
+  const size_t off = (size_t)chunk * rows * 16 + (size_t)r * 16;
+#pragma unroll
+  for (int k = 0; k < NT; ++k)
+    *reinterpret_cast<uint4*>(base + (size_t)k * term_stride + off) = *reinterpret_cast<const uint4*>(t[k]);
+}
+
+// nn.Linear weight [n_real][k_real] (row-major fp32) -> NT operand tiles with NP rows, KP features
+template <int NP, int KP, int NT>
+__device__ __forceinline__ void load_weight_terms(const float* __restrict__ w, int n_real, int k_real, uint8_t* base) {
   for (int i = threadIdx.x; i < NP * KP; i += TP) {
     const int n = i / KP, k = i - n * KP;
     const float v = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
+    __nv_bfloat16 s[NT];
+    split_terms<NT>(v, s);
     const size_t off = (size_t)(k >> 3) * NP * 16 + (size_t)n * 16 + (k & 7) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(hi + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(lo + off) = l;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) *reinterpret_cast<__nv_bfloat16*>(base + (size_t)t * NP * KP * 2 + off) = s[t];
   }
 }
 
-// D[128 x N] (+)= A[128 x K] * B[N x K]^T with split operands: 3 * K/16 MMAs, issued by ONE thread
-template <int N, int K>
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+// D[128 x N] = A[128 x K] * B[N x K]^T, both K-major, NT-term operands: all term pairs (i,j) with i+j < NT
+template <int N, int K, int NT>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_base, uint32_t a_term, uint32_t b_base) {
   constexpr uint32_t idesc = instr_desc_bf16(TP, N, false, false);
+  constexpr uint32_t b_term = N * K * 2;
   uint32_t acc = 0;
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const uint32_t a = (s == 1) ? a_lo : a_hi;
-    const uint32_t b = (s == 2) ? b_lo : b_hi;
+  for (int i = 0; i < NT; ++i)
 #pragma unroll
-    for (int k = 0; k < K / 16; ++k) {
-      // K-major tiles: chunk stride (LBO) = rows*16 bytes, 8-row group stride (SBO) = 128 bytes
-      const uint64_t ad = smem_desc(a + k * 2 * (TP * 16), TP * 16, 128);
-      const uint64_t bd = smem_desc(b + k * 2 * (N * 16), N * 16, 128);
-      mma_bf16(tmem_d, ad, bd, idesc, acc);
-      acc = 1;
-    }
-  }
+    for (int j = 0; j < NT - i; ++j)
+#pragma unroll
+      for (int k = 0; k < K / 16; ++k) {
+        // K-major tiles: chunk stride (LBO) = rows*16 bytes, 8-row group stride (SBO) = 128 bytes
+        const uint64_t ad = smem_desc(a_base + i * a_term + k * 2 * CH, CH, 128);
+        const uint64_t bd = smem_desc(b_base + j * b_term + k * 2 * (N * 16), N * 16, 128);
+        mma_bf16(tmem_d, ad, bd, idesc, acc);
+        acc = 1;
+      }
 }
 
-template <int IN, int W, int NL>
-struct TcSmem {
-  static constexpr int w1 = 0;                                   // hi, then lo
-  static constexpr int w2 = w1 + 2 * IN * W * 2;
-  static constexpr int w3 = w2 + (NL == 3 ? 2 * W * W * 2 : 0);
-  static constexpr int bias = w3 + 2 * W * OUTP * 2;             // fp32: b1[W] b2[W] b3[OUTP]
-  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // A0 hi, lo : IN*256 bytes each
-  static constexpr int h = a0 + 2 * IN * TP * 2;                 // H hi, lo  : W*256 bytes each (also the fp32 stage)
-  static constexpr int stage_bytes = TP * 65 * 4;                // fp32 [128][in_dim|1] input staging
-  static constexpr int h_bytes = (2 * W * TP * 2 > stage_bytes) ? 2 * W * TP * 2 : stage_bytes;
-  static constexpr int bar = h + h_bytes;                        // mbarrier (8 B) + tmem slot (4 B)
-  static constexpr int total = bar + 16;
-};
-
-template <int W>
-__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* h_hi,
-                                                uint8_t* h_lo, int row) {
+// hidden layer epilogue: TMEM row -> +bias, ReLU -> NT-term operand tile of the next layer (+ optional mask bits)
+template <int W, int NT>
+__device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* h_base,
+                                                int h_term, int row, uint32_t* __restrict__ mask_words) {
+  uint32_t bits = 0;
 #pragma unroll
   for (int c0 = 0; c0 < W; c0 += 16) {
     float v[16];
@@ -89,32 +110,57 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* 
     for (int half = 0; half < 2; ++half) {
       float u[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = fmaxf(v[half * 8 + i] + bias[c0 + half * 8 + i], 0.f);
-      store_chunk_split(h_hi, h_lo, TP, (c0 >> 3) + half, row, u);
+      for (int i = 0; i < 8; ++i) {
+        const float z = v[half * 8 + i] + bias[c0 + half * 8 + i];
+        u[i] = fmaxf(z, 0.f);
+        bits |= (z > 0.f ? 1u : 0u) << ((c0 + half * 8 + i) & 31);
+      }
+      store_chunk_terms<NT>(h_base, h_term, TP, (c0 >> 3) + half, row, u);
+    }
+    if (((c0 + 16) & 31) == 0 || c0 + 16 == W) {
+      if (mask_words) mask_words[c0 >> 5] = bits;
+      bits = 0;
     }
   }
 }
 
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int FT = 3;  // bf16 terms per operand in the forward
+
+template <int IN, int W, int NL>
+struct TcSmem {
+  static constexpr int w1 = 0;                                   // FT term tiles each
+  static constexpr int w2 = w1 + FT * IN * W * 2;
+  static constexpr int w3 = w2 + (NL == 3 ? FT * W * W * 2 : 0);
+  static constexpr int bias = w3 + FT * W * OUTP * 2;            // fp32: b1[W] b2[W] b3[OUTP]
+  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // A0 terms: IN/8 chunks each
+  static constexpr int a0_term = (IN / 8) * CH;
+  static constexpr int h = a0 + FT * a0_term;                    // H terms: W/8 chunks each (also the fp32 stage)
+  static constexpr int h_term = (W / 8) * CH;
+  static constexpr int stage_bytes = TP * 65 * 4;                // fp32 [128][in_dim|1] input staging
+  static constexpr int h_bytes = (FT * h_term > stage_bytes) ? FT * h_term : stage_bytes;
+  static constexpr int bar = h + h_bytes;                        // mbarrier (8 B) + tmem slot (4 B)
+  static constexpr int total = bar + 16;
+};
+
 template <int IN, int W, int NL>
 __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict__ x, int64_t N, TcParams prm,
-                                                        float* __restrict__ y) {
+                                                        float* __restrict__ y, uint32_t* __restrict__ relu_mask) {
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcSmem<IN, W, NL>;
   constexpr int TCOLS = W >= 64 ? 64 : 32;
+  constexpr int MW = W >= 32 ? W / 32 : 1;  // mask words per point and hidden layer
   const int tid = threadIdx.x, warp = tid >> 5;
-  uint8_t* w1h = sm + L::w1; uint8_t* w1l = w1h + IN * W * 2;
-  uint8_t* w2h = sm + L::w2; uint8_t* w2l = w2h + W * W * 2;
-  uint8_t* w3h = sm + L::w3; uint8_t* w3l = w3h + W * OUTP * 2;
   float* bias = reinterpret_cast<float*>(sm + L::bias);
-  uint8_t* a0h = sm + L::a0; uint8_t* a0l = a0h + IN * TP * 2;
-  uint8_t* hh = sm + L::h;   uint8_t* hl = hh + W * TP * 2;
+  uint8_t* a0 = sm + L::a0;
+  uint8_t* hb = sm + L::h;
   float* stage = reinterpret_cast<float*>(sm + L::h);
   const uint32_t bar = smem_u32(sm + L::bar);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 8);
 
-  load_weight_split<W, IN>(prm.w[0], W, prm.in_dim, w1h, w1l);
-  if constexpr (NL == 3) load_weight_split<W, W>(prm.w[1], W, W, w2h, w2l);
-  load_weight_split<OUTP, W>(prm.w[NL - 1], prm.out_dim, W, w3h, w3l);
+  load_weight_terms<W, IN, FT>(prm.w[0], W, prm.in_dim, sm + L::w1);
+  if constexpr (NL == 3) load_weight_terms<W, W, FT>(prm.w[1], W, W, sm + L::w2);
+  load_weight_terms<OUTP, W, FT>(prm.w[NL - 1], prm.out_dim, W, sm + L::w3);
   for (int i = tid; i < W; i += TP) {
     bias[i] = __ldg(prm.b[0] + i);
     if constexpr (NL == 3) bias[W + i] = __ldg(prm.b[1] + i);
@@ -138,6 +184,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
+    uint32_t* mrow = (relu_mask && tid < rows) ? relu_mask + (row0 + tid) * (NL - 1) * MW : nullptr;
     // ---- input tile: coalesced global -> fp32 stage -> per-thread row -> split -> A0 operand tiles
     {
       const float* src = x + row0 * prm.in_dim;
@@ -156,20 +203,20 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
         const int k = c * 8 + i;
         u[i] = (tid < rows && k < prm.in_dim) ? stage[tid * sstride + k] : 0.f;
       }
-      store_chunk_split(a0h, a0l, TP, c, tid, u);
+      store_chunk_terms<FT>(a0, L::a0_term, TP, c, tid, u);
     }
     fence_async_smem();
     __syncthreads();  // A0 visible to the async proxy; the stage (aliasing H) is free again
     // ---- layer 1
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<W, IN>(tmem, smem_u32(a0h), smem_u32(a0l), smem_u32(w1h), smem_u32(w1l));
+      issue_layer<W, IN, FT>(tmem, smem_u32(a0), L::a0_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    hidden_epilogue<W>(tmem_row, bias, hh, hl, tid);
+    hidden_epilogue<W, FT>(tmem_row, bias, hb, L::h_term, tid, mrow);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -177,13 +224,13 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
     if constexpr (NL == 3) {
       if (tid == 0) {
         tc_fence_after();
-        issue_layer<W, W>(tmem, smem_u32(hh), smem_u32(hl), smem_u32(w2h), smem_u32(w2l));
+        issue_layer<W, W, FT>(tmem, smem_u32(hb), L::h_term, smem_u32(sm + L::w2));
         mma_commit(bar);
       }
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      hidden_epilogue<W>(tmem_row, bias + W, hh, hl, tid);  // the MMAs that read H have completed
+      hidden_epilogue<W, FT>(tmem_row, bias + W, hb, L::h_term, tid, mrow ? mrow + MW : nullptr);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -191,7 +238,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
     // ---- output layer
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<OUTP, W>(tmem, smem_u32(hh), smem_u32(hl), smem_u32(w3h), smem_u32(w3l));
+      issue_layer<OUTP, W, FT>(tmem, smem_u32(hb), L::h_term, smem_u32(sm + L::w3));
       mma_commit(bar);
     }
     mbar_wait(bar, phase);
@@ -221,14 +268,15 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
 }
 
 template <int IN, int W, int NL>
-static int launch_tc_fwd(const float* x, int64_t N, const TcParams& prm, float* y, cudaStream_t st) {
+static int launch_tc_fwd(const float* x, int64_t N, const TcParams& prm, float* y, uint32_t* mask, cudaStream_t st) {
   using L = TcSmem<IN, W, NL>;
+  static_assert(L::total <= 227 * 1024, "forward tile set does not fit in shared memory");
   auto k = mlp_tc_fwd_kernel<IN, W, NL>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   const int64_t tiles = (N + TP - 1) / TP;
-  const int per_sm = max(1, min(4, (220 * 1024) / (L::total + 1024)));
+  const int per_sm = max(1, min(6, (224 * 1024) / (L::total + 1024)));
   const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * per_sm);
-  k<<<grid, TP, L::total, st>>>(x, N, prm, y);
+  k<<<grid, TP, L::total, st>>>(x, N, prm, y, mask);
   return check_launch("mlp_tc_fwd_kernel");
 }
 
@@ -241,121 +289,130 @@ static int launch_tc_fwd(const float* x, int64_t N, const TcParams& prm, float* 
 // The dW^T accumulators stay in TMEM across all tiles of the persistent CTA (lane = input feature, column =
 // output feature) and are flushed once with atomics.  Each activation tile carries one extra "ones" chunk, so
 // the row after the last input feature of dW^T is the bias gradient -- no separate reduction.
+constexpr int BT = 2;  // bf16 terms per operand in the backward
+
 template <int IN, int W, int NL>
 struct TcBwdSmem {
-  static constexpr int CH = 2048;                                // bytes of one 16-byte chunk column (128 rows)
   static constexpr int w1 = 0;
-  static constexpr int w2 = w1 + 2 * IN * W * 2;
-  static constexpr int w3 = w2 + (NL == 3 ? 2 * W * W * 2 : 0);
-  static constexpr int bias = w3 + 2 * W * OUTP * 2;
-  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // hi then lo, (IN/8 + 1) chunks each
-  static constexpr int a0_bytes = (IN / 8 + 1) * CH;
-  static constexpr int h1 = a0 + 2 * a0_bytes;                   // hi then lo, (W/8 + 1) chunks each
-  static constexpr int h_bytes = (W / 8 + 1) * CH;
-  static constexpr int h2 = h1 + 2 * h_bytes;
-  static constexpr int g = h2 + (NL == 3 ? 2 * h_bytes : 0);     // dZ tile hi then lo (8 chunks each) / fp32 stage
-  static constexpr int g_half = 8 * CH;
-  static constexpr int g_bytes = 2 * g_half + 2048;              // >= 128*65*4 stage, and M=128 over-read slack
+  static constexpr int w2 = w1 + BT * IN * W * 2;
+  static constexpr int w3 = w2 + (NL == 3 ? BT * W * W * 2 : 0);
+  static constexpr int bias = w3 + BT * W * OUTP * 2;
+  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // BT terms, (IN/8 + 1) chunks each
+  static constexpr int a0_term = (IN / 8 + 1) * CH;
+  static constexpr int h1 = a0 + BT * a0_term;                   // BT terms, (W/8 + 1) chunks each
+  static constexpr int h_term = (W / 8 + 1) * CH;
+  static constexpr int h2 = h1 + BT * h_term;
+  static constexpr int g = h2 + (NL == 3 ? BT * h_term : 0);     // dZ tile: BT terms of 8 chunks / fp32 stage
+  static constexpr int g_term = 8 * CH;
+  static constexpr int g_bytes = BT * g_term + 2048;             // >= 128*65*4 stage, and M=128 over-read slack
   static constexpr int bar = g + g_bytes;
   static constexpr int total = bar + 16;
+  // TMEM columns: forward accumulators / dH / dX, then the three dW^T accumulators
+  static constexpr int c_acc = 0;
+  static constexpr int acc_cols = (W > IN ? W : IN) > 16 ? (W > IN ? W : IN) : 16;
+  static constexpr int c_dw1 = c_acc + acc_cols;
+  static constexpr int c_dw2 = c_dw1 + W;
+  static constexpr int c_dw3 = c_dw2 + (NL == 3 ? W : 0);
+  static constexpr int cols_used = c_dw3 + OUTP;
+  static constexpr int tcols = cols_used <= 32 ? 32 : cols_used <= 64 ? 64 : cols_used <= 128 ? 128 : 256;
 };
 
 // D[128 x N] (+)= Act^T-view . dZ^T-view over the 128 points of the tile (both operands MN-major)
 template <int N>
-__device__ __forceinline__ void issue_dw(uint32_t tmem_d, uint32_t act_hi, uint32_t act_lo, uint32_t dz_hi,
-                                         uint32_t dz_lo, uint32_t accumulate) {
+__device__ __forceinline__ void issue_dw(uint32_t tmem_d, uint32_t act_base, uint32_t act_term, uint32_t dz_base,
+                                         uint32_t dz_term, uint32_t accumulate) {
   constexpr uint32_t idesc = instr_desc_bf16(TP, N, true, true);
   uint32_t acc = accumulate;
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const uint32_t a = (s == 1) ? act_lo : act_hi;
-    const uint32_t b = (s == 2) ? dz_lo : dz_hi;
+  for (int i = 0; i < BT; ++i)
 #pragma unroll
-    for (int j = 0; j < TP / 16; ++j) {  // 16 points per MMA
-      const uint64_t ad = smem_desc(a + j * 256, 128, 2048);
-      const uint64_t bd = smem_desc(b + j * 256, 128, 2048);
-      mma_bf16(tmem_d, ad, bd, idesc, acc);
-      acc = 1;
-    }
-  }
+    for (int j = 0; j < BT - i; ++j)
+#pragma unroll
+      for (int q = 0; q < TP / 16; ++q) {  // 16 points per MMA
+        const uint64_t ad = smem_desc(act_base + i * act_term + q * 256, 128, CH);
+        const uint64_t bd = smem_desc(dz_base + j * dz_term + q * 256, 128, CH);
+        mma_bf16(tmem_d, ad, bd, idesc, acc);
+        acc = 1;
+      }
 }
 
 // D[128 x NIN] = dZ[128 x KOUT] . Wtile  (Wtile has NP rows = out features, NIN input features)
 template <int NIN, int KOUT, int NP>
-__device__ __forceinline__ void issue_dh(uint32_t tmem_d, uint32_t dz_hi, uint32_t dz_lo, uint32_t w_hi, uint32_t w_lo) {
+__device__ __forceinline__ void issue_dh(uint32_t tmem_d, uint32_t dz_base, uint32_t dz_term, uint32_t w_base) {
   constexpr uint32_t idesc = instr_desc_bf16(TP, NIN, false, true);
+  constexpr uint32_t w_term = NP * NIN * 2;
   uint32_t acc = 0;
 #pragma unroll
-  for (int s = 0; s < 3; ++s) {
-    const uint32_t a = (s == 1) ? dz_lo : dz_hi;
-    const uint32_t b = (s == 2) ? w_lo : w_hi;
+  for (int i = 0; i < BT; ++i)
 #pragma unroll
-    for (int kk = 0; kk < KOUT / 16; ++kk) {
-      const uint64_t ad = smem_desc(a + kk * 2 * 2048, 2048, 128);          // K-major dZ tile
-      const uint64_t bd = smem_desc(b + kk * 256, 128, NP * 16);            // W tile, MN-major view
-      mma_bf16(tmem_d, ad, bd, idesc, acc);
-      acc = 1;
-    }
-  }
+    for (int j = 0; j < BT - i; ++j)
+#pragma unroll
+      for (int kk = 0; kk < KOUT / 16; ++kk) {
+        const uint64_t ad = smem_desc(dz_base + i * dz_term + kk * 2 * CH, CH, 128);        // K-major dZ tile
+        const uint64_t bd = smem_desc(w_base + j * w_term + kk * 256, 128, NP * 16);       // W tile, MN-major view
+        mma_bf16(tmem_d, ad, bd, idesc, acc);
+        acc = 1;
+      }
 }
 
-__device__ __forceinline__ void store_ones_chunk(uint8_t* hi, uint8_t* lo, int chunk, int row) {
-  const size_t off = (size_t)chunk * 2048 + (size_t)row * 16;
-  *reinterpret_cast<uint4*>(hi + off) = make_uint4(0x00003F80u, 0u, 0u, 0u);  // bf16 {1,0,0,0,0,0,0,0}
-  *reinterpret_cast<uint4*>(lo + off) = make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ void store_ones_chunk(uint8_t* base, int term_stride, int chunk, int row) {
+  const size_t off = (size_t)chunk * CH + (size_t)row * 16;
+  *reinterpret_cast<uint4*>(base + off) = make_uint4(0x00003F80u, 0u, 0u, 0u);  // bf16 {1,0,0,0,0,0,0,0}
+#pragma unroll
+  for (int t = 1; t < BT; ++t) *reinterpret_cast<uint4*>(base + (size_t)t * term_stride + off) = make_uint4(0, 0, 0, 0);
 }
 
-// dZ_prev = dH (TMEM) masked by relu'(H_prev) -> split -> G tile
+// dZ_prev = dH (TMEM) gated by the ReLU mask of the previous layer -> split -> G tile
 template <int W>
-__device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, const uint8_t* h_hi, uint8_t* g_hi, uint8_t* g_lo, int row) {
+__device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, const uint32_t* __restrict__ mask_words,
+                                            const uint8_t* h_hi, uint8_t* g_base, int g_term, int row) {
 #pragma unroll
   for (int c0 = 0; c0 < W; c0 += 16) {
     float v[16];
     tmem_ld16(tmem_row + c0, v);
     tmem_ld_wait();
+    const uint32_t word = mask_words ? mask_words[c0 >> 5] : 0u;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int chunk = (c0 >> 3) + half;
-      const uint4 hv = *reinterpret_cast<const uint4*>(h_hi + (size_t)chunk * 2048 + (size_t)row * 16);
-      const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hv);
       float u[8];
+      if (mask_words) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = __bfloat162float(hb[i]) > 0.f ? v[half * 8 + i] : 0.f;
-      store_chunk_split(g_hi, g_lo, TP, chunk, row, u);
+        for (int i = 0; i < 8; ++i) u[i] = ((word >> ((c0 + half * 8 + i) & 31)) & 1u) ? v[half * 8 + i] : 0.f;
+      } else {  // no saved masks: gate on the recomputed activation
+        const uint4 hv = *reinterpret_cast<const uint4*>(h_hi + (size_t)chunk * CH + (size_t)row * 16);
+        const __nv_bfloat16* hbv = reinterpret_cast<const __nv_bfloat16*>(&hv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = __bfloat162float(hbv[i]) > 0.f ? v[half * 8 + i] : 0.f;
+      }
+      store_chunk_terms<BT>(g_base, g_term, TP, chunk, row, u);
     }
   }
 }
 
 template <int IN, int W, int NL, bool NEED_DX>
 __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                        int64_t N, TcParams prm, float* __restrict__ dx) {
+                                                        const uint32_t* __restrict__ relu_mask, int64_t N,
+                                                        TcParams prm, float* __restrict__ dx) {
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcBwdSmem<IN, W, NL>;
-  constexpr int TCOLS = 256;
-  constexpr int C_ACC = 0;        // forward accumulators / dH / dX   (64 columns)
-  constexpr int C_DW1 = 64;       // dW1^T  [IN(+1) lanes x W cols]
-  constexpr int C_DW2 = 128;      // dW2^T  [W(+1) lanes x W cols]
-  constexpr int C_DW3 = 192;      // dWlast^T [W(+1) lanes x OUTP cols]
+  constexpr int MW = W >= 32 ? W / 32 : 1;
   const int tid = threadIdx.x, warp = tid >> 5;
-  uint8_t* w1h = sm + L::w1; uint8_t* w1l = w1h + IN * W * 2;
-  uint8_t* w2h = sm + L::w2; uint8_t* w2l = w2h + W * W * 2;
-  uint8_t* w3h = sm + L::w3; uint8_t* w3l = w3h + W * OUTP * 2;
   float* bias = reinterpret_cast<float*>(sm + L::bias);
-  uint8_t* a0h = sm + L::a0; uint8_t* a0l = a0h + L::a0_bytes;
-  uint8_t* h1h = sm + L::h1; uint8_t* h1l = h1h + L::h_bytes;
-  uint8_t* h2h = sm + L::h2; uint8_t* h2l = h2h + L::h_bytes;
-  uint8_t* gh = sm + L::g;   uint8_t* gl = gh + L::g_half;
+  uint8_t* a0 = sm + L::a0;
+  uint8_t* h1 = sm + L::h1;
+  uint8_t* h2 = sm + L::h2;
+  uint8_t* gb = sm + L::g;
   float* stage = reinterpret_cast<float*>(sm + L::g);
-  uint8_t* hlast_h = NL == 3 ? h2h : h1h;
-  uint8_t* hlast_l = NL == 3 ? h2l : h1l;
+  uint8_t* hlast = NL == 3 ? h2 : h1;
   const uint32_t bar = smem_u32(sm + L::bar);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 8);
 
   // zero the whole operand area once: padding chunks / over-read regions must hold finite values
   for (int i = tid; i < (L::bar - L::a0) / 16; i += TP) reinterpret_cast<uint4*>(sm + L::a0)[i] = make_uint4(0, 0, 0, 0);
-  load_weight_split<W, IN>(prm.w[0], W, prm.in_dim, w1h, w1l);
-  if constexpr (NL == 3) load_weight_split<W, W>(prm.w[1], W, W, w2h, w2l);
-  load_weight_split<OUTP, W>(prm.w[NL - 1], prm.out_dim, W, w3h, w3l);
+  load_weight_terms<W, IN, BT>(prm.w[0], W, prm.in_dim, sm + L::w1);
+  if constexpr (NL == 3) load_weight_terms<W, W, BT>(prm.w[1], W, W, sm + L::w2);
+  load_weight_terms<OUTP, W, BT>(prm.w[NL - 1], prm.out_dim, W, sm + L::w3);
   for (int i = tid; i < W; i += TP) {
     bias[i] = __ldg(prm.b[0] + i);
     if constexpr (NL == 3) bias[W + i] = __ldg(prm.b[1] + i);
@@ -365,12 +422,12 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc<TCOLS>(smem_u32((const void*)tmem_slot));
+  if (warp == 0) tmem_alloc<L::tcols>(smem_u32((const void*)tmem_slot));
   __syncthreads();
   // "ones" chunks (bias-gradient rows) are constant across tiles
-  store_ones_chunk(a0h, a0l, IN / 8, tid);
-  store_ones_chunk(h1h, h1l, W / 8, tid);
-  if constexpr (NL == 3) store_ones_chunk(h2h, h2l, W / 8, tid);
+  store_ones_chunk(a0, L::a0_term, IN / 8, tid);
+  store_ones_chunk(h1, L::h_term, W / 8, tid);
+  if constexpr (NL == 3) store_ones_chunk(h2, L::h_term, W / 8, tid);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -385,6 +442,15 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
+    uint32_t mwords[2 * MW];
+#pragma unroll
+    for (int i = 0; i < 2 * MW; ++i) mwords[i] = 0;
+    if (relu_mask && tid < rows) {
+#pragma unroll
+      for (int i = 0; i < (NL - 1) * MW; ++i) mwords[i] = __ldg(relu_mask + (row0 + tid) * (NL - 1) * MW + i);
+    }
+    const uint32_t* m_first = relu_mask ? mwords : nullptr;             // mask of hidden layer 1
+    const uint32_t* m_last = relu_mask ? mwords + (NL - 2) * MW : nullptr;  // mask of the last hidden layer
     {
       const float* src = x + row0 * prm.in_dim;
       const int n = rows * prm.in_dim;
@@ -402,38 +468,38 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
         const int k = c * 8 + i;
         u[i] = (tid < rows && k < prm.in_dim) ? stage[tid * sstride + k] : 0.f;
       }
-      store_chunk_split(a0h, a0l, TP, c, tid, u);
+      store_chunk_terms<BT>(a0, L::a0_term, TP, c, tid, u);
     }
     fence_async_smem();
     __syncthreads();
-    // ---------------- forward recompute
+    // ---------------- forward recompute (activation VALUES; gating below uses the forward's masks)
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<W, IN>(tmem + C_ACC, smem_u32(a0h), smem_u32(a0l), smem_u32(w1h), smem_u32(w1l));
+      issue_layer<W, IN, BT>(tmem + L::c_acc, smem_u32(a0), L::a0_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    hidden_epilogue<W>(tmem_row + C_ACC, bias, h1h, h1l, tid);
+    hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias, h1, L::h_term, tid, nullptr);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if constexpr (NL == 3) {
       if (tid == 0) {
         tc_fence_after();
-        issue_layer<W, W>(tmem + C_ACC, smem_u32(h1h), smem_u32(h1l), smem_u32(w2h), smem_u32(w2l));
+        issue_layer<W, W, BT>(tmem + L::c_acc, smem_u32(h1), L::h_term, smem_u32(sm + L::w2));
         mma_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      hidden_epilogue<W>(tmem_row + C_ACC, bias + W, h2h, h2l, tid);
+      hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias + W, h2, L::h_term, tid, nullptr);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
     }
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<OUTP, W>(tmem + C_ACC, smem_u32(hlast_h), smem_u32(hlast_l), smem_u32(w3h), smem_u32(w3l));
+      issue_layer<OUTP, W, BT>(tmem + L::c_acc, smem_u32(hlast), L::h_term, smem_u32(sm + L::w3));
       mma_commit(bar);
     }
     mbar_wait(bar, phase); phase ^= 1;
@@ -441,9 +507,9 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     // ---------------- dZ_out = dy * act'(z)  -> G tile (16 features = 2 chunks)
     {
       float z[16];
-      tmem_ld16(tmem_row + C_ACC, z);
+      tmem_ld16(tmem_row + L::c_acc, z);
       tmem_ld_wait();
-      float g[16];
+      float u0[8], u1[8];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float gv = 0.f;
@@ -457,13 +523,10 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
             gv *= expf(fminf(fmaxf(zz, -15.f), 15.f));
           }
         }
-        g[j] = gv;
+        if (j < 8) u0[j] = gv; else u1[j - 8] = gv;
       }
-      float u0[8], u1[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { u0[i] = g[i]; u1[i] = g[8 + i]; }
-      store_chunk_split(gh, gl, TP, 0, tid, u0);
-      store_chunk_split(gh, gl, TP, 1, tid, u1);
+      store_chunk_terms<BT>(gb, L::g_term, TP, 0, tid, u0);
+      store_chunk_terms<BT>(gb, L::g_term, TP, 1, tid, u1);
     }
     fence_async_smem();
     tc_fence_before();
@@ -471,26 +534,26 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     // ---------------- last layer: dWlast^T, dH_last
     if (tid == 0) {
       tc_fence_after();
-      issue_dw<OUTP>(tmem + C_DW3, smem_u32(hlast_h), smem_u32(hlast_l), smem_u32(gh), smem_u32(gl), dw_acc);
-      issue_dh<W, OUTP, OUTP>(tmem + C_ACC, smem_u32(gh), smem_u32(gl), smem_u32(w3h), smem_u32(w3l));
+      issue_dw<OUTP>(tmem + L::c_dw3, smem_u32(hlast), L::h_term, smem_u32(gb), L::g_term, dw_acc);
+      issue_dh<W, OUTP, OUTP>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w3));
       mma_commit(bar);
     }
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    dh_epilogue<W>(tmem_row + C_ACC, hlast_h, gh, gl, tid);  // G now holds dZ of the last hidden layer
+    dh_epilogue<W>(tmem_row + L::c_acc, m_last, hlast, gb, L::g_term, tid);  // G = dZ of the last hidden layer
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     if constexpr (NL == 3) {
       if (tid == 0) {
         tc_fence_after();
-        issue_dw<W>(tmem + C_DW2, smem_u32(h1h), smem_u32(h1l), smem_u32(gh), smem_u32(gl), dw_acc);
-        issue_dh<W, W, W>(tmem + C_ACC, smem_u32(gh), smem_u32(gl), smem_u32(w2h), smem_u32(w2l));
+        issue_dw<W>(tmem + L::c_dw2, smem_u32(h1), L::h_term, smem_u32(gb), L::g_term, dw_acc);
+        issue_dh<W, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w2));
         mma_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      dh_epilogue<W>(tmem_row + C_ACC, h1h, gh, gl, tid);  // dZ1
+      dh_epilogue<W>(tmem_row + L::c_acc, m_first, h1, gb, L::g_term, tid);  // dZ1
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -498,8 +561,8 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     // ---------------- first layer: dW1^T (and dX)
     if (tid == 0) {
       tc_fence_after();
-      issue_dw<W>(tmem + C_DW1, smem_u32(a0h), smem_u32(a0l), smem_u32(gh), smem_u32(gl), dw_acc);
-      if constexpr (NEED_DX) issue_dh<IN, W, W>(tmem + C_ACC, smem_u32(gh), smem_u32(gl), smem_u32(w1h), smem_u32(w1l));
+      issue_dw<W>(tmem + L::c_dw1, smem_u32(a0), L::a0_term, smem_u32(gb), L::g_term, dw_acc);
+      if constexpr (NEED_DX) issue_dh<IN, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
     dw_acc = 1;
@@ -510,7 +573,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
 #pragma unroll
       for (int c0 = 0; c0 < IN; c0 += 16) {
         float v[16];
-        tmem_ld16(tmem_row + C_ACC + c0, v);
+        tmem_ld16(tmem_row + L::c_acc + c0, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 16; ++i)
@@ -533,7 +596,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
 #pragma unroll 1
     for (int c0 = 0; c0 < W; c0 += 16) {
       float v[16];
-      tmem_ld16(tmem_row + C_DW1 + c0, v);
+      tmem_ld16(tmem_row + L::c_dw1 + c0, v);
       tmem_ld_wait();
       if (tid < prm.in_dim) {
 #pragma unroll
@@ -543,7 +606,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
         for (int i = 0; i < 16; ++i) atomicAdd(prm.db[0] + c0 + i, v[i]);
       }
       if constexpr (NL == 3) {
-        tmem_ld16(tmem_row + C_DW2 + c0, v);
+        tmem_ld16(tmem_row + L::c_dw2 + c0, v);
         tmem_ld_wait();
         if (tid < W) {
 #pragma unroll
@@ -555,7 +618,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
       }
     }
     float v[16];
-    tmem_ld16(tmem_row + C_DW3, v);
+    tmem_ld16(tmem_row + L::c_dw3, v);
     tmem_ld_wait();
     if (tid < W) {
       for (int o = 0; o < prm.out_dim; ++o) atomicAdd(prm.dw[NL - 1] + (size_t)o * W + tid, v[o]);
@@ -567,24 +630,27 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc<TCOLS>(tmem);
+    tmem_dealloc<L::tcols>(tmem);
   }
 }
 
 template <int IN, int W, int NL>
-static int launch_tc_bwd(const float* x, const float* dy, int64_t N, const TcParams& prm, float* dx, cudaStream_t st) {
+static int launch_tc_bwd(const float* x, const float* dy, const uint32_t* mask, int64_t N, const TcParams& prm,
+                         float* dx, cudaStream_t st) {
   using L = TcBwdSmem<IN, W, NL>;
   static_assert(L::total <= 227 * 1024, "backward tile set does not fit in shared memory");
   const int64_t tiles = (N + TP - 1) / TP;
-  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs);
+  // resident CTAs per SM: bounded by shared memory and by the 512 TMEM columns
+  const int per_sm = max(1, min(min(4, 512 / L::tcols), (224 * 1024) / (L::total + 1024)));
+  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * per_sm);
   if (dx) {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, TP, L::total, st>>>(x, dy, N, prm, dx);
+    k<<<grid, TP, L::total, st>>>(x, dy, mask, N, prm, dx);
   } else {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, TP, L::total, st>>>(x, dy, N, prm, dx);
+    k<<<grid, TP, L::total, st>>>(x, dy, mask, N, prm, dx);
   }
   return check_launch("mlp_tc_bwd_kernel");
 }
@@ -631,19 +697,20 @@ using namespace tn;
 
 extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
                              const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
-                             void* stream) {
+                             uint32_t* relu_mask_out, void* stream) {
   TcParams prm = {};
   int rc = fill_tc(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
   if (N == 0) return TN_OK;
   TN_REQUIRE(x && y && N > 0, TN_EINVAL, "mlp_tc_fwd: bad x/y/N");
   cudaStream_t st = (cudaStream_t)stream;
-  TN_TC_DISPATCH(launch_tc_fwd, x, N, prm, y, st);
+  TN_TC_DISPATCH(launch_tc_fwd, x, N, prm, y, relu_mask_out, st);
 }
 
-extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width, int out_dim, int n_layers,
-                             const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* dx,
-                             float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream) {
+extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim,
+                             int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
+                             const float* const* b_host_ptrs, int out_act, float* dx, float* const* dw_host_ptrs,
+                             float* const* db_host_ptrs, void* stream) {
   TcParams prm = {};
   int rc = fill_tc(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
@@ -655,5 +722,5 @@ extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, int64_t N, int in_
     prm.db[i] = db_host_ptrs[i];
   }
   cudaStream_t st = (cudaStream_t)stream;
-  TN_TC_DISPATCH(launch_tc_bwd, x, dy, N, prm, dx, st);
+  TN_TC_DISPATCH(launch_tc_bwd, x, dy, relu_mask, N, prm, dx, st);
 }

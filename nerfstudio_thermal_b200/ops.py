@@ -166,28 +166,38 @@ class _MlpFn(torch.autograd.Function):
         n, in_dim = x.shape
         width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
         y = torch.empty((n, out_dim), device=x.device)
-        fwd = "tn_mlp_tc_fwd" if MLP_BACKEND["fwd"] == "tc" else "tn_mlp_fwd"
-        call(fwd, ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
-             stream(), tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
+        tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
+        mask = None
+        if MLP_BACKEND["fwd"] == "tc":
+            if MLP_BACKEND["bwd"] == "tc" and any(ctx.needs_input_grad):
+                mask = torch.empty((n, nl - 1, max(1, width // 32)), device=x.device, dtype=torch.int32)
+            call("tn_mlp_tc_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
+                 ptr(mask), stream(), tag=tag)
+        else:
+            call("tn_mlp_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
+                 stream(), tag=tag)
         ctx.out_act = out_act
-        ctx.save_for_backward(x, *ws, *bs)
+        ctx.nl = nl
+        ctx.save_for_backward(x, mask, *ws, *bs)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         saved = ctx.saved_tensors
-        x = saved[0]
-        nl = (len(saved) - 1) // 2
-        ws, bs = list(saved[1:1 + nl]), list(saved[1 + nl:])
+        x, mask, nl = saved[0], saved[1], ctx.nl
+        ws, bs = list(saved[2:2 + nl]), list(saved[2 + nl:])
         n, in_dim = x.shape
         width, out_dim = ws[0].shape[0], ws[-1].shape[0]
         dws = [torch.zeros_like(w) for w in ws]
         dbs = [torch.zeros_like(b) for b in bs]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        bwd = "tn_mlp_tc_bwd" if MLP_BACKEND["bwd"] == "tc" else "tn_mlp_bwd"
-        call(bwd, ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
-             ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(),
-             tag=f"[{in_dim}-{width}x{nl - 1}-{out_dim}]")
+        tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
+        if MLP_BACKEND["bwd"] == "tc":
+            call("tn_mlp_tc_bwd", ptr(x), ptr(_f32c(dy)), ptr(mask), n, in_dim, width, out_dim, nl, ptr_array(ws),
+                 ptr_array(bs), ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+        else:
+            call("tn_mlp_bwd", ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
+                 ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [dw, db]
