@@ -96,6 +96,23 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_base, ui
       }
 }
 
+// one row of x[N][in_dim] into registers, zero padded to IN; all loads are independent (issued back to back)
+template <int IN>
+__device__ __forceinline__ void load_input_row(const float* __restrict__ x, int64_t row, int in_dim, bool valid,
+                                               float (&v)[IN]) {
+  const float* src = x + row * in_dim;
+  if (valid && in_dim == IN && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {  // rows are 16-byte aligned
+#pragma unroll
+    for (int k = 0; k < IN; k += 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(src + k));
+      v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < IN; ++k) v[k] = (valid && k < in_dim) ? __ldg(src + k) : 0.f;
+  }
+}
+
 // hidden layer epilogue: TMEM row -> +bias, ReLU -> NT-term operand tile of the next layer (+ optional mask bits)
 template <int W, int NT>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* h_base,
@@ -185,28 +202,21 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
     uint32_t* mrow = (relu_mask && tid < rows) ? relu_mask + (row0 + tid) * (NL - 1) * MW : nullptr;
-    // ---- input tile: coalesced global -> fp32 stage -> per-thread row -> split -> A0 operand tiles
+    // ---- input tile: every thread pulls its own row with all loads in flight at once (a row is consumed whole,
+    //      so each fetched sector is fully used), splits it and writes the A0 operand tiles
     {
-      const float* src = x + row0 * prm.in_dim;
-      const int n = rows * prm.in_dim;
-      for (int i = tid; i < n; i += TP) {
-        const int p = i / prm.in_dim, k = i - p * prm.in_dim;
-        stage[p * sstride + k] = __ldg(src + i);
-      }
-    }
-    __syncthreads();
+      float xr[IN];
+      load_input_row<IN>(x, row0 + tid, prm.in_dim, tid < rows, xr);
 #pragma unroll
-    for (int c = 0; c < IN / 8; ++c) {
-      float u[8];
+      for (int c = 0; c < IN / 8; ++c) {
+        float u[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = c * 8 + i;
-        u[i] = (tid < rows && k < prm.in_dim) ? stage[tid * sstride + k] : 0.f;
+        for (int i = 0; i < 8; ++i) u[i] = xr[c * 8 + i];
+        store_chunk_terms<FT>(a0, L::a0_term, TP, c, tid, u);
       }
-      store_chunk_terms<FT>(a0, L::a0_term, TP, c, tid, u);
     }
     fence_async_smem();
-    __syncthreads();  // A0 visible to the async proxy; the stage (aliasing H) is free again
+    __syncthreads();  // A0 visible to the async proxy
     // ---- layer 1
     if (tid == 0) {
       tc_fence_after();
@@ -452,23 +462,15 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     const uint32_t* m_first = relu_mask ? mwords : nullptr;             // mask of hidden layer 1
     const uint32_t* m_last = relu_mask ? mwords + (NL - 2) * MW : nullptr;  // mask of the last hidden layer
     {
-      const float* src = x + row0 * prm.in_dim;
-      const int n = rows * prm.in_dim;
-      for (int i = tid; i < n; i += TP) {
-        const int p = i / prm.in_dim, k = i - p * prm.in_dim;
-        stage[p * sstride + k] = __ldg(src + i);
-      }
-    }
-    __syncthreads();
+      float xr[IN];
+      load_input_row<IN>(x, row0 + tid, prm.in_dim, tid < rows, xr);
 #pragma unroll
-    for (int c = 0; c < IN / 8; ++c) {
-      float u[8];
+      for (int c = 0; c < IN / 8; ++c) {
+        float u[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = c * 8 + i;
-        u[i] = (tid < rows && k < prm.in_dim) ? stage[tid * sstride + k] : 0.f;
+        for (int i = 0; i < 8; ++i) u[i] = xr[c * 8 + i];
+        store_chunk_terms<BT>(a0, L::a0_term, TP, c, tid, u);
       }
-      store_chunk_terms<BT>(a0, L::a0_term, TP, c, tid, u);
     }
     fence_async_smem();
     __syncthreads();
@@ -569,22 +571,25 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     if constexpr (NEED_DX) {
-      // dX rows: TMEM -> fp32 stage (G is free: its readers completed) -> coalesced global store
+      // dX rows: TMEM -> registers -> this thread's row of dx (whole rows, so every written sector is full)
+      float* dst = dx + (row0 + tid) * prm.in_dim;
+      const bool vec = prm.in_dim == IN && (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
 #pragma unroll
       for (int c0 = 0; c0 < IN; c0 += 16) {
         float v[16];
         tmem_ld16(tmem_row + L::c_acc + c0, v);
         tmem_ld_wait();
+        if (tid < rows) {
+          if (vec) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < prm.in_dim) stage[tid * sstride + c0 + i] = v[i];
-      }
-      __syncthreads();
-      float* dst = dx + row0 * prm.in_dim;
-      const int n = rows * prm.in_dim;
-      for (int i = tid; i < n; i += TP) {
-        const int p = i / prm.in_dim, k = i - p * prm.in_dim;
-        dst[i] = stage[p * sstride + k];
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < prm.in_dim) dst[c0 + i] = v[i];
+          }
+        }
       }
     }
     tc_fence_before();
