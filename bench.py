@@ -308,8 +308,12 @@ def run_b200(args):
         alg = algorithmic_bytes_per_point(L, 2, tb, bwd, dx="dx" in dom_tag) * pts_per_launch
         avg_ms = dom_ms / dom_n
         achieved = alg / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes per launch of this kernel from the committed ncu capture
+            traffic = json.load(open(tpath)).get(dom_tag)
         roofline = {"bound": "hbm", "kernel": dom_tag, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "launches_per_step": n_per_step, "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg, "share_of_kernel_time": dom_ms / args.steps / kern_ms}
         if args.profile_kernels:
