@@ -157,6 +157,37 @@ int tn_render_bwd(const float* weights, const float* colour, const float* starts
                   const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S, int C,
                   int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Glue fusions between the field kernels, and the per-ray losses.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: fields/nerfacto_field.py:221-228 (split, trunc_exp, selector) + :335-344 (head input concatenation).
+ * h[R*S, h_width] = density-MLP output (column 0 = raw density, columns 1..geo_dim = geometry features),
+ * sel[R*S], sh[R,16] (per-ray SH basis), emb_ray[R,emb_dim] (per-ray appearance embedding, NULL if emb_dim = 0).
+ * density_out[R*S] = density_scale * exp(h0) * sel;  x_out[R*S, 16+geo_dim+emb_dim] = [sh | geo | emb]. */
+int tn_field_split_fwd(const float* h, const float* sel, const float* sh, const float* emb_ray, int64_t R, int S,
+                       int h_width, int geo_dim, int emb_dim, float density_scale, float* density_out,
+                       float* x_out, void* stream);
+/* d_density[R*S] and dx[R*S, in] (either may be NULL = zero) -> dh_out[R*S, h_width] (overwritten) and
+ * demb_ray_out[R, emb_dim] (overwritten; sum over the samples of each ray; may be NULL). */
+int tn_field_split_bwd(const float* h, const float* sel, const float* d_density, const float* dx, int64_t R, int S,
+                       int h_width, int geo_dim, int emb_dim, float density_scale, float* dh_out,
+                       float* demb_ray_out, void* stream);
+/* replaces: fields/density_fields.py:116-117.  density[i] = scale * trunc_exp(raw[i*raw_stride]) * sel[i] and its
+ * backward (draw_out[i*draw_stride] is overwritten): raw may be a column of a row-major matrix. */
+int tn_density_act_fwd(const float* raw, int raw_stride, const float* sel, int64_t N, float scale,
+                       float* density_out, void* stream);
+int tn_density_act_bwd(const float* raw, int raw_stride, const float* sel, const float* d_density, int64_t N,
+                       float scale, float* draw_out, int draw_stride, void* stream);
+/* replaces: model_components/losses.py:139-150 (lossfun_distortion) per ray.  weights[R,S], sbins[R,S+1] ->
+ * loss_ray_out[R] (un-averaged) and dweights_out[R,S] = d loss_ray / d weights (may be NULL). */
+int tn_distortion_loss(const float* weights, const float* sbins, int64_t R, int S, float* loss_ray_out,
+                       float* dweights_out, void* stream);
+/* replaces: model_components/losses.py:57-103 (outer + lossfun_outer) per ray for ONE proposal level.
+ * fine histogram (w_fine[R,S_fine], sbins_fine[R,S_fine+1]) against the proposal histogram (w_prop, sbins_prop).
+ * loss_ray_out[R] = sum_i loss_i (un-averaged); dw_prop_out[R,S_prop] = d loss_ray / d w_prop (may be NULL). */
+int tn_interlevel_loss(const float* w_fine, const float* sbins_fine, const float* w_prop, const float* sbins_prop,
+                       int64_t R, int S_fine, int S_prop, float* loss_ray_out, float* dw_prop_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,12 @@ _SIGNATURES = {
     "tn_weights_bwd": [_P, _P, _P, c_int64, c_int, _P, _P],
     "tn_render_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int, _P, _P, _P, _P, _P, _P],
     "tn_render_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), _P, _P, _P],
+    "tn_field_split_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
+    "tn_field_split_bwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
+    "tn_density_act_fwd": [_P, c_int, _P, c_int64, c_float, _P, _P],
+    "tn_density_act_bwd": [_P, c_int, _P, _P, c_int64, c_float, _P, c_int, _P],
+    "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
+    "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
 }
 _RESTYPES = {"tn_last_error_string": c_char_p, "tn_build_arch": c_char_p}
 

@@ -8,7 +8,7 @@ from typing import Dict, Literal, Optional, Tuple
 import torch
 from torch import Tensor, nn
 
-from . import ops
+from . import fused_ops, ops
 from .field_components import (
     MLP,
     Embedding,
@@ -141,12 +141,40 @@ class NerfactoField(Field):
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape
         self._sample_locations = x.view(*shape, 3)
-        h = self.mlp_base(x).view(*shape, -1)
+        h_flat = self.mlp_base(x)
+        h = h_flat.view(*shape, -1)
         density_before_activation, base_mlp_out = torch.split(h, [1, self.geo_feat_dim], dim=-1)
         self._density_before_activation = density_before_activation
-        density = self.average_init_density * trunc_exp(density_before_activation)
-        density = density * selector.view(*shape, 1)
+        # average_init_density * trunc_exp(h0) * selector in one kernel (:227-228)
+        density = fused_ops.density_act(h_flat, selector, self.average_init_density).view(*shape, 1)
         return density, base_mlp_out
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
+        """Field.forward (fields/base_field.py:114-133).  For samples that carry a per-ray layout the density
+        activation, the geo/SH/appearance concatenation (:335-344) and its backward run as one kernel each
+        (`fused_ops.field_split`); the values are those of get_density + get_outputs."""
+        lay = ray_samples._layout
+        if compute_normals or lay is None or not _is_linf_contraction(self.spatial_distortion) \
+                or ray_samples.camera_indices is None:
+            return super().forward(ray_samples, compute_normals=compute_normals)
+        rays, samples = lay.num_rays, lay.num_samples
+        x, selector = ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+        self._sample_locations = x.view(rays, samples, 3)
+        h = self.mlp_base(x)
+        self._density_before_activation = h.view(rays, samples, -1)[..., :1]
+        sh = self.direction_encoding(get_normalized_directions(lay.directions))
+        emb_ray = None
+        if self.embedding_appearance is not None:
+            if self.training:  # one lookup per ray; the samples of a ray share the camera (:289-290)
+                emb_ray = self.embedding_appearance(ray_samples.camera_indices[:, 0, 0])
+            elif self.use_average_appearance_embedding:
+                emb_ray = self.embedding_appearance.mean(dim=0)[None, :].expand(rays, -1)
+            else:
+                emb_ray = torch.zeros((rays, self.appearance_embedding_dim), device=x.device)
+        density, head_in = fused_ops.field_split(h, selector, sh, emb_ray, rays, samples, self.geo_feat_dim,
+                                                 self.average_init_density)
+        rgb = self.mlp_head(head_in).view(rays, samples, -1)
+        return {FieldHeadNames.RGB: rgb, FieldHeadNames.DENSITY: density.view(rays, samples, 1)}
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None):
         """fields/nerfacto_field.py:272-348."""
@@ -217,11 +245,11 @@ class HashMLPDensityField(Field):
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape
         if not self.use_linear:
-            raw = self.mlp_base(x).view(*shape, -1)
+            raw = self.mlp_base(x)
         else:
-            raw = self.linear(self.encoding(x)).view(*shape, -1)
-        density = self.average_init_density * trunc_exp(raw)
-        density = density * selector.view(*shape, 1)
+            raw = self.linear(self.encoding(x))
+        # average_init_density * trunc_exp(raw) * selector in one kernel (:116-117)
+        density = fused_ops.density_act(raw, selector, self.average_init_density).view(*shape, 1)
         return density, None
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:

@@ -1,0 +1,118 @@
+"""torch.autograd bindings of the glue fusions and per-ray loss kernels (csrc/tn_fused.cu)."""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ._lib import call, ptr, stream
+from .ops import _f32c
+
+
+class _FieldSplitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, sel, sh, emb_ray, rays, samples, geo_dim, scale):
+        h, sel, sh = _f32c(h), _f32c(sel), _f32c(sh)
+        emb_ray = None if emb_ray is None else _f32c(emb_ray)
+        emb_dim = 0 if emb_ray is None else emb_ray.shape[-1]
+        n = rays * samples
+        density = torch.empty((n,), device=h.device)
+        x = torch.empty((n, 16 + geo_dim + emb_dim), device=h.device)
+        call("tn_field_split_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, h.shape[-1], geo_dim, emb_dim,
+             float(scale), ptr(density), ptr(x), stream())
+        ctx.dims = (rays, samples, geo_dim, emb_dim, float(scale))
+        ctx.save_for_backward(h, sel)
+        return density, x
+
+    @staticmethod
+    def backward(ctx, d_density, dx):
+        h, sel = ctx.saved_tensors
+        rays, samples, geo_dim, emb_dim, scale = ctx.dims
+        dh = torch.empty_like(h)
+        want_emb = emb_dim > 0 and ctx.needs_input_grad[3] and dx is not None
+        demb = torch.empty((rays, emb_dim), device=h.device) if want_emb else None
+        call("tn_field_split_bwd", ptr(h), ptr(sel), ptr(None if d_density is None else _f32c(d_density)),
+             ptr(None if dx is None else _f32c(dx)), rays, samples, h.shape[-1], geo_dim, emb_dim, scale, ptr(dh),
+             ptr(demb), stream())
+        return dh, None, None, demb, None, None, None, None
+
+
+def field_split(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Optional[Tensor], rays: int, samples: int, geo_dim: int,
+                scale: float) -> Tuple[Tensor, Tensor]:
+    """h[R*S,1+geo] -> (density[R*S], head input [R*S, 16+geo+emb]).  fields/nerfacto_field.py:221-228, 335-344."""
+    return _FieldSplitFn.apply(h, sel, sh, emb_ray, rays, samples, geo_dim, scale)
+
+
+class _DensityActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, sel, scale):
+        h, sel = _f32c(h), _f32c(sel).view(-1)
+        n, width = h.shape
+        out = torch.empty((n,), device=h.device)
+        call("tn_density_act_fwd", ptr(h), width, ptr(sel), n, float(scale), ptr(out), stream())
+        ctx.scale = float(scale)
+        ctx.save_for_backward(h, sel)
+        return out
+
+    @staticmethod
+    def backward(ctx, dd):
+        h, sel = ctx.saved_tensors
+        n, width = h.shape
+        dh = torch.zeros_like(h) if width > 1 else torch.empty_like(h)
+        call("tn_density_act_bwd", ptr(h), width, ptr(sel), ptr(_f32c(dd).view(-1)), n, ctx.scale, ptr(dh), width,
+             stream())
+        return dh, None, None
+
+
+def density_act(h: Tensor, sel: Tensor, scale: float) -> Tensor:
+    """scale * trunc_exp(h[:, 0]) * selector -> [N] for an MLP output h[N, width] whose column 0 is the raw
+    density.  fields/density_fields.py:116-117, fields/nerfacto_field.py:227-228."""
+    return _DensityActFn.apply(h, sel, scale)
+
+
+class _DistortionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, sbins):
+        w, sbins = _f32c(w), _f32c(sbins)
+        r, s = w.shape
+        loss_ray = torch.empty((r,), device=w.device)
+        dw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        call("tn_distortion_loss", ptr(w), ptr(sbins), r, s, ptr(loss_ray), ptr(dw), stream())
+        ctx.save_for_backward(dw)
+        ctx.rays = r
+        return loss_ray.sum() / r
+
+    @staticmethod
+    def backward(ctx, g):
+        (dw,) = ctx.saved_tensors
+        return (None if dw is None else dw * (g / ctx.rays)), None
+
+
+def distortion_loss_rays(w: Tensor, sbins: Tensor) -> Tensor:
+    """mean over rays of lossfun_distortion(sbins, w).  model_components/losses.py:139-158."""
+    return _DistortionFn.apply(w, sbins.detach())
+
+
+class _InterlevelFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w_fine, c_fine, w_prop, c_prop):
+        w_fine, c_fine, w_prop, c_prop = _f32c(w_fine), _f32c(c_fine), _f32c(w_prop), _f32c(c_prop)
+        r, sf = w_fine.shape
+        sp = w_prop.shape[1]
+        loss_ray = torch.empty((r,), device=w_fine.device)
+        dwp = torch.empty_like(w_prop) if ctx.needs_input_grad[2] else None
+        call("tn_interlevel_loss", ptr(w_fine), ptr(c_fine), ptr(w_prop), ptr(c_prop), r, sf, sp, ptr(loss_ray), ptr(dwp),
+             stream())
+        ctx.save_for_backward(dwp)
+        ctx.count = r * sf
+        return loss_ray.sum() / ctx.count
+
+    @staticmethod
+    def backward(ctx, g):
+        (dwp,) = ctx.saved_tensors
+        return None, None, (None if dwp is None else dwp * (g / ctx.count)), None
+
+
+def interlevel_loss_level(w_fine: Tensor, c_fine: Tensor, w_prop: Tensor, c_prop: Tensor) -> Tensor:
+    """mean(lossfun_outer(c_fine, w_fine, c_prop, w_prop)); the fine histogram carries no gradient.
+    model_components/losses.py:87-103, 117-135."""
+    return _InterlevelFn.apply(w_fine.detach(), c_fine.detach(), w_prop, c_prop.detach())

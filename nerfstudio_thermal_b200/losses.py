@@ -40,7 +40,11 @@ def ray_samples_to_sdist(ray_samples) -> Tensor:
 
 
 def interlevel_loss(weights_list, ray_samples_list) -> Tensor:
-    """losses.py:114-135."""
+    """losses.py:114-135: the final histogram (detached) must be bounded by every proposal histogram.  One
+    warp-per-ray kernel per proposal level computes the value and the gradient w.r.t. the proposal weights
+    (`outer`/`lossfun_outer` above are the same math as torch expressions, kept for callers and tests)."""
+    from . import fused_ops
+
     c = ray_samples_to_sdist(ray_samples_list[-1]).detach()
     w = weights_list[-1][..., 0].detach()
     assert len(ray_samples_list) > 0
@@ -48,7 +52,7 @@ def interlevel_loss(weights_list, ray_samples_list) -> Tensor:
     for ray_samples, weights in zip(ray_samples_list[:-1], weights_list[:-1]):
         cp = ray_samples_to_sdist(ray_samples)
         wp = weights[..., 0]
-        loss_interlevel += torch.mean(lossfun_outer(c, w, cp, wp))
+        loss_interlevel = loss_interlevel + fused_ops.interlevel_loss_level(w, c, wp, cp)
     assert isinstance(loss_interlevel, Tensor)
     return loss_interlevel
 
@@ -63,10 +67,13 @@ def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
 
 
 def distortion_loss(weights_list, ray_samples_list) -> Tensor:
-    """losses.py:153-158."""
+    """losses.py:153-158: mean over rays of lossfun_distortion on the final level.  The O(S^2) pairwise term runs
+    in one warp-per-ray kernel (no [R,S,S] temporaries); `lossfun_distortion` above is the torch expression."""
+    from . import fused_ops
+
     c = ray_samples_to_sdist(ray_samples_list[-1])
     w = weights_list[-1][..., 0]
-    return torch.mean(lossfun_distortion(c, w))
+    return fused_ops.distortion_loss_rays(w, c)
 
 
 def _rgb_patch_mask(is_thermal: Tensor) -> Tensor:

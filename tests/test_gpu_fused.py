@@ -1,0 +1,119 @@
+"""GPU parity tests for the glue fusions and the per-ray loss kernels (csrc/tn_fused.cu) against the oracle."""
+import pytest
+import torch
+
+import oracle
+from oracle import model as om
+from oracle import sampling as osamp
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import fused_ops, losses
+
+DEV = "cuda"
+
+
+def close(a, b, atol=1e-6, rtol=1e-5):
+    torch.testing.assert_close(a.detach().cpu(), b.detach().cpu(), atol=atol, rtol=rtol)
+
+
+@pytest.mark.parametrize("emb_dim", [32, 0])
+def test_field_split_fwd_bwd(emb_dim):
+    torch.manual_seed(0)
+    R, S, geo = 13, 48, 15
+    h = (torch.randn(R * S, 16) * 2).requires_grad_(True)
+    sel = (torch.rand(R * S) > 0.2).float()
+    sh = torch.randn(R, 16)
+    emb = torch.randn(R, emb_dim).requires_grad_(True) if emb_dim else None
+    # torch composition of fields/nerfacto_field.py:221-228 and :335-344
+    dens_ref = 0.7 * oracle.trunc_exp(h[:, :1]) * sel[:, None]
+    parts = [sh[:, None, :].expand(R, S, 16).reshape(-1, 16), h[:, 1:]]
+    if emb_dim:
+        parts.append(emb[:, None, :].expand(R, S, emb_dim).reshape(-1, emb_dim))
+    x_ref = torch.cat(parts, -1)
+    gd, gx = torch.randn(R * S), torch.randn_like(x_ref)
+    ((dens_ref[:, 0] * gd).sum() + (x_ref * gx).sum()).backward()
+
+    hg = h.detach().to(DEV).requires_grad_(True)
+    eg = emb.detach().to(DEV).requires_grad_(True) if emb_dim else None
+    dens, x = fused_ops.field_split(hg, sel.to(DEV), sh.to(DEV), eg, R, S, geo, 0.7)
+    close(dens, dens_ref[:, 0], 1e-6, 1e-5)
+    assert torch.equal(x.cpu(), x_ref.detach())
+    ((dens * gd.to(DEV)).sum() + (x * gx.to(DEV)).sum()).backward()
+    close(hg.grad, h.grad, 1e-5, 1e-5)
+    if emb_dim:
+        close(eg.grad, emb.grad, 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("width", [1, 16])
+def test_density_act(width):
+    torch.manual_seed(1)
+    n = 1000
+    h = (torch.randn(n, width) * 6).requires_grad_(True)  # includes |x| > 15 after scaling: clamp in the gradient
+    with torch.no_grad():
+        h[:5, 0] = torch.tensor([20.0, -20.0, 15.0, -15.0, 0.0])
+    sel = (torch.rand(n) > 0.3).float()
+    ref = 1.3 * oracle.trunc_exp(h[:, 0]) * sel
+    g = torch.randn(n)
+    (ref * g).sum().backward()
+    hg = h.detach().to(DEV).requires_grad_(True)
+    out = fused_ops.density_act(hg, sel.to(DEV), 1.3)
+    close(out, ref, 1e-6, 2e-6)
+    (out * g.to(DEV)).sum().backward()
+    close(hg.grad, h.grad, 1e-6, 2e-6)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_losses_golden(golden, mode):
+    """distortion + interlevel on the reference's sampling chain: values vs the reference, gradients vs autograd
+    of the oracle's torch expressions"""
+    g = golden("sampling.npz")
+
+    def sdist(tag):
+        return torch.cat([g[f"{mode}_{tag}_spacing_starts"][..., 0], g[f"{mode}_{tag}_spacing_ends"][..., -1:, 0]], -1)
+
+    c0, c1, c2 = sdist("s0"), sdist("s1"), sdist("s2")
+    w0 = g[f"{mode}_w0"][..., 0].clone().requires_grad_(True)
+    w1 = g[f"{mode}_w1"][..., 0].clone().requires_grad_(True)
+    w2 = g[f"{mode}_w2"][..., 0].clone().requires_grad_(True)
+    dist = fused_ops.distortion_loss_rays(w2.detach().to(DEV).requires_grad_(True), c2.to(DEV))
+    close(dist, g[f"{mode}_distortion"], 1e-7, 1e-5)
+    w2g = w2.detach().to(DEV).requires_grad_(True)
+    fused_ops.distortion_loss_rays(w2g, c2.to(DEV)).backward()
+    close(w2g.grad, g[f"{mode}_ddist_w2"][..., 0], 1e-7, 1e-4)
+    w0g, w1g = w0.detach().to(DEV).requires_grad_(True), w1.detach().to(DEV).requires_grad_(True)
+    inter = (fused_ops.interlevel_loss_level(w2.detach().to(DEV), c2.to(DEV), w0g, c0.to(DEV))
+             + fused_ops.interlevel_loss_level(w2.detach().to(DEV), c2.to(DEV), w1g, c1.to(DEV)))
+    close(inter, g[f"{mode}_interlevel"], 1e-7, 1e-5)
+    inter.backward()
+    close(w0g.grad, g[f"{mode}_dinter_w0"][..., 0], 1e-7, 1e-4)
+    close(w1g.grad, g[f"{mode}_dinter_w1"][..., 0], 1e-7, 1e-4)
+
+
+def test_losses_random_vs_oracle():
+    torch.manual_seed(3)
+    R = 50
+    for sf, sp in ((48, 96), (48, 256), (7, 33)):
+        c = torch.sort(torch.rand(R, sf + 1), -1).values
+        cp = torch.sort(torch.rand(R, sp + 1), -1).values
+        w = torch.rand(R, sf) * 0.05
+        wp = (torch.rand(R, sp) * 0.02).requires_grad_(True)
+        sf_ = osamp.OracleSamples(None, None, None, None, None, c[:, :-1, None], c[:, 1:, None], None, None)
+        sp_ = osamp.OracleSamples(None, None, None, None, None, cp[:, :-1, None], cp[:, 1:, None], None, None)
+        ref = om.interlevel_loss([wp[..., None], w[..., None]], [sp_, sf_])
+        ref.backward()
+        wpg = wp.detach().to(DEV).requires_grad_(True)
+        got = fused_ops.interlevel_loss_level(w.to(DEV), c.to(DEV), wpg, cp.to(DEV))
+        close(got, ref, 1e-8, 1e-5)
+        got.backward()
+        close(wpg.grad, wp.grad, 1e-8, 1e-4)
+        wv = w.clone().requires_grad_(True)
+        refd = om.distortion_loss([wv[..., None]], [sf_])
+        refd.backward()
+        wg = w.to(DEV).requires_grad_(True)
+        gotd = fused_ops.distortion_loss_rays(wg, c.to(DEV))
+        close(gotd, refd, 1e-8, 1e-5)
+        gotd.backward()
+        close(wg.grad, wv.grad, 1e-8, 1e-4)
