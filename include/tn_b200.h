@@ -188,6 +188,26 @@ int tn_distortion_loss(const float* weights, const float* sbins, int64_t R, int 
 int tn_interlevel_loss(const float* w_fine, const float* sbins_fine, const float* w_prop, const float* sbins_prop,
                        int64_t R, int S_fine, int S_prop, float* loss_ray_out, float* dw_prop_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused proposal density field: ray samples -> density in one kernel, and its whole backward in one kernel.
+ *   replaces: fields/density_fields.py:95-118 (HashMLPDensityField.get_density) end to end, i.e.
+ *   cameras/rays.py:49-58 + spatial_distortions.py:66-69 + encodings.py:401-461 (L <= 8 levels, F = 2) +
+ *   mlp.py:159-178 (Linear(2L,hidden=16) ReLU Linear(16,1)) + activations.py:28-42 (trunc_exp) + selector.
+ * origins/directions [R,3], ebins[R,S+1], table[L*T,2] fp32, w1[16,2L] b1[16] w2[1,16] b2[1] (nn.Linear layout).
+ * density_out[R*S] = density_scale * exp(raw) * selector.
+ * ------------------------------------------------------------------------------------------------ */
+int tn_prop_density_fwd(const float* origins, const float* directions, const float* ebins, const float* table,
+                        const float* scales_host, int64_t R, int S, int L, int log2_T, int hidden, const float* w1,
+                        const float* b1, const float* w2, const float* b2, float density_scale,
+                        float* density_out, void* stream);
+/* d_density[R*S] -> dtable (ACCUMULATED), dw1/db1/dw2/db2 (ACCUMULATED, atomics), and, when non-NULL,
+ * d_origins/d_directions [R,3] (ACCUMULATED with atomics: zero them first). */
+int tn_prop_density_bwd(const float* origins, const float* directions, const float* ebins, const float* table,
+                        const float* scales_host, int64_t R, int S, int L, int log2_T, int hidden, const float* w1,
+                        const float* b1, const float* w2, const float* b2, float density_scale,
+                        const float* d_density, float* dtable, float* dw1, float* db1, float* dw2, float* db2,
+                        float* d_origins, float* d_directions, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,10 @@ _SIGNATURES = {
     "tn_field_split_bwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
     "tn_density_act_fwd": [_P, c_int, _P, c_int64, c_float, _P, _P],
     "tn_density_act_bwd": [_P, c_int, _P, _P, c_int64, c_float, _P, c_int, _P],
+    "tn_prop_density_fwd": [_P, _P, _P, _P, POINTER(c_float), c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                            c_float, _P, _P],
+    "tn_prop_density_bwd": [_P, _P, _P, _P, POINTER(c_float), c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
+                            c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
 }

@@ -11,7 +11,7 @@ pids=()
 build() {  # build <file> [extra flags]: skip when the object is newer than the source and headers
   local src="$HERE/$1"; shift
   local obj="$OBJ/$(basename "${src%.cu}").o"
-  if [[ -f "$obj" && "$obj" -nt "$src" && "$obj" -nt "$HERE/tn_common.cuh" && "$obj" -nt "$HERE/tn_tc.cuh" &&"$obj" -nt "$HERE/../../include/tn_b200.h" && "$obj" -nt "$HERE/build.sh" ]]; then return; fi
+  if [[ -f "$obj" && "$obj" -nt "$src" && "$obj" -nt "$HERE/tn_common.cuh" && "$obj" -nt "$HERE/tn_tc.cuh" && "$obj" -nt "$HERE/tn_encode_core.cuh" && "$obj" -nt "$HERE/tn_geometry.cuh" &&"$obj" -nt "$HERE/../../include/tn_b200.h" && "$obj" -nt "$HERE/build.sh" ]]; then return; fi
   $NVCC $COMMON "$@" -c "$src" -o "$obj" &
   pids+=($!)
 }
@@ -19,6 +19,7 @@ build() {  # build <file> [extra flags]: skip when the object is newer than the 
 build tn_encode.cu -fmad=false
 build tn_geometry.cu -fmad=false
 build tn_ray.cu -fmad=false
+build tn_prop.cu -fmad=false
 build tn_mlp.cu
 build tn_mlp_tc.cu
 build tn_fused.cu

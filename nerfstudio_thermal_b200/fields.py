@@ -226,6 +226,7 @@ class HashMLPDensityField(Field):
         self.register_buffer("aabb", aabb)
         self.spatial_distortion = spatial_distortion
         self.use_linear = use_linear
+        self.fuse = True  # use the single-kernel path for ray samples when the shapes allow (see get_density)
         self.average_init_density = average_init_density
         self.register_buffer("max_res", torch.tensor(max_res))
         self.register_buffer("num_levels", torch.tensor(num_levels))
@@ -242,6 +243,16 @@ class HashMLPDensityField(Field):
 
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
         """fields/density_fields.py:95-118."""
+        lay = ray_samples._layout
+        enc = self.encoding
+        if (self.fuse and lay is not None and _is_linf_contraction(self.spatial_distortion) and not self.use_linear
+                and enc.features_per_level == 2 and enc.num_levels <= 8 and not enc.use_half_table
+                and len(self.mlp_base[1].layers) == 2 and self.mlp_base[1].layer_width == 16):
+            # whole field in one kernel: positions -> contraction -> hash grid -> 16-wide MLP -> trunc_exp * selector
+            l0, l1 = self.mlp_base[1].layers
+            density = fused_ops.prop_density(lay.origins, lay.directions, lay.ebins, enc.hash_table, l0.weight, l0.bias,
+                                             l1.weight, l1.bias, enc.spec, self.average_init_density, enc.grad_sink)
+            return density.view(lay.num_rays, lay.num_samples, 1), None
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape
         if not self.use_linear:

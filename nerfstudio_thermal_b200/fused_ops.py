@@ -69,6 +69,47 @@ def density_act(h: Tensor, sel: Tensor, scale: float) -> Tensor:
     return _DensityActFn.apply(h, sel, scale)
 
 
+class _PropDensityFn(torch.autograd.Function):
+    """ray samples -> proposal density, one kernel each way (csrc/tn_prop.cu)."""
+
+    @staticmethod
+    def forward(ctx, origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink):
+        origins, directions, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
+        w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
+        r, s = ebins.shape[0], ebins.shape[1] - 1
+        density = torch.empty((r * s,), device=ebins.device)
+        call("tn_prop_density_fwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
+             spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), float(scale), ptr(density),
+             stream(), tag=f"[L{spec.num_levels},S{s}]")
+        ctx.spec, ctx.scale, ctx.grad_sink = spec, float(scale), grad_sink
+        ctx.save_for_backward(origins, directions, ebins, table, w1, b1, w2, b2)
+        return density
+
+    @staticmethod
+    def backward(ctx, d_density):
+        origins, directions, ebins, table, w1, b1, w2, b2 = ctx.saved_tensors
+        spec = ctx.spec
+        r, s = ebins.shape[0], ebins.shape[1] - 1
+        need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        d_o = torch.zeros_like(origins) if need_rays else None
+        d_d = torch.zeros_like(directions) if need_rays else None
+        sink = ctx.grad_sink if ctx.needs_input_grad[3] else None
+        dtable = sink if sink is not None else torch.zeros_like(table)
+        dw1, db1, dw2, db2 = (torch.zeros_like(t) for t in (w1, b1, w2, b2))
+        call("tn_prop_density_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
+             spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), ctx.scale,
+             ptr(_f32c(d_density)), ptr(dtable), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(d_o), ptr(d_d), stream(),
+             tag=f"[L{spec.num_levels},S{s}{',dx' if need_rays else ''}]")
+        dt = dtable if (ctx.needs_input_grad[3] and sink is None) else None
+        return d_o, d_d, None, dt, dw1, db1, dw2, db2, None, None, None
+
+
+def prop_density(origins: Tensor, directions: Tensor, ebins: Tensor, table: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
+                 b2: Tensor, spec, scale: float, grad_sink: Optional[Tensor] = None) -> Tensor:
+    """HashMLPDensityField.get_density for ray samples, fused end to end.  fields/density_fields.py:95-118."""
+    return _PropDensityFn.apply(origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink)
+
+
 class _DistortionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, w, sbins):

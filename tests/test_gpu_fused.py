@@ -117,3 +117,49 @@ def test_losses_random_vs_oracle():
         close(gotd, refd, 1e-8, 1e-5)
         gotd.backward()
         close(wg.grad, wv.grad, 1e-8, 1e-4)
+
+
+@pytest.mark.parametrize("S,max_res", [(256, 128), (96, 256), (48, 64)])
+def test_fused_proposal_field_vs_oracle(S, max_res):
+    """positions -> contraction -> 5-level grid -> 10-16-1 MLP -> trunc_exp*selector in one kernel, fwd + bwd"""
+    torch.manual_seed(4)
+    R = 70
+    field = tn.HashMLPDensityField(torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), hidden_dim=16, num_levels=5,
+                                   max_res=max_res, log2_hashmap_size=12,
+                                   spatial_distortion=tn.SceneContraction(order=float("inf")))
+    with torch.no_grad():
+        field.encoding.hash_table.mul_(500.0)
+    sd = {f"p.{k}": v.detach().clone().requires_grad_(v.dtype == torch.float32 and k != "aabb")
+          for k, v in field.state_dict().items()}
+    sd["p.mlp_base.0.hash_table"] = sd["p.encoding.hash_table"]
+    field = field.to(DEV)
+    o = (torch.randn(R, 3) * 0.4).requires_grad_(True)
+    d = torch.nn.functional.normalize(torch.randn(R, 3), dim=-1).requires_grad_(True)
+    nears, fars = torch.full((R, 1), 0.05), torch.full((R, 1), 1000.0)
+    og, dg = o.detach().to(DEV).requires_grad_(True), d.detach().to(DEV).requires_grad_(True)
+    rb = tn.RayBundle(origins=og, directions=dg, pixel_area=torch.ones(R, 1, device=DEV), nears=nears.to(DEV),
+                      fars=fars.to(DEV))
+    jit = torch.rand(R, 1)
+    rs = tn.UniformLinDispPiecewiseSampler(single_jitter=True).train()(rb, num_samples=S, jitter=jit.to(DEV))
+    assert rs._layout is not None
+    dens = field.get_density(rs)[0]
+    # oracle on the same samples
+    samples = osamp.initial_samples(o, d, None, nears, fars, S, jit)
+    ref = oracle.proposal_density(sd, "p", osamp.sample_positions(samples), num_levels=5, base_res=16, max_res=max_res,
+                                  log2_hashmap_size=12)
+    close(dens, ref, 1e-5, 2e-5)
+    g = torch.rand_like(ref)
+    (ref * g).sum().backward()
+    (dens * g.to(DEV)).sum().backward()
+
+    def rel(a, b):
+        return ((a.detach().cpu().double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+    assert rel(field.encoding.hash_table.grad, sd["p.encoding.hash_table"].grad) < 1e-4
+    for i in (0, 1):
+        assert rel(field.mlp_base[1].layers[i].weight.grad, sd[f"p.mlp_base.1.layers.{i}.weight"].grad) < 1e-4
+        assert rel(field.mlp_base[1].layers[i].bias.grad, sd[f"p.mlp_base.1.layers.{i}.bias"].grad) < 1e-4
+    assert rel(og.grad, o.grad) < 1e-3 and rel(dg.grad, d.grad) < 1e-3
+    # and the unfused kernel chain gives the same density
+    field.fuse = False
+    close(field.get_density(rs)[0], dens, 1e-6, 1e-5)
