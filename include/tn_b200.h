@@ -208,6 +208,36 @@ int tn_prop_density_bwd(const float* origins, const float* directions, const flo
                         const float* d_density, float* dtable, float* dw1, float* db1, float* dw2, float* db2,
                         float* d_origins, float* d_directions, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Model glue as single launches.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: cameras/camera_optimizers.py:132-176 (CameraOptimizer.forward + apply_to_raybundle, mode SO3xR3 or
+ * shared_SO3xR3) with cameras/lie_groups.py:24-59.  pose[num_cams|1, 6] = (translation, so(3) log-rotation);
+ * frozen: NULL or uint8[num_cams] (1 = non-trainable camera, identity correction); camera_indices int64[R].
+ * origins_out = o + t, directions_out = R(w) d. */
+int tn_camera_opt_fwd(const float* pose, const uint8_t* frozen, const int64_t* camera_indices, const float* origins,
+                      const float* directions, int64_t R, int shared_pose, float* origins_out,
+                      float* directions_out, void* stream);
+/* gradients w.r.t. the outputs (either may be NULL) -> dpose[num_cams|1, 6], ACCUMULATED with atomics. */
+int tn_camera_opt_bwd(const float* pose, const uint8_t* frozen, const int64_t* camera_indices,
+                      const float* directions, const float* d_origins_out, const float* d_directions_out, int64_t R,
+                      int shared_pose, float* dpose, void* stream);
+/* replaces: models/thermal_nerfacto.py:286-354 pixel terms (MSE on RGB / thermal rays, model_components/losses.py:
+ * 603-620 tv_pixel_loss, :623-651 cross_channel_loss, utils/rgbt_utils.py:6-33) for patch-ordered batches (groups
+ * of four rays = one 2x2 patch of one camera).  rgb[R,3], thermal[R] (NULL in rgb_only mode), image[R,3],
+ * is_thermal[R].  losses_out[4] = {rgb MSE, thermal MSE, tv_pixel, cross_channel} (un-multiplied; may be NULL).
+ * d_rgb_out[R,3] / d_thermal_out[R] (may be NULL) = sum_k upstream[k] * d losses[k] / d input; upstream: device
+ * float[4]. */
+int tn_pixel_losses(const float* rgb, const float* thermal, const float* image, const float* is_thermal, int64_t R,
+                    const float* upstream, float* losses_out, float* d_rgb_out, float* d_thermal_out, void* stream);
+/* replaces: models/thermal_nerfacto.py:328-344 (cross-field density L1 with its stop-gradient pattern).
+ * d, d2, dt, d2t [N].  partial_out[n_partial]: per-CTA partial sums of value_mult * (mean|d2-dt| + mean|d-d2t|).
+ * Gradients (all four or none): g_dt = -thermal_grad_mult*sgn(d2-dt)/N, g_d2t = -thermal_grad_mult*sgn(d-d2t)/N,
+ * g_d2 = rgb_grad_mult*sgn(d2-dt)/N, g_d = rgb_grad_mult*sgn(d-d2t)/N. */
+int tn_density_l1(const float* d, const float* d2, const float* dt, const float* d2t, int64_t N, float value_mult,
+                  float thermal_grad_mult, float rgb_grad_mult, float* partial_out, int n_partial, float* g_d,
+                  float* g_d2, float* g_dt, float* g_d2t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

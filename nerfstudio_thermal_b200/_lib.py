@@ -55,6 +55,10 @@ _SIGNATURES = {
                             c_float, _P, _P],
     "tn_prop_density_bwd": [_P, _P, _P, _P, POINTER(c_float), c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P,
                             c_float, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "tn_camera_opt_fwd": [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
+    "tn_camera_opt_bwd": [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P],
+    "tn_pixel_losses": [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P],
+    "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
 }

@@ -23,6 +23,7 @@ build tn_prop.cu -fmad=false
 build tn_mlp.cu
 build tn_mlp_tc.cu
 build tn_fused.cu
+build tn_model.cu
 build tn_api.cu
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libtn_b200.so" "$OBJ"/*.o -lcudart

@@ -150,6 +150,8 @@ class MLP(FieldComponent):
                     layers.append(nn.Linear(layer_width, layer_width))
             layers.append(nn.Linear(layer_width, self.out_dim))
         self.layers = nn.ModuleList(layers)
+        # optional accumulation targets [(dW_i, db_i)] for the backward kernels (parallel.FlatGradBuffer.attach_sinks)
+        self.grad_sinks = None
         if isinstance(out_activation, nn.Sigmoid):
             self._out_act = ops.ACT_SIGMOID
         elif out_activation is None:
@@ -165,7 +167,8 @@ class MLP(FieldComponent):
 
     def forward(self, in_tensor: Tensor) -> Tensor:
         flat = in_tensor.reshape(-1, self.in_dim)
-        y = ops.mlp(flat, [l.weight for l in self.layers], [l.bias for l in self.layers], self._out_act)
+        y = ops.mlp(flat, [l.weight for l in self.layers], [l.bias for l in self.layers], self._out_act,
+                    sinks=self.grad_sinks)
         return y.view(*in_tensor.shape[:-1], self.out_dim)
 
 

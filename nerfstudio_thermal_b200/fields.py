@@ -166,7 +166,8 @@ class NerfactoField(Field):
         emb_ray = None
         if self.embedding_appearance is not None:
             if self.training:  # one lookup per ray; the samples of a ray share the camera (:289-290)
-                emb_ray = self.embedding_appearance(ray_samples.camera_indices[:, 0, 0])
+                emb_ray = fused_ops.embed_rows(self.embedding_appearance.embedding.weight,
+                                               ray_samples.camera_indices[:, 0, 0])
             elif self.use_average_appearance_embedding:
                 emb_ray = self.embedding_appearance.mean(dim=0)[None, :].expand(rays, -1)
             else:
@@ -251,7 +252,8 @@ class HashMLPDensityField(Field):
             # whole field in one kernel: positions -> contraction -> hash grid -> 16-wide MLP -> trunc_exp * selector
             l0, l1 = self.mlp_base[1].layers
             density = fused_ops.prop_density(lay.origins, lay.directions, lay.ebins, enc.hash_table, l0.weight, l0.bias,
-                                             l1.weight, l1.bias, enc.spec, self.average_init_density, enc.grad_sink)
+                                             l1.weight, l1.bias, enc.spec, self.average_init_density, enc.grad_sink,
+                                             self.mlp_base[1].grad_sinks)
             return density.view(lay.num_rays, lay.num_samples, 1), None
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape

@@ -73,7 +73,8 @@ class _PropDensityFn(torch.autograd.Function):
     """ray samples -> proposal density, one kernel each way (csrc/tn_prop.cu)."""
 
     @staticmethod
-    def forward(ctx, origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink):
+    def forward(ctx, origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks):
+        ctx.mlp_sinks = mlp_sinks
         origins, directions, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
         w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
         r, s = ebins.shape[0], ebins.shape[1] - 1
@@ -95,19 +96,141 @@ class _PropDensityFn(torch.autograd.Function):
         d_d = torch.zeros_like(directions) if need_rays else None
         sink = ctx.grad_sink if ctx.needs_input_grad[3] else None
         dtable = sink if sink is not None else torch.zeros_like(table)
-        dw1, db1, dw2, db2 = (torch.zeros_like(t) for t in (w1, b1, w2, b2))
+        ms = ctx.mlp_sinks
+        if ms is not None:
+            (dw1, db1), (dw2, db2) = ms
+        else:
+            dw1, db1, dw2, db2 = (torch.zeros_like(t) for t in (w1, b1, w2, b2))
         call("tn_prop_density_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
              spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), ctx.scale,
              ptr(_f32c(d_density)), ptr(dtable), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(d_o), ptr(d_d), stream(),
              tag=f"[L{spec.num_levels},S{s}{',dx' if need_rays else ''}]")
         dt = dtable if (ctx.needs_input_grad[3] and sink is None) else None
-        return d_o, d_d, None, dt, dw1, db1, dw2, db2, None, None, None
+        if ms is not None:
+            dw1 = db1 = dw2 = db2 = None
+        return d_o, d_d, None, dt, dw1, db1, dw2, db2, None, None, None, None
 
 
 def prop_density(origins: Tensor, directions: Tensor, ebins: Tensor, table: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
-                 b2: Tensor, spec, scale: float, grad_sink: Optional[Tensor] = None) -> Tensor:
-    """HashMLPDensityField.get_density for ray samples, fused end to end.  fields/density_fields.py:95-118."""
-    return _PropDensityFn.apply(origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink)
+                 b2: Tensor, spec, scale: float, grad_sink: Optional[Tensor] = None, mlp_sinks=None) -> Tensor:
+    """HashMLPDensityField.get_density for ray samples, fused end to end.  fields/density_fields.py:95-118.
+    grad_sink / mlp_sinks: optional accumulation targets for the table and [(dW1,db1),(dW2,db2)] gradients."""
+    return _PropDensityFn.apply(origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks)
+
+
+class _EmbedRowsFn(torch.autograd.Function):
+    """weight[idx] whose backward is an index_add_ (atomics) instead of torch's sort-based embedding backward."""
+
+    @staticmethod
+    def forward(ctx, weight, idx):
+        ctx.save_for_backward(idx)
+        ctx.shape = weight.shape
+        return weight.index_select(0, idx)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        gw = torch.zeros(ctx.shape, device=g.device, dtype=g.dtype)
+        gw.index_add_(0, idx, g.contiguous())
+        return gw, None
+
+
+def embed_rows(weight: Tensor, idx: Tensor) -> Tensor:
+    """Embedding lookup for a few thousand per-ray indices (field_components/embedding.py:48-55)."""
+    return _EmbedRowsFn.apply(weight, idx)
+
+
+class _CameraOptFn(torch.autograd.Function):
+    """CameraOptimizer.apply_to_raybundle (SO3xR3 / shared) as one kernel each way (csrc/tn_model.cu)."""
+
+    @staticmethod
+    def forward(ctx, pose, frozen, cam, origins, directions, shared):
+        pose, origins, directions = _f32c(pose), _f32c(origins), _f32c(directions)
+        cam = cam.contiguous()
+        r = origins.shape[0]
+        oo, dd = torch.empty_like(origins), torch.empty_like(directions)
+        call("tn_camera_opt_fwd", ptr(pose), ptr(frozen), ptr(cam), ptr(origins), ptr(directions), r, int(shared),
+             ptr(oo), ptr(dd), stream())
+        ctx.shared = int(shared)
+        ctx.save_for_backward(pose, frozen, cam, directions)
+        return oo, dd
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        pose, frozen, cam, directions = ctx.saved_tensors
+        dpose = torch.zeros_like(pose)
+        call("tn_camera_opt_bwd", ptr(pose), ptr(frozen), ptr(cam), ptr(directions),
+             ptr(None if g_o is None else _f32c(g_o)), ptr(None if g_d is None else _f32c(g_d)), directions.shape[0],
+             ctx.shared, ptr(dpose), stream())
+        # rays are data: the reference's bundle tensors do not require grad either
+        return dpose, None, None, None, None, None
+
+
+def camera_opt_apply(pose: Tensor, frozen: Optional[Tensor], camera_indices: Tensor, origins: Tensor,
+                     directions: Tensor, shared: bool) -> Tuple[Tensor, Tensor]:
+    """(origins + t_c, R(w_c) directions) for the per-camera pose adjustments.
+    cameras/camera_optimizers.py:132-176, cameras/lie_groups.py:24-59."""
+    return _CameraOptFn.apply(pose, frozen, camera_indices, origins, directions, shared)
+
+
+class _PixelLossesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb, thermal, image, is_thermal):
+        rgb, image, is_thermal = _f32c(rgb), _f32c(image), _f32c(is_thermal)
+        thermal = None if thermal is None else _f32c(thermal).view(-1)
+        losses = torch.empty((4,), device=rgb.device)
+        call("tn_pixel_losses", ptr(rgb), ptr(thermal), ptr(image), ptr(is_thermal), rgb.shape[0], None, ptr(losses),
+             None, None, stream())
+        ctx.has_thermal = thermal is not None
+        ctx.save_for_backward(rgb, thermal, image, is_thermal)
+        return losses
+
+    @staticmethod
+    def backward(ctx, g):
+        rgb, thermal, image, is_thermal = ctx.saved_tensors
+        d_rgb = torch.empty_like(rgb)
+        d_th = torch.empty_like(thermal) if ctx.has_thermal else None
+        call("tn_pixel_losses", ptr(rgb), ptr(thermal), ptr(image), ptr(is_thermal), rgb.shape[0], ptr(_f32c(g)), None,
+             ptr(d_rgb), ptr(d_th), stream())
+        return d_rgb, (None if d_th is None else d_th.view(-1, 1)), None, None
+
+
+def pixel_losses(rgb: Tensor, thermal: Optional[Tensor], image: Tensor, is_thermal: Tensor) -> Tensor:
+    """[rgb MSE, thermal MSE, tv_pixel, cross_channel] (un-multiplied) for a patch-ordered batch.
+    models/thermal_nerfacto.py:286-354; rgb[R,3], thermal[R,1] or None, image[R,3], is_thermal[R]."""
+    return _PixelLossesFn.apply(rgb, thermal, image, is_thermal)
+
+
+_L1_PARTIALS = 64
+
+
+class _DensityL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d, d2, dt, d2t, mult, rgb_mult):
+        ctx.shape = d.shape
+        d, d2, dt, d2t = (_f32c(t).view(-1) for t in (d, d2, dt, d2t))
+        n = d.numel()
+        if rgb_mult == 1:  # symmetric branch (:331-334)
+            vm, m, rm = mult, mult, mult
+        else:              # asymmetric stop-gradient pattern (:336-344)
+            vm, m, rm = mult * (1.0 + rgb_mult), mult, mult * rgb_mult
+        partial = torch.empty((_L1_PARTIALS,), device=d.device)
+        grads = [torch.empty_like(d) for _ in range(4)]
+        call("tn_density_l1", ptr(d), ptr(d2), ptr(dt), ptr(d2t), n, float(vm), float(m), float(rm), ptr(partial),
+             _L1_PARTIALS, ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), ptr(grads[3]), stream())
+        ctx.save_for_backward(*grads)
+        return partial.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        s = ctx.shape
+        return (*[(t * g).view(s) for t in ctx.saved_tensors], None, None)
+
+
+def density_l1(d: Tensor, d2: Tensor, dt: Tensor, d2t: Tensor, mult: float, rgb_mult: float) -> Tensor:
+    """density_loss of ThermalNerfactoModel.get_loss_dict (models/thermal_nerfacto.py:328-344), value and the
+    gradients to all four densities in one launch."""
+    return _DensityL1Fn.apply(d, d2, dt, d2t, mult, rgb_mult)
 
 
 class _DistortionFn(torch.autograd.Function):

@@ -15,6 +15,7 @@ import torch
 from torch import Tensor, nn
 from torch.nn import Parameter
 
+from . import fused_ops, ops
 from .field_components import SceneContraction
 from .fields import FieldHeadNames, HashMLPDensityField, ThermalNerfactoField
 from .losses import L1Loss, MSELoss, cross_channel_loss, distortion_loss, interlevel_loss, tv_pixel_loss
@@ -69,6 +70,8 @@ class CameraOptimizer(nn.Module):
             frozen[non_trainable_camera_indices.long()] = True
         self.has_frozen = non_trainable_camera_indices is not None
         self.register_buffer("_frozen", frozen, persistent=False)
+        self.register_buffer("_frozen_u8", frozen.to(torch.uint8), persistent=False)
+        self.fused = True  # single-kernel apply_to_raybundle on CUDA (the torch expression is kept in forward())
 
     def forward(self, indices: Tensor) -> Tensor:
         if self.config.mode == "off":
@@ -83,6 +86,13 @@ class CameraOptimizer(nn.Module):
         return out
 
     def apply_to_raybundle(self, raybundle: RayBundle) -> None:
+        if self.config.mode != "off" and self.fused and raybundle.origins.is_cuda and raybundle.origins.dim() == 2:
+            # exp map + masking + translation + rotation of the bundle as one kernel (and one for the backward)
+            raybundle.origins, raybundle.directions = fused_ops.camera_opt_apply(
+                self.pose_adjustment, self._frozen_u8 if self.has_frozen else None,
+                raybundle.camera_indices.reshape(-1), raybundle.origins, raybundle.directions,
+                self.config.mode == "shared_SO3xR3")
+            return
         if self.config.mode != "off":
             c = self(raybundle.camera_indices.squeeze(-1))
             raybundle.origins = raybundle.origins + c[:, :3, 3]
@@ -204,6 +214,7 @@ class ThermalNerfactoModel(nn.Module):
         self.num_train_data = num_train_data
         self.kwargs = dict(metadata=metadata or {}, **kwargs)
         self.device_indicator_param = nn.Parameter(torch.empty(0))  # models/base_model.py:85
+        self.fuse_losses = True  # pixel / density loss terms as single kernels (torch expressions otherwise)
         self._populate(aabb)
 
     @property
@@ -333,11 +344,21 @@ class ThermalNerfactoModel(nn.Module):
         weights = ray_samples.get_weights(field_outputs[FieldHeadNames.DENSITY])
         weights_list.append(weights)
         ray_samples_list.append(ray_samples)
-        rgb = renderer(rgb=field_outputs[FieldHeadNames.RGB], weights=weights)
-        with torch.no_grad():
-            depth = self.renderer_depth(weights=weights, ray_samples=ray_samples)
-        expected_depth = self.renderer_expected_depth(weights=weights, ray_samples=ray_samples)
-        accumulation = self.renderer_accumulation(weights=weights)
+        colour = field_outputs[FieldHeadNames.RGB]
+        bg_mode, bg_const, bg_per_ray = renderer._bg_args(renderer.background_color, colour.shape[-1])
+        if bg_per_ray is None and weights.dim() == 3:
+            # the four renderer calls below (models/nerfacto.py:316-320) read the same weights: one launch
+            r_, s_ = weights.shape[0], weights.shape[1]
+            rgb, accumulation, depth, exp_raw, minmax = ops.render(
+                weights.reshape(r_, s_), colour, ray_samples.frustums.starts, ray_samples.frustums.ends,
+                bg_mode=bg_mode, bg=bg_const, eval_mode=not self.training, want_depth=True)
+            expected_depth = torch.clamp(exp_raw, minmax[0], minmax[1])  # batch-global clip, renderers.py:574
+        else:
+            rgb = renderer(rgb=colour, weights=weights)
+            with torch.no_grad():
+                depth = self.renderer_depth(weights=weights, ray_samples=ray_samples)
+            expected_depth = self.renderer_expected_depth(weights=weights, ray_samples=ray_samples)
+            accumulation = self.renderer_accumulation(weights=weights)
         outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth, "expected_depth": expected_depth,
                    "density": field_outputs[FieldHeadNames.DENSITY]}
         if self.training:
@@ -447,22 +468,35 @@ class ThermalNerfactoModel(nn.Module):
         loss_dict = {}
         image = batch["image"].to(self.device)
         is_thermal = batch["is_thermal"].to(self.device)
-        if c.density_mode != "rgb_only":
-            pred = torch.cat((outputs["rgb"], outputs["rgb_thermal"]), dim=1)
+        fused_pixels = (self.fuse_losses and c.background_color != "random" and image.shape[-1] == 3
+                        and image.shape[0] % 4 == 0)
+        if fused_pixels:
+            # rgb / thermal MSE, tv_pixel and cross_channel terms (:315-354) in one launch each way
+            thermal = outputs["rgb_thermal"] if c.density_mode != "rgb_only" else None
+            pl = fused_ops.pixel_losses(outputs["rgb"], thermal, image, is_thermal)
+            loss_dict["rgb_loss"] = pl[0]
+            if c.density_mode != "rgb_only":
+                loss_dict["thermal_loss"] = c.thermal_loss_mult * pl[1]
         else:
-            pred = torch.cat((outputs["rgb"], torch.zeros(outputs["rgb"].shape[0], 1, device=self.device)), dim=1)
-        pred_rgb, gt_rgb = self.renderer_rgbt.blend_background_for_loss_computation(
-            pred_image=pred, pred_accumulation=outputs["accumulation"], gt_image=image, is_thermal=is_thermal)
-        is_rgb = (1 - is_thermal)[:, None]
-        loss_dict["rgb_loss"] = self.rgb_loss(gt_rgb[..., :3] * is_rgb, pred_rgb[..., :3] * is_rgb)
-        if c.density_mode != "rgb_only":
-            th = is_thermal[:, None]
-            loss_dict["thermal_loss"] = c.thermal_loss_mult * self.rgb_loss(gt_rgb[..., 3:] * th, pred_rgb[..., 3:] * th)
+            if c.density_mode != "rgb_only":
+                pred = torch.cat((outputs["rgb"], outputs["rgb_thermal"]), dim=1)
+            else:
+                pred = torch.cat((outputs["rgb"], torch.zeros(outputs["rgb"].shape[0], 1, device=self.device)), dim=1)
+            pred_rgb, gt_rgb = self.renderer_rgbt.blend_background_for_loss_computation(
+                pred_image=pred, pred_accumulation=outputs["accumulation"], gt_image=image, is_thermal=is_thermal)
+            is_rgb = (1 - is_thermal)[:, None]
+            loss_dict["rgb_loss"] = self.rgb_loss(gt_rgb[..., :3] * is_rgb, pred_rgb[..., :3] * is_rgb)
+            if c.density_mode != "rgb_only":
+                th = is_thermal[:, None]
+                loss_dict["thermal_loss"] = c.thermal_loss_mult * self.rgb_loss(gt_rgb[..., 3:] * th,
+                                                                              pred_rgb[..., 3:] * th)
         if c.density_mode == "separate" and c.density_loss_mult > 0:
             m, r = c.density_loss_mult, c.rgb_density_loss_mult
             d, d2, dt, d2t = (outputs["density"], outputs["density2"], outputs["density_thermal"],
                               outputs["density2_thermal"])
-            if r == 1:
+            if self.fuse_losses:  # the four L1 terms and their stop-gradient pattern (:328-344) in one launch
+                loss_dict["density_loss"] = fused_ops.density_l1(d, d2, dt, d2t, m, r)
+            elif r == 1:
                 loss_dict["density_loss"] = m * self.density_loss(d2, dt) + m * self.density_loss(d, d2t)
             else:  # asymmetric stop-gradient pattern, :336-344
                 loss_dict["density_loss"] = (m * self.density_loss(d2.detach(), dt)
@@ -470,10 +504,11 @@ class ThermalNerfactoModel(nn.Module):
                                              + r * m * self.density_loss(d2, dt.detach())
                                              + r * m * self.density_loss(d, d2t.detach()))
         if c.density_mode != "rgb_only" and c.tv_pixel_loss_mult > 0:
-            loss_dict["tv_pixel_loss"] = c.tv_pixel_loss_mult * tv_pixel_loss(pred_rgb[..., 3:], is_thermal)
+            loss_dict["tv_pixel_loss"] = c.tv_pixel_loss_mult * (
+                pl[2] if fused_pixels else tv_pixel_loss(pred_rgb[..., 3:], is_thermal))
         if c.density_mode != "rgb_only" and c.cross_channel_loss_mult > 0:
-            loss_dict["cross_channel_loss"] = c.cross_channel_loss_mult * cross_channel_loss(
-                pred_rgb[..., 3:], gt_rgb[..., :3], is_thermal)
+            loss_dict["cross_channel_loss"] = c.cross_channel_loss_mult * (
+                pl[3] if fused_pixels else cross_channel_loss(pred_rgb[..., 3:], gt_rgb[..., :3], is_thermal))
         if self.training:
             loss_dict["interlevel_loss"] = 0
             loss_dict["distortion_loss"] = 0

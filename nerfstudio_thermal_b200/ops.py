@@ -159,10 +159,11 @@ MLP_BACKEND = {"fwd": "tc", "bwd": "tc"}
 
 class _MlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, out_act, *wb):
+    def forward(ctx, x, out_act, sinks, *wb):
         x = _f32c(x)
         ws = [_f32c(t) for t in wb[0::2]]
         bs = [_f32c(t) for t in wb[1::2]]
+        ctx.sinks = sinks
         n, in_dim = x.shape
         width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
         y = torch.empty((n, out_dim), device=x.device)
@@ -188,8 +189,12 @@ class _MlpFn(torch.autograd.Function):
         ws, bs = list(saved[2:2 + nl]), list(saved[2 + nl:])
         n, in_dim = x.shape
         width, out_dim = ws[0].shape[0], ws[-1].shape[0]
-        dws = [torch.zeros_like(w) for w in ws]
-        dbs = [torch.zeros_like(b) for b in bs]
+        sinks = ctx.sinks
+        if sinks is not None:  # accumulate straight into the parameters' (flat-buffer) gradients
+            dws, dbs = [s[0] for s in sinks], [s[1] for s in sinks]
+        else:
+            dws = [torch.zeros_like(w) for w in ws]
+            dbs = [torch.zeros_like(b) for b in bs]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
         if MLP_BACKEND["bwd"] == "tc":
@@ -200,16 +205,19 @@ class _MlpFn(torch.autograd.Function):
                  ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
         grads = []
         for dw, db in zip(dws, dbs):
-            grads += [dw, db]
-        return (dx, None, *grads)
+            grads += [None, None] if sinks is not None else [dw, db]
+        return (dx, None, None, *grads)
 
 
-def mlp(x: Tensor, weights: List[Tensor], biases: List[Tensor], out_act: int = ACT_NONE) -> Tensor:
-    """Fully fused MLP (ReLU hidden activations).  field_components/mlp.py:159-178."""
+def mlp(x: Tensor, weights: List[Tensor], biases: List[Tensor], out_act: int = ACT_NONE, sinks=None) -> Tensor:
+    """Fully fused MLP (ReLU hidden activations).  field_components/mlp.py:159-178.
+
+    sinks: optional [(dW_i, db_i)] float32 tensors the backward kernel accumulates INTO (the parameters' slices of
+    a FlatGradBuffer); autograd then receives no weight gradients."""
     wb = []
     for w, b in zip(weights, biases):
         wb += [w, b]
-    return _MlpFn.apply(x, out_act, *wb)
+    return _MlpFn.apply(x, out_act, sinks, *wb)
 
 
 def mlp_shape_supported(in_dim: int, width: int, out_dim: int, n_layers: int) -> bool:

@@ -48,12 +48,16 @@ class FlatGradBuffer:
         """Let every HashEncoding of `module` scatter its table gradient directly into this buffer (the
         backward kernel accumulates into the parameter's slice; no temporary, no extra add pass).  The caller
         must `zero_()` the buffer once per step.  Returns the number of tables attached."""
-        from .field_components import HashEncoding
+        from .field_components import MLP, HashEncoding
 
         n = 0
         for m in module.modules():
             if isinstance(m, HashEncoding) and m.hash_table.grad is not None:
                 m.grad_sink = m.hash_table.grad
+                n += 1
+            elif isinstance(m, MLP) and all(l.weight.grad is not None and l.bias.grad is not None for l in m.layers):
+                # MLP backward kernels add dW/db straight into the buffer too (no temporaries, no accumulate pass)
+                m.grad_sinks = [(l.weight.grad, l.bias.grad) for l in m.layers]
                 n += 1
         return n
 

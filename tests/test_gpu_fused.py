@@ -163,3 +163,87 @@ def test_fused_proposal_field_vs_oracle(S, max_res):
     # and the unfused kernel chain gives the same density
     field.fuse = False
     close(field.get_density(rs)[0], dens, 1e-6, 1e-5)
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_camera_optimizer_kernel(shared):
+    torch.manual_seed(5)
+    R, cams = 257, 8
+    pose = (torch.randn(1 if shared else cams, 6) * 0.05)
+    pose[0 if shared else 3, 3:] = 0.0  # |w| below the 1e-4 clamp: constant-angle branch
+    pose = pose.requires_grad_(True)
+    frozen = torch.tensor([False] * 5 + [True] * 3)
+    idx = torch.randint(0, cams, (R, 1))
+    o, d = torch.randn(R, 3), torch.nn.functional.normalize(torch.randn(R, 3), dim=-1)
+    src = pose.expand(cams, 6) if shared else pose
+    ro, rd = om.apply_camera_optimizer(src, frozen, idx, o, d)
+    go, gd = torch.randn(R, 3), torch.randn(R, 3)
+    ((ro * go).sum() + (rd * gd).sum()).backward()
+    pg = pose.detach().to(DEV).requires_grad_(True)
+    oo, dd = fused_ops.camera_opt_apply(pg, frozen.to(torch.uint8).to(DEV), idx.view(-1).to(DEV), o.to(DEV), d.to(DEV),
+                                        shared)
+    close(oo, ro, 1e-6, 1e-6)
+    close(dd, rd, 1e-6, 1e-6)
+    ((oo * go.to(DEV)).sum() + (dd * gd.to(DEV)).sum()).backward()
+    close(pg.grad, pose.grad, 2e-4, 1e-4)
+    # and through the module, fused vs torch expression
+    opt = tn.CameraOptimizer(tn.CameraOptimizerConfig(mode="SO3xR3"), cams,
+                             non_trainable_camera_indices=torch.tensor([5, 6, 7])).to(DEV)
+    with torch.no_grad():
+        opt.pose_adjustment.normal_(0, 0.05)
+    rb1 = tn.RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                       camera_indices=idx.to(DEV))
+    rb2 = tn.RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                       camera_indices=idx.to(DEV))
+    opt.apply_to_raybundle(rb1)
+    opt.fused = False
+    opt.apply_to_raybundle(rb2)
+    close(rb1.origins, rb2.origins, 1e-6, 1e-6)
+    close(rb1.directions, rb2.directions, 1e-6, 1e-6)
+
+
+@pytest.mark.parametrize("with_thermal", [True, False])
+def test_pixel_losses_kernel(with_thermal):
+    torch.manual_seed(6)
+    R = 512
+    is_thermal = (torch.arange(R // 4) % 3 == 1).float().repeat_interleave(4)
+    rgb = torch.rand(R, 3, requires_grad=True)
+    th = torch.rand(R, 1, requires_grad=True)
+    image = torch.rand(R, 3)
+    cfg = oracle.OracleConfig(density_mode="shared" if with_thermal else "rgb_only")
+    outs = {"rgb": rgb, "rgb_thermal": th}
+    ref = oracle.thermal_nerfacto_losses({}, cfg, outs, image, is_thermal, training=False)
+    up = torch.tensor([0.7, 1.3, 0.4, 2.0])
+    keys = ["rgb_loss", "thermal_loss", "tv_pixel_loss", "cross_channel_loss"]
+    mults = [1.0, cfg.thermal_loss_mult, cfg.tv_pixel_loss_mult, cfg.cross_channel_loss_mult]
+    total = sum(up[i] * ref[k] / mults[i] for i, k in enumerate(keys) if k in ref)
+    total.backward()
+    rg = rgb.detach().to(DEV).requires_grad_(True)
+    tg = th.detach().to(DEV).requires_grad_(True)
+    pl = fused_ops.pixel_losses(rg, tg if with_thermal else None, image.to(DEV), is_thermal.to(DEV))
+    for i, k in enumerate(keys):
+        if k in ref:
+            close(pl[i], ref[k] / mults[i], 1e-7, 1e-5)
+    (pl * up.to(DEV)).sum().backward()
+    close(rg.grad, rgb.grad, 1e-8, 1e-4)
+    if with_thermal:
+        close(tg.grad, th.grad, 1e-8, 1e-4)
+
+
+@pytest.mark.parametrize("rgb_mult", [0.01, 1.0])
+def test_density_l1_kernel(rgb_mult):
+    torch.manual_seed(7)
+    shape = (37, 48, 1)
+    ts = [(torch.rand(shape) * 5).requires_grad_(True) for _ in range(4)]
+    cfg = oracle.OracleConfig(density_mode="separate", rgb_density_loss_mult=rgb_mult, tv_pixel_loss_mult=0,
+                              cross_channel_loss_mult=0)
+    outs = {"density": ts[0], "density2": ts[1], "density_thermal": ts[2], "density2_thermal": ts[3],
+            "rgb": torch.zeros(4, 3), "rgb_thermal": torch.zeros(4, 1)}
+    ref = oracle.thermal_nerfacto_losses({}, cfg, outs, torch.zeros(4, 3), torch.zeros(4), training=False)["density_loss"]
+    ref.backward()
+    gs = [t.detach().to(DEV).requires_grad_(True) for t in ts]
+    got = fused_ops.density_l1(gs[0], gs[1], gs[2], gs[3], cfg.density_loss_mult, rgb_mult)
+    close(got, ref, 1e-9, 1e-5)
+    got.backward()
+    for a, b in zip(gs, ts):
+        close(a.grad, b.grad, 1e-12, 1e-5)
