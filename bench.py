@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--half-tables", action="store_true", help="fp16 gather caches of the hash tables")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--mode", choices=["train", "render"], default="train",
+                    help="train: BASELINE configs[1] (the headline metric); render: configs[2] full-frame eval render")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel time table to stderr")
     return ap.parse_args()
 
@@ -206,6 +208,103 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ render (config 3)
+def pinhole_rays(width, height, cam_index, seed):
+    """Rays of one pinhole camera looking at the origin from a seeded position (keep_shape=True layout [H,W,*])."""
+    g = torch.Generator().manual_seed(seed)
+    eye = torch.nn.functional.normalize(torch.randn(3, generator=g), dim=0) * 0.8
+    fwd = -eye / eye.norm()
+    right = torch.nn.functional.normalize(torch.linalg.cross(fwd, torch.tensor([0.0, 0.0, 1.0])), dim=0)
+    up = torch.linalg.cross(right, fwd)
+    f = 0.9 * width
+    ys, xs = torch.meshgrid(torch.arange(height, dtype=torch.float32), torch.arange(width, dtype=torch.float32),
+                            indexing="ij")
+    d = fwd[None, None] + ((xs - width / 2 + 0.5) / f)[..., None] * right + (-(ys - height / 2 + 0.5) / f)[..., None] * up
+    d = torch.nn.functional.normalize(d, dim=-1)
+    o = eye.expand(height, width, 3).contiguous()
+    return dict(origins=o, directions=d, pixel_area=torch.full((height, width, 1), 1.0 / (f * f)),
+                camera_indices=torch.full((height, width, 1), cam_index, dtype=torch.long))
+
+
+def run_render(args):
+    """BASELINE.json configs[2]: full-frame eval render, 640x512 thermal + 1920x1080 RGB camera, rays sharded over
+    the ranks on the reference's chunk boundaries (eval_num_rays_per_chunk = 1<<15), zero communication."""
+    import torch.distributed as dist
+
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    model = build_model(args).to(dev).eval()
+    frames = [pinhole_rays(640, 512, NUM_CAMERAS - 1, 7), pinhole_rays(1920, 1080, 0, 8)]
+    keys = ["rgb", "rgb_thermal", "depth", "depth_thermal", "accumulation", "accumulation_thermal"]
+    if args.density_mode != "separate":
+        keys = [k for k in keys if not k.endswith("_thermal") or k == "rgb_thermal"]
+    if args.density_mode == "rgb_only":
+        keys = ["rgb", "depth", "accumulation"]
+    chunk = model.config.eval_num_rays_per_chunk
+    host_frames = [{k: v.reshape(-1, v.shape[-1]).pin_memory() for k, v in fr.items()} for fr in frames]
+    total_rays = sum(fr["origins"].shape[0] for fr in host_frames)
+
+    def render_all(from_host):
+        outs = []
+        with torch.no_grad():
+            for fr in host_frames:
+                n = fr["origins"].shape[0]
+                for s, e in parallel.shard_chunks(n, chunk, rank, world):
+                    b = {k: v[s:e].to(dev, non_blocking=True) for k, v in fr.items()}
+                    res = model(tn.RayBundle(origins=b["origins"], directions=b["directions"],
+                                             pixel_area=b["pixel_area"], camera_indices=b["camera_indices"]))
+                    if from_host:  # end to end: rendered chunk back to the host, as base_model.py:200-203 does
+                        outs.append({k: res[k].to("cpu", non_blocking=True) for k in keys})
+                    else:
+                        outs.append(res[keys[0]])
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        render_all(False)
+    steps = max(1, min(args.steps, 5))
+    times = {}
+    for name, from_host in (("value", False), ("e2e", True)):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            render_all(from_host)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times[name] = ms.item() / steps
+    if rank == 0:
+        out_bytes = sum({"rgb": 12, "rgb_thermal": 4}.get(k, 4) for k in keys) * total_rays
+        line = {
+            "metric": "render rays/s, thermal-nerfacto", "value": total_rays / (times["value"] * 1e-3), "unit": "rays/s",
+            "n_gpus": world, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": times["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"full-frame eval render 640x512 thermal + 1920x1080 RGB, density_mode={args.density_mode}, "
+                                   f"chunks of {chunk} rays sharded over {world} rank(s)", "rays_per_step": total_rays,
+                       "init": args.init, "parallelism": f"dp{world}"},
+            "e2e": {"value": total_rays / (times["e2e"] * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 52 * total_rays,
+                    "d2h_bytes_per_step": out_bytes, "ms_per_step": times["e2e"]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -357,5 +456,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mode == "render":
+        run_render(a)
     else:
         run_b200(a)
