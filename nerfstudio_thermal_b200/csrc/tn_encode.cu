@@ -145,6 +145,9 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
   __syncthreads();
   const int rowmod = tid % L;
   float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+  // One level per iteration on purpose. Prefetching the next level's corner rows one iteration ahead (16 gathers
+  // in flight) and merging x-neighbour rows into 16-byte accesses were both measured and both lost: the kernel
+  // is bound by L2 atomic throughput, not by gather latency ("experiments that lost").
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const float scale = sc.s[l];

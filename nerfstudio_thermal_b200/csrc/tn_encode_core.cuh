@@ -12,6 +12,10 @@ struct LevelScales {
 constexpr uint32_t kPrimeY = 2654435761u;  // encodings.py:413
 constexpr uint32_t kPrimeZ = 805459861u;
 constexpr int kPts = 128;                  // points per CTA
+// Measured on B200 (profiles/): fetching / reducing adjacent x-pairs of corners as one 16-byte access lowers the L2
+// sector count by 25 % but is SLOWER (bwd main grid 0.633 -> 0.654 ms/step, fused proposal bwd 0.475 -> 0.557): the
+// atomic path is bound by REDs per lane-address, and unmerged lanes pay a padded 16-byte RED plus the 8-byte one.
+constexpr bool kMergeXPairs = false;
 
 template <int F, bool HALF>
 __device__ __forceinline__ void load_row(const void* __restrict__ table, uint32_t row, float (&f)[F]) {
@@ -48,6 +52,7 @@ struct Cell {
   uint32_t idx[8];
   float ox, oy, oz;
   uint64_t key;  // identifies (floor, ceil) triple: equal keys <=> identical eight rows
+  bool xmerge;   // floor(x) even and ceil(x) = floor(x)+1: each x-pair of corners is one aligned pair of rows
 };
 
 __device__ __forceinline__ Cell locate(float x0, float x1, float x2, float scale, uint32_t mask, uint32_t base) {
@@ -73,6 +78,9 @@ __device__ __forceinline__ Cell locate(float x0, float x1, float x2, float scale
   c.key = (uint64_t)(uint32_t)(lo0 & 0xFFFFF) | ((uint64_t)(uint32_t)(lo1 & 0xFFFFF) << 20) |
           ((uint64_t)(uint32_t)(lo2 & 0xFFFFF) << 40) | ((uint64_t)(hi0 != lo0) << 60) |
           ((uint64_t)(hi1 != lo1) << 61) | ((uint64_t)(hi2 != lo2) << 62);
+  // hash = x ^ (y*P1) ^ (z*P2): for even floor(x) the ceil corner's row is the floor corner's row with bit 0
+  // flipped, i.e. the two rows of an x-pair are adjacent and 2-row aligned
+  c.xmerge = ((lo0 & 1) == 0) && (hi0 == lo0 + 1);
   return c;
 }
 
@@ -86,6 +94,61 @@ __device__ __forceinline__ void red_row(float* __restrict__ dtable, uint32_t row
   } else {
 #pragma unroll
     for (int i = 0; i < F; i += 4) red_add_v4(a + i, g[i], g[i + 1], g[i + 2], g[i + 3]);
+  }
+}
+
+// The eight corner rows of a cell.  For F = 2 fp32 tables the four x-pairs {3,0} {2,1} {7,4} {6,5} (floor-x corner,
+// ceil-x corner) are fetched as ONE 16-byte access each when the pair is adjacent (Cell::xmerge, half of all cells):
+// 6 L2 sector accesses per cell on average instead of 8.  Values are identical to eight separate loads.
+template <int F, bool HALF>
+__device__ __forceinline__ void load_cell(const void* __restrict__ table, const Cell& c, float (&f)[8][F]) {
+  if constexpr (kMergeXPairs && F == 2 && !HALF) {
+    const float* t = reinterpret_cast<const float*>(table);
+    constexpr int pf[4] = {3, 2, 7, 6}, pc[4] = {0, 1, 4, 5};
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = __ldg(reinterpret_cast<const float4*>(t + (size_t)(c.idx[pf[q]] & ~1u) * 2));
+    float2 w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      w[q] = make_float2(0.f, 0.f);
+      if (!c.xmerge) w[q] = __ldg(reinterpret_cast<const float2*>(t + (size_t)c.idx[pc[q]] * 2));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool odd = c.idx[pf[q]] & 1u;
+      f[pf[q]][0] = odd ? v[q].z : v[q].x;
+      f[pf[q]][1] = odd ? v[q].w : v[q].y;
+      f[pc[q]][0] = c.xmerge ? (odd ? v[q].x : v[q].z) : w[q].x;
+      f[pc[q]][1] = c.xmerge ? (odd ? v[q].y : v[q].w) : w[q].y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
+  }
+}
+
+// scatter-add the eight corner gradients; same pairing: one 16-byte RED per adjacent x-pair
+template <int F>
+__device__ __forceinline__ void red_cell(float* __restrict__ dtable, const Cell& c, const float (&g)[8][F]) {
+  if constexpr (kMergeXPairs && F == 2) {
+    constexpr int pf[4] = {3, 2, 7, 6}, pc[4] = {0, 1, 4, 5};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t rf = c.idx[pf[q]];
+      const bool odd = rf & 1u;
+      const float cx = c.xmerge ? g[pc[q]][0] : 0.f, cy = c.xmerge ? g[pc[q]][1] : 0.f;
+      float* a = dtable + (size_t)(rf & ~1u) * 2;
+      if (odd) red_add_v4(a, cx, cy, g[pf[q]][0], g[pf[q]][1]);
+      else red_add_v4(a, g[pf[q]][0], g[pf[q]][1], cx, cy);
+    }
+    if (!c.xmerge) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) red_add_v2(dtable + (size_t)c.idx[pc[q]] * 2, g[pc[q]][0], g[pc[q]][1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red_row<F>(dtable, c.idx[k], g[k]);
   }
 }
 

@@ -46,10 +46,13 @@ __device__ __forceinline__ void load_prop_weights(PropWeights& sw, const float* 
   if (threadIdx.x == 0) sw.b2 = __ldg(b2);
 }
 
-// features of one point: all levels, 8 gathers each, two levels' gathers in flight together
-template <int L>
+// features of one point: all levels, 8 gathers each, two levels' gathers in flight together.
+// JAC additionally returns d(feat[k])/d(x) (already times the level scale), so the backward kernel never gathers
+// the corner rows a second time.
+template <int L, bool JAC>
 __device__ __forceinline__ void prop_features(const float* __restrict__ table, const float* s_scale, uint32_t mask,
-                                              uint32_t T, float x0, float x1, float x2, float (&feat)[2 * L]) {
+                                              uint32_t T, float x0, float x1, float x2, float (&feat)[2 * L],
+                                              float (&jac)[JAC ? 2 * L : 1][3]) {
 #pragma unroll
   for (int l0 = 0; l0 < L; l0 += 2) {
     Cell c[2];
@@ -60,9 +63,7 @@ __device__ __forceinline__ void prop_features(const float* __restrict__ table, c
       c[b] = locate(x0, x1, x2, s_scale[l], mask, (uint32_t)l * T);
     }
 #pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) load_row<2, false>(table, c[b].idx[k], f[b][k]);
+    for (int b = 0; b < 2; ++b) load_cell<2, false>(table, c[b], f[b]);
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       if (l0 + b < L) {
@@ -77,6 +78,14 @@ __device__ __forceinline__ void prop_features(const float* __restrict__ table, c
           const float f0312 = f03 * oy + f12 * my;
           const float f4756 = f47 * oy + f56 * my;
           feat[(l0 + b) * 2 + j] = f0312 * oz + f4756 * mz;
+          if constexpr (JAC) {
+            const float sl = s_scale[l0 + b];
+            const float e03 = f[b][0][j] - f[b][3][j], e12 = f[b][1][j] - f[b][2][j];
+            const float e56 = f[b][5][j] - f[b][6][j], e47 = f[b][4][j] - f[b][7][j];
+            jac[(l0 + b) * 2 + j][0] = ((e03 * oy + e12 * my) * oz + (e47 * oy + e56 * my) * mz) * sl;
+            jac[(l0 + b) * 2 + j][1] = ((f03 - f12) * oz + (f47 - f56) * mz) * sl;
+            jac[(l0 + b) * 2 + j][2] = (f0312 - f4756) * sl;
+          }
         }
       }
     }
@@ -120,8 +129,8 @@ __global__ void __launch_bounds__(kPts, 4) prop_fwd_kernel(const float* __restri
     float x1 = sample_pos(__ldg(origins + 3 * r + 1), __ldg(dirs + 3 * r + 1), st, en);
     float x2 = sample_pos(__ldg(origins + 3 * r + 2), __ldg(dirs + 3 * r + 2), st, en);
     const float sel = contract_normalise(x0, x1, x2);
-    float feat[2 * L], h[PH];
-    prop_features<L>(table, s_scale, mask, T, x0, x1, x2, feat);
+    float feat[2 * L], h[PH], nojac[1][3];
+    prop_features<L, false>(table, s_scale, mask, T, x0, x1, x2, feat, nojac);
     const float raw = prop_mlp<L>(sw, feat, h);
     density[p] = scale * expf(raw) * sel;
   }
@@ -168,8 +177,8 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
     const float p0 = sample_pos(o0, d0, st, en), p1 = sample_pos(o1, d1, st, en), p2 = sample_pos(o2, d2, st, en);
     float x0 = p0, x1 = p1, x2 = p2;
     const float sel = contract_normalise(x0, x1, x2);
-    float feat[IN], h[PH];
-    prop_features<L>(table, s_scale, mask, T, x0, x1, x2, feat);
+    float feat[IN], h[PH], jac[NEED_DX ? IN : 1][3];
+    prop_features<L, NEED_DX>(table, s_scale, mask, T, x0, x1, x2, feat, jac);
     const float raw = prop_mlp<L>(sw, feat, h);
     // d(density)/d(raw) = scale * sel * exp(clamp(raw, -15, 15))   (activations.py:41)
     const float g = valid ? __ldg(d_density + p) * scale * sel * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
@@ -188,20 +197,21 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
 #pragma unroll
     for (int k = 0; k < IN; ++k) stage[(2 * PH + k) * kStageStride + tid] = feat[k];
     stage[(2 * PH + 2 * PMAXL) * kStageStride + tid] = g;
-    // ---- encode backward: table scatter (+ dL/dx)
+    // ---- dL/dx from the Jacobian of the first pass, then the table scatter
     float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+    if constexpr (NEED_DX) {
+#pragma unroll
+      for (int k = 0; k < IN; ++k) {
+        dx0 = fmaf(dfeat[k], jac[k][0], dx0);
+        dx1 = fmaf(dfeat[k], jac[k][1], dx1);
+        dx2 = fmaf(dfeat[k], jac[k][2], dx2);
+      }
+    }
 #pragma unroll 1
     for (int l = 0; l < L; ++l) {
-      const float sc_l = s_scale[l];
-      const Cell c = locate(x0, x1, x2, sc_l, mask, (uint32_t)l * T);
-      float f[8][2];
-      if constexpr (NEED_DX) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) load_row<2, false>(table, c.idx[k], f[k]);
-      }
+      const Cell c = locate(x0, x1, x2, s_scale[l], mask, (uint32_t)l * T);
       const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
       float gc[8][2];
-      float dox = 0.f, doy = 0.f, doz = 0.f;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const float gj = dfeat[l * 2 + j];
@@ -212,21 +222,6 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
         gc[1][j] = g12 * c.ox; gc[2][j] = g12 * mx;
         gc[5][j] = g56 * c.ox; gc[6][j] = g56 * mx;
         gc[4][j] = g47 * c.ox; gc[7][j] = g47 * mx;
-        if constexpr (NEED_DX) {
-          const float f03 = f[0][j] * c.ox + f[3][j] * mx;
-          const float f12 = f[1][j] * c.ox + f[2][j] * mx;
-          const float f56 = f[5][j] * c.ox + f[6][j] * mx;
-          const float f47 = f[4][j] * c.ox + f[7][j] * mx;
-          const float f0312 = f03 * c.oy + f12 * my;
-          const float f4756 = f47 * c.oy + f56 * my;
-          dox += g03 * (f[0][j] - f[3][j]) + g12 * (f[1][j] - f[2][j]) + g56 * (f[5][j] - f[6][j]) +
-                 g47 * (f[4][j] - f[7][j]);
-          doy += g0312 * (f03 - f12) + g4756 * (f47 - f56);
-          doz += gj * (f0312 - f4756);
-        }
-      }
-      if constexpr (NEED_DX) {
-        dx0 += dox * sc_l; dx1 += doy * sc_l; dx2 += doz * sc_l;
       }
       bool issue = valid;
       if (l < n_coarse) {  // warp-uniform: fold contiguous runs of equal cells into their head lane
@@ -248,10 +243,7 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
         }
         issue = valid && head;
       }
-      if (issue) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) red_row<2>(dtable, c.idx[k], gc[k]);
-      }
+      if (issue) red_cell<2>(dtable, c, gc);
     }
     // ---- dL/dx -> contraction backward -> per-ray (origin, direction) gradients, folded over runs of one ray
     if constexpr (NEED_DX) {
