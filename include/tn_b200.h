@@ -95,16 +95,20 @@ int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width
  * are sums of bf16 terms, products a few MMAs accumulated in fp32: three terms / six MMAs in the forward
  * (fp32-faithful pre-activations, so ReLU masks agree with the fp32 reference), two terms / three MMAs in the
  * backward (~2e-5 relative).  Arguments as tn_mlp_fwd, plus:
+ * x_stride: floats between consecutive rows of x (and of dx); 0 = in_dim.  A stride that is a multiple of 4
+ *   with 16-byte aligned x lets a tile read whole 16-byte runs (a 63-wide input padded to 64: columns
+ *   [in_dim, x_stride) are ignored on read and written as zeros in dx when x_stride <= 64);
  * relu_mask_out: NULL, or uint32[N, n_layers-1, max(1,width/32)] receiving bit j of hidden layer l = (z_lj > 0). */
-int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
+int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int x_stride, int width, int out_dim, int n_layers,
                   const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
                   uint32_t* relu_mask_out, void* stream);
 /* Backward on the tensor cores as well (arguments as tn_mlp_bwd): activations recomputed per tile, dH = dZ.W
  * and dW^T += A^T.dZ as tcgen05 MMAs, dW/db accumulators resident in TMEM across the tiles of a persistent CTA
  * and flushed once with atomics.  relu_mask: the forward's masks (NULL: gate on the recomputed activations). */
-int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim, int width,
-                  int out_dim, int n_layers, const float* const* w_host_ptrs, const float* const* b_host_ptrs,
-                  int out_act, float* dx, float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
+int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim, int x_stride,
+                  int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
+                  const float* const* b_host_ptrs, int out_act, float* dx, float* const* dw_host_ptrs,
+                  float* const* db_host_ptrs, void* stream);
 
 /* Real spherical-harmonics basis, 4 levels (16 components).
  *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */
@@ -163,14 +167,15 @@ int tn_render_bwd(const float* weights, const float* colour, const float* starts
 /* replaces: fields/nerfacto_field.py:221-228 (split, trunc_exp, selector) + :335-344 (head input concatenation).
  * h[R*S, h_width] = density-MLP output (column 0 = raw density, columns 1..geo_dim = geometry features),
  * sel[R*S], sh[R,16] (per-ray SH basis), emb_ray[R,emb_dim] (per-ray appearance embedding, NULL if emb_dim = 0).
- * density_out[R*S] = density_scale * exp(h0) * sel;  x_out[R*S, 16+geo_dim+emb_dim] = [sh | geo | emb]. */
+ * density_out[R*S] = density_scale * exp(h0) * sel;  x_out[R*S, x_stride] = [sh | geo | emb | zero padding]
+ * (x_stride = 0 means 16+geo_dim+emb_dim; a stride of 64 gives the tensor-core MLP 16-byte aligned rows). */
 int tn_field_split_fwd(const float* h, const float* sel, const float* sh, const float* emb_ray, int64_t R, int S,
-                       int h_width, int geo_dim, int emb_dim, float density_scale, float* density_out,
-                       float* x_out, void* stream);
+                       int h_width, int geo_dim, int emb_dim, int x_stride, float density_scale,
+                       float* density_out, float* x_out, void* stream);
 /* d_density[R*S] and dx[R*S, in] (either may be NULL = zero) -> dh_out[R*S, h_width] (overwritten) and
  * demb_ray_out[R, emb_dim] (overwritten; sum over the samples of each ray; may be NULL). */
 int tn_field_split_bwd(const float* h, const float* sel, const float* d_density, const float* dx, int64_t R, int S,
-                       int h_width, int geo_dim, int emb_dim, float density_scale, float* dh_out,
+                       int h_width, int geo_dim, int emb_dim, int x_stride, float density_scale, float* dh_out,
                        float* demb_ray_out, void* stream);
 /* replaces: fields/density_fields.py:116-117.  density[i] = scale * trunc_exp(raw[i*raw_stride]) * sel[i] and its
  * backward (draw_out[i*draw_stride] is overwritten): raw may be a column of a row-major matrix. */

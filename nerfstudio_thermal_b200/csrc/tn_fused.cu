@@ -19,19 +19,19 @@ __device__ __forceinline__ float trunc_exp_grad(float x) { return expf(fminf(fma
 // one warp per row: lane l writes columns l and l+32 of the head input (coalesced 252-byte rows)
 __global__ void __launch_bounds__(32 * kWarps) field_split_fwd_kernel(
     const float* __restrict__ h, const float* __restrict__ sel, const float* __restrict__ sh,
-    const float* __restrict__ emb_ray, int64_t N, int S, int hw, int geo, int emb_dim, float scale,
+    const float* __restrict__ emb_ray, int64_t N, int S, int hw, int geo, int emb_dim, int xs, float scale,
     float* __restrict__ density, float* __restrict__ xout) {
   const int lane = threadIdx.x & 31;
-  const int in_dim = 16 + geo + emb_dim;
+  const int in_dim = 16 + geo + emb_dim;  // xs >= in_dim: row stride of xout, padding columns written as zero
   for (int64_t p = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); p < N; p += (int64_t)gridDim.x * kWarps) {
     const int64_t r = p / S;
     if (lane == 0) density[p] = scale * expf(__ldg(h + p * hw)) * __ldg(sel + p);
-    for (int c = lane; c < in_dim; c += 32) {
-      float v;
+    for (int c = lane; c < xs; c += 32) {
+      float v = 0.f;
       if (c < 16) v = __ldg(sh + r * 16 + c);
       else if (c < 16 + geo) v = __ldg(h + p * hw + 1 + (c - 16));
-      else v = __ldg(emb_ray + r * emb_dim + (c - 16 - geo));
-      xout[p * in_dim + c] = v;
+      else if (c < in_dim) v = __ldg(emb_ray + r * emb_dim + (c - 16 - geo));
+      xout[p * xs + c] = v;
     }
   }
 }
@@ -40,12 +40,12 @@ __global__ void __launch_bounds__(32 * kWarps) field_split_fwd_kernel(
 // d_emb_ray[r] = sum_s dX[r,s][16+geo:]
 __global__ void __launch_bounds__(32 * kWarps) field_split_bwd_kernel(
     const float* __restrict__ h, const float* __restrict__ sel, const float* __restrict__ d_density,
-    const float* __restrict__ dx, int64_t R, int S, int hw, int geo, int emb_dim, float scale, float* __restrict__ dh,
-    float* __restrict__ demb_ray) {
+    const float* __restrict__ dx, int64_t R, int S, int hw, int geo, int emb_dim, int xs, float scale,
+    float* __restrict__ dh, float* __restrict__ demb_ray) {
   const int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
-  const int in_dim = 16 + geo + emb_dim;
+  const int in_dim = xs;  // row stride of dx (>= 16 + geo + emb_dim)
   float acc0 = 0.f, acc1 = 0.f;  // lane's appearance columns: 16+geo+lane and 16+geo+lane+32
   for (int s = 0; s < S; ++s) {
     const int64_t p = r * S + s;
@@ -198,28 +198,33 @@ using namespace tn;
 static inline unsigned warp_blocks(int64_t n) { return (unsigned)((n + kWarps - 1) / kWarps); }
 
 extern "C" int tn_field_split_fwd(const float* h, const float* sel, const float* sh, const float* emb_ray, int64_t R,
-                                  int S, int h_width, int geo_dim, int emb_dim, float density_scale, float* density_out,
-                                  float* x_out, void* stream) {
+                                  int S, int h_width, int geo_dim, int emb_dim, int x_stride, float density_scale,
+                                  float* density_out, float* x_out, void* stream) {
   TN_REQUIRE(h && sel && sh && density_out && x_out && (emb_ray || emb_dim == 0), TN_EINVAL, "field_split_fwd: null pointer");
   TN_REQUIRE(R >= 0 && S >= 1 && h_width >= 1 + geo_dim && geo_dim >= 0 && geo_dim <= 31 && emb_dim >= 0 && emb_dim <= 64,
              TN_EINVAL, "field_split_fwd: bad sizes");
+  if (x_stride == 0) x_stride = 16 + geo_dim + emb_dim;
+  TN_REQUIRE(x_stride >= 16 + geo_dim + emb_dim, TN_EINVAL, "field_split_fwd: x_stride=%d too small", x_stride);
   if (R == 0) return TN_OK;
   const int64_t N = R * S;
   const unsigned grid = (unsigned)min((int64_t)kNumSMs * 32, (N + kWarps - 1) / kWarps);
   field_split_fwd_kernel<<<grid, 32 * kWarps, 0, (cudaStream_t)stream>>>(h, sel, sh, emb_ray, N, S, h_width, geo_dim,
-                                                                       emb_dim, density_scale, density_out, x_out);
+                                                                       emb_dim, x_stride, density_scale, density_out,
+                                                                       x_out);
   return check_launch("field_split_fwd_kernel");
 }
 
 extern "C" int tn_field_split_bwd(const float* h, const float* sel, const float* d_density, const float* dx, int64_t R,
-                                  int S, int h_width, int geo_dim, int emb_dim, float density_scale, float* dh_out,
-                                  float* demb_ray_out, void* stream) {
+                                  int S, int h_width, int geo_dim, int emb_dim, int x_stride, float density_scale,
+                                  float* dh_out, float* demb_ray_out, void* stream) {
   TN_REQUIRE(h && sel && dh_out, TN_EINVAL, "field_split_bwd: null pointer");
   TN_REQUIRE(R >= 0 && S >= 1 && h_width >= 1 + geo_dim && geo_dim >= 0 && geo_dim <= 31 && emb_dim >= 0 && emb_dim <= 64,
              TN_EINVAL, "field_split_bwd: bad sizes");
+  if (x_stride == 0) x_stride = 16 + geo_dim + emb_dim;
+  TN_REQUIRE(x_stride >= 16 + geo_dim + emb_dim, TN_EINVAL, "field_split_bwd: x_stride=%d too small", x_stride);
   if (R == 0) return TN_OK;
   field_split_bwd_kernel<<<warp_blocks(R), 32 * kWarps, 0, (cudaStream_t)stream>>>(
-      h, sel, d_density, dx, R, S, h_width, geo_dim, emb_dim, density_scale, dh_out, demb_ray_out);
+      h, sel, d_density, dx, R, S, h_width, geo_dim, emb_dim, x_stride, density_scale, dh_out, demb_ray_out);
   return check_launch("field_split_bwd_kernel");
 }
 

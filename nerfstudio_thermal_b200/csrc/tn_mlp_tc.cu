@@ -1,9 +1,11 @@
 // Fully fused small MLPs on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
 //
-// One CTA = 128 threads = one 128-point tile (UMMA M = 128): thread t owns point t of the tile, which is also
-// TMEM lane t, so every epilogue (bias, ReLU, activation, re-quantisation for the next layer) is a plain
-// thread-per-point loop over the row that `tcgen05.ld.32x32b` hands to that thread.  Hidden activations go
-// TMEM -> registers -> shared memory (as the next layer's A operand) and never reach HBM.
+// One CTA = 256 threads = one 128-point tile (UMMA M = 128).  Thread t works on point (t & 127), which is TMEM
+// lane (t & 127); the two threads of a point (warps w and w+4 address the same 32 TMEM lanes) split the COLUMNS of
+// every epilogue (bias, ReLU, activation, re-quantisation for the next layer) between them, so a tile keeps eight
+// warps busy.  Hidden activations go TMEM -> registers -> shared memory (as the next layer's A operand, written
+// over the previous layer's operand: it is dead once the layer's MMAs have committed) and never reach HBM.  The
+// next tile's inputs are fetched into registers while the current tile's MMAs run.
 //
 // Precision.  Operands are sums of bf16 terms and a product is a few MMAs accumulated in fp32 by the tensor core:
 //   * forward: THREE terms per operand (x = x1+x2+x3, 24 mantissa bits), six MMAs per product (all term pairs
@@ -12,8 +14,8 @@
 //     optionally stores the ReLU masks (W bits per point and hidden layer);
 //   * backward: two terms, three MMAs (hi*hi + lo*hi + hi*lo, ~2e-5 relative) for the recomputed activations,
 //     dH = dZ.W and dW^T += A^T.dZ; ReLU gating uses the forward's masks.
-// The MLPs are a few per cent of the step either way; what the tensor cores buy is that hidden layers cost no
-// SIMT issue slots and no shared-memory operand traffic.
+// The kernels are bound by instruction issue and latency, not by the tensor pipe: what the tensor cores buy is
+// that the layer products cost no SIMT issue slots and no shared-memory operand traffic.
 //
 // The reference math: field_components/mlp.py:159-178 (nn.Linear stack, ReLU, optional Sigmoid).
 #include "tn_tc.cuh"
@@ -22,7 +24,8 @@ namespace tn {
 
 using namespace tc;
 
-constexpr int TP = 128;      // points per tile == threads per CTA == UMMA M
+constexpr int TP = 128;      // points per tile == UMMA M
+constexpr int NTH = 256;     // threads per CTA: two per point (column halves)
 constexpr int OUTP = 16;     // padded width of the output layer (UMMA N must be a multiple of 16 at M = 128)
 constexpr int CH = TP * 16;  // bytes of one chunk column of an activation tile (8 features x 128 rows)
 
@@ -31,48 +34,47 @@ struct TcParams {
   const float* b[3];
   float* dw[3];
   float* db[3];
-  int in_dim, out_dim, out_act;
+  int in_dim, out_dim, out_act, x_stride;
 };
 
-// x = t[0] + t[1] + ... (bf16 terms, each the rounding of what the previous ones left)
+// 8 consecutive features (one 16-byte chunk) of row r into the NT term tiles of a 128-row operand.
+// x = t[0] + t[1] + ... (bf16 terms, each the rounding of what the previous ones left); two features per cvt.
 template <int NT>
-__device__ __forceinline__ void split_terms(float x, __nv_bfloat16 (&t)[NT]) {
+__device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride, int chunk, int r, const float* v) {
+  uint32_t w[NT][4];
 #pragma unroll
-  for (int i = 0; i < NT; ++i) {
-    t[i] = __float2bfloat16_rn(x);
-    x -= __bfloat162float(t[i]);
+  for (int i = 0; i < 4; ++i) {
+    float a = v[2 * i], b = v[2 * i + 1];
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+      const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);  // .x (low half, lower address) = a
+      const uint32_t u = *reinterpret_cast<const uint32_t*>(&p);
+      w[k][i] = u;
+      if (k + 1 < NT) {
+        a -= __uint_as_float(u << 16);
+        b -= __uint_as_float(u & 0xffff0000u);
+      }
+    }
   }
-}
-
-// 8 consecutive features (one 16-byte chunk) of row r into the NT term tiles of an operand with `rows` rows
-template <int NT>
-__device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride, int rows, int chunk, int r,
-                                                  const float (&v)[8]) {
-  __nv_bfloat16 t[NT][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat16 s[NT];
-    split_terms<NT>(v[i], s);
-#pragma unroll
-    for (int k = 0; k < NT; ++k) t[k][i] = s[k];
-  }
-  const size_t off = (size_t)chunk * rows * 16 + (size_t)r * 16;
+  const size_t off = (size_t)chunk * CH + (size_t)r * 16;
 #pragma unroll
   for (int k = 0; k < NT; ++k)
-    *reinterpret_cast<uint4*>(base + (size_t)k * term_stride + off) = *reinterpret_cast<const uint4*>(t[k]);
+    *reinterpret_cast<uint4*>(base + (size_t)k * term_stride + off) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
 }
 
 // nn.Linear weight [n_real][k_real] (row-major fp32) -> NT operand tiles with NP rows, KP features
 template <int NP, int KP, int NT>
 __device__ __forceinline__ void load_weight_terms(const float* __restrict__ w, int n_real, int k_real, uint8_t* base) {
-  for (int i = threadIdx.x; i < NP * KP; i += TP) {
+  for (int i = threadIdx.x; i < NP * KP; i += NTH) {
     const int n = i / KP, k = i - n * KP;
-    const float v = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
-    __nv_bfloat16 s[NT];
-    split_terms<NT>(v, s);
+    float v = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
     const size_t off = (size_t)(k >> 3) * NP * 16 + (size_t)n * 16 + (k & 7) * 2;
 #pragma unroll
-    for (int t = 0; t < NT; ++t) *reinterpret_cast<__nv_bfloat16*>(base + (size_t)t * NP * KP * 2 + off) = s[t];
+    for (int t = 0; t < NT; ++t) {
+      const __nv_bfloat16 s = __float2bfloat16_rn(v);
+      v -= __bfloat162float(s);
+      *reinterpret_cast<__nv_bfloat16*>(base + (size_t)t * NP * KP * 2 + off) = s;
+    }
   }
 }
 
@@ -96,49 +98,68 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_base, ui
       }
 }
 
-// one row of x[N][in_dim] into registers, zero padded to IN; all loads are independent (issued back to back)
-template <int IN>
-__device__ __forceinline__ void load_input_row(const float* __restrict__ x, int64_t row, int in_dim, bool valid,
-                                               float (&v)[IN]) {
-  const float* src = x + row * in_dim;
-  if (valid && in_dim == IN && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {  // rows are 16-byte aligned
+// CNT consecutive columns (from col0) of one row of x[N][stride] into registers; columns >= in_dim read as zero.
+// All loads are independent (issued back to back).
+template <int CNT>
+__device__ __forceinline__ void load_row_part(const float* __restrict__ x, int64_t row, int stride, int in_dim,
+                                              bool valid, int col0, float (&v)[CNT]) {
+  const float* src = x + row * stride + col0;
+  const bool vec = ((stride & 3) == 0) && (col0 + CNT <= stride) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (!valid) {
 #pragma unroll
-    for (int k = 0; k < IN; k += 4) {
+    for (int k = 0; k < CNT; ++k) v[k] = 0.f;
+  } else if (vec) {
+#pragma unroll
+    for (int k = 0; k < CNT; k += 4) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(src + k));
       v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
     }
+    if (col0 + CNT > in_dim) {  // padding columns of the caller's rows: never trusted to be finite
+#pragma unroll
+      for (int k = 0; k < CNT; ++k)
+        if (col0 + k >= in_dim) v[k] = 0.f;
+    }
   } else {
 #pragma unroll
-    for (int k = 0; k < IN; ++k) v[k] = (valid && k < in_dim) ? __ldg(src + k) : 0.f;
+    for (int k = 0; k < CNT; ++k) v[k] = (col0 + k < in_dim) ? __ldg(src + k) : 0.f;
   }
 }
 
-// hidden layer epilogue: TMEM row -> +bias, ReLU -> NT-term operand tile of the next layer (+ optional mask bits)
+// columns of a W-wide layer handled by one of the two threads of a point
+template <int W>
+struct ColSplit {
+  static_assert(W == 16 || W == 32 || W == 64, "layer width");
+  static constexpr int cols = W >= 32 ? W / 2 : W;  // per active thread (multiples of 16: tcgen05.ld.x16)
+  __device__ static __forceinline__ bool active(int half) { return W >= 32 || half == 0; }
+  __device__ static __forceinline__ int base(int half) { return W >= 32 ? half * cols : 0; }
+};
+
+// hidden layer epilogue: TMEM row -> +bias, ReLU -> NT-term operand tile of the next layer (+ optional mask bits).
+// mask_words: this point's words of this layer (W/32 of them, or 1), or null.
 template <int W, int NT>
 __device__ __forceinline__ void hidden_epilogue(uint32_t tmem_row, const float* __restrict__ bias, uint8_t* h_base,
-                                                int h_term, int row, uint32_t* __restrict__ mask_words) {
+                                                int h_term, int row, int half, uint32_t* __restrict__ mask_words) {
+  using CS = ColSplit<W>;
+  static_assert(W != 32, "mask words of a 32-wide layer would be shared by the two column halves");
+  if (!CS::active(half)) return;
+  const int cb = CS::base(half);
+  float v[CS::cols];
+#pragma unroll
+  for (int c0 = 0; c0 < CS::cols; c0 += 16) tmem_ld16(tmem_row + cb + c0, v + c0);
+  tmem_ld_wait();
   uint32_t bits = 0;
 #pragma unroll
-  for (int c0 = 0; c0 < W; c0 += 16) {
-    float v[16];
-    tmem_ld16(tmem_row + c0, v);
-    tmem_ld_wait();
+  for (int c = 0; c < CS::cols / 8; ++c) {
+    float u[8];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float u[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float z = v[half * 8 + i] + bias[c0 + half * 8 + i];
-        u[i] = fmaxf(z, 0.f);
-        bits |= (z > 0.f ? 1u : 0u) << ((c0 + half * 8 + i) & 31);
-      }
-      store_chunk_terms<NT>(h_base, h_term, TP, (c0 >> 3) + half, row, u);
+    for (int i = 0; i < 8; ++i) {
+      const float z = v[c * 8 + i] + bias[cb + c * 8 + i];
+      u[i] = fmaxf(z, 0.f);
+      bits |= (z > 0.f ? 1u : 0u) << (c * 8 + i);
     }
-    if (((c0 + 16) & 31) == 0 || c0 + 16 == W) {
-      if (mask_words) mask_words[c0 >> 5] = bits;
-      bits = 0;
-    }
+    store_chunk_terms<NT>(h_base, h_term, (cb >> 3) + c, row, u);
   }
+  if (mask_words) mask_words[W >= 64 ? half : 0] = bits;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -146,39 +167,43 @@ constexpr int FT = 3;  // bf16 terms per operand in the forward
 
 template <int IN, int W, int NL>
 struct TcSmem {
+  static constexpr int KMAX = IN > W ? IN : W;
   static constexpr int w1 = 0;                                   // FT term tiles each
   static constexpr int w2 = w1 + FT * IN * W * 2;
   static constexpr int w3 = w2 + (NL == 3 ? FT * W * W * 2 : 0);
   static constexpr int bias = w3 + FT * W * OUTP * 2;            // fp32: b1[W] b2[W] b3[OUTP]
-  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // A0 terms: IN/8 chunks each
-  static constexpr int a0_term = (IN / 8) * CH;
-  static constexpr int h = a0 + FT * a0_term;                    // H terms: W/8 chunks each (also the fp32 stage)
-  static constexpr int h_term = (W / 8) * CH;
-  static constexpr int stage_bytes = TP * 65 * 4;                // fp32 [128][in_dim|1] input staging
-  static constexpr int h_bytes = (FT * h_term > stage_bytes) ? FT * h_term : stage_bytes;
-  static constexpr int bar = h + h_bytes;                        // mbarrier (8 B) + tmem slot (4 B)
+  static constexpr int act = bias + (2 * W + OUTP) * 4;          // the ONE activation operand, rewritten per layer
+  static constexpr int act_term = (KMAX / 8) * CH;
+  static constexpr int bar = act + FT * act_term;                // mbarrier (8 B) + tmem slot (4 B)
   static constexpr int total = bar + 16;
+  // resident CTAs per SM (shared memory bound); also the register budget the compiler is held to
+  static constexpr int per_sm_raw = (224 * 1024) / (total + 1024);
+  static constexpr int per_sm = per_sm_raw < 1 ? 1 : (per_sm_raw > 4 ? 4 : per_sm_raw);
 };
 
 template <int IN, int W, int NL>
-__global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict__ x, int64_t N, TcParams prm,
-                                                        float* __restrict__ y, uint32_t* __restrict__ relu_mask) {
+__global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_kernel(const float* __restrict__ x, int64_t N, TcParams prm,
+                                                         float* __restrict__ y, uint32_t* __restrict__ relu_mask) {
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcSmem<IN, W, NL>;
   constexpr int TCOLS = W >= 64 ? 64 : 32;
   constexpr int MW = W >= 32 ? W / 32 : 1;  // mask words per point and hidden layer
-  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int XP = IN / 2;                // input columns per thread
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TP - 1), half = tid >> 7;
   float* bias = reinterpret_cast<float*>(sm + L::bias);
-  uint8_t* a0 = sm + L::a0;
-  uint8_t* hb = sm + L::h;
-  float* stage = reinterpret_cast<float*>(sm + L::h);
+  uint8_t* act = sm + L::act;
   const uint32_t bar = smem_u32(sm + L::bar);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 8);
+
+  const int64_t tiles = (N + TP - 1) / TP;
+  float xr[XP];  // this thread's half of its point's input row: fetched one tile ahead
+  load_row_part<XP>(x, (int64_t)blockIdx.x * TP + row, prm.x_stride, prm.in_dim,
+                    (int64_t)blockIdx.x * TP + row < N, half * XP, xr);
 
   load_weight_terms<W, IN, FT>(prm.w[0], W, prm.in_dim, sm + L::w1);
   if constexpr (NL == 3) load_weight_terms<W, W, FT>(prm.w[1], W, W, sm + L::w2);
   load_weight_terms<OUTP, W, FT>(prm.w[NL - 1], prm.out_dim, W, sm + L::w3);
-  for (int i = tid; i < W; i += TP) {
+  for (int i = tid; i < W; i += NTH) {
     bias[i] = __ldg(prm.b[0] + i);
     if constexpr (NL == 3) bias[W + i] = __ldg(prm.b[1] + i);
   }
@@ -193,40 +218,32 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);  // this warp's 32 lanes
+  const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes
   uint32_t phase = 0;
-  const int sstride = prm.in_dim | 1;  // odd row stride of the fp32 stage: conflict-free per-thread row reads
 
-  const int64_t tiles = (N + TP - 1) / TP;
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
-    uint32_t* mrow = (relu_mask && tid < rows) ? relu_mask + (row0 + tid) * (NL - 1) * MW : nullptr;
-    // ---- input tile: every thread pulls its own row with all loads in flight at once (a row is consumed whole,
-    //      so each fetched sector is fully used), splits it and writes the A0 operand tiles
-    {
-      float xr[IN];
-      load_input_row<IN>(x, row0 + tid, prm.in_dim, tid < rows, xr);
+    uint32_t* mrow = (relu_mask && row < rows) ? relu_mask + (row0 + row) * (NL - 1) * MW : nullptr;
+    // ---- input tile: split the prefetched half row and write the A0 operand chunks
 #pragma unroll
-      for (int c = 0; c < IN / 8; ++c) {
-        float u[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = xr[c * 8 + i];
-        store_chunk_terms<FT>(a0, L::a0_term, TP, c, tid, u);
-      }
-    }
+    for (int c = 0; c < XP / 8; ++c) store_chunk_terms<FT>(act, L::act_term, half * (XP / 8) + c, row, xr + c * 8);
     fence_async_smem();
     __syncthreads();  // A0 visible to the async proxy
     // ---- layer 1
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<W, IN, FT>(tmem, smem_u32(a0), L::a0_term, smem_u32(sm + L::w1));
+      issue_layer<W, IN, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w1));
       mma_commit(bar);
+    }
+    {  // next tile's input rows: in flight while this tile computes
+      const int64_t rn = (t + gridDim.x) * TP + row;
+      if (t + gridDim.x < tiles) load_row_part<XP>(x, rn, prm.x_stride, prm.in_dim, rn < N, half * XP, xr);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    hidden_epilogue<W, FT>(tmem_row, bias, hb, L::h_term, tid, mrow);
+    hidden_epilogue<W, FT>(tmem_row, bias, act, L::act_term, row, half, mrow);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -234,13 +251,13 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
     if constexpr (NL == 3) {
       if (tid == 0) {
         tc_fence_after();
-        issue_layer<W, W, FT>(tmem, smem_u32(hb), L::h_term, smem_u32(sm + L::w2));
+        issue_layer<W, W, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w2));
         mma_commit(bar);
       }
       mbar_wait(bar, phase);
       phase ^= 1;
       tc_fence_after();
-      hidden_epilogue<W, FT>(tmem_row, bias + W, hb, L::h_term, tid, mrow ? mrow + MW : nullptr);
+      hidden_epilogue<W, FT>(tmem_row, bias + W, act, L::act_term, row, half, mrow ? mrow + MW : nullptr);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -248,28 +265,38 @@ __global__ void __launch_bounds__(TP) mlp_tc_fwd_kernel(const float* __restrict_
     // ---- output layer
     if (tid == 0) {
       tc_fence_after();
-      issue_layer<OUTP, W, FT>(tmem, smem_u32(hb), L::h_term, smem_u32(sm + L::w3));
+      issue_layer<OUTP, W, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w3));
       mma_commit(bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
-    {
+    if (half == 0) {
       float v[16];
       tmem_ld16(tmem_row, v);
       tmem_ld_wait();
-      if (tid < rows) {
-        float* dst = y + (row0 + tid) * prm.out_dim;
-        for (int j = 0; j < prm.out_dim; ++j) {
+      if (row < rows) {
+        float* dst = y + (row0 + row) * prm.out_dim;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
           float z = v[j] + bias[2 * W + j];
           if (prm.out_act == 1) z = 1.f / (1.f + expf(-z));
           else if (prm.out_act == 2) z = expf(z);
-          dst[j] = z;
+          v[j] = z;
+        }
+        if (prm.out_dim == 16 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < prm.out_dim) dst[j] = v[j];
         }
       }
     }
     tc_fence_before();
-    __syncthreads();  // TMEM and the stage/H region are reused by the next tile
+    __syncthreads();  // TMEM and the activation operand are reused by the next tile
   }
   if (warp == 0) {
     tc_fence_after();
@@ -284,9 +311,8 @@ static int launch_tc_fwd(const float* x, int64_t N, const TcParams& prm, float* 
   auto k = mlp_tc_fwd_kernel<IN, W, NL>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   const int64_t tiles = (N + TP - 1) / TP;
-  const int per_sm = max(1, min(6, (224 * 1024) / (L::total + 1024)));
-  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * per_sm);
-  k<<<grid, TP, L::total, st>>>(x, N, prm, y, mask);
+  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
+  k<<<grid, NTH, L::total, st>>>(x, N, prm, y, mask);
   return check_launch("mlp_tc_fwd_kernel");
 }
 
@@ -312,9 +338,9 @@ struct TcBwdSmem {
   static constexpr int h1 = a0 + BT * a0_term;                   // BT terms, (W/8 + 1) chunks each
   static constexpr int h_term = (W / 8 + 1) * CH;
   static constexpr int h2 = h1 + BT * h_term;
-  static constexpr int g = h2 + (NL == 3 ? BT * h_term : 0);     // dZ tile: BT terms of 8 chunks / fp32 stage
+  static constexpr int g = h2 + (NL == 3 ? BT * h_term : 0);     // dZ tile: BT terms of 8 chunks
   static constexpr int g_term = 8 * CH;
-  static constexpr int g_bytes = BT * g_term + 2048;             // >= 128*65*4 stage, and M=128 over-read slack
+  static constexpr int g_bytes = BT * g_term + 2048;             // + M=128 over-read slack
   static constexpr int bar = g + g_bytes;
   static constexpr int total = bar + 16;
   // TMEM columns: forward accumulators / dH / dX, then the three dW^T accumulators
@@ -325,6 +351,11 @@ struct TcBwdSmem {
   static constexpr int c_dw3 = c_dw2 + (NL == 3 ? W : 0);
   static constexpr int cols_used = c_dw3 + OUTP;
   static constexpr int tcols = cols_used <= 32 ? 32 : cols_used <= 64 ? 64 : cols_used <= 128 ? 128 : 256;
+  // resident CTAs per SM: bounded by shared memory and by the 512 TMEM columns (and held to in registers)
+  static constexpr int per_sm_smem = (224 * 1024) / (total + 1024);
+  static constexpr int per_sm_tmem = 512 / tcols;
+  static constexpr int per_sm_raw = per_sm_smem < per_sm_tmem ? per_sm_smem : per_sm_tmem;
+  static constexpr int per_sm = per_sm_raw < 1 ? 1 : (per_sm_raw > 2 ? 2 : per_sm_raw);
 };
 
 // D[128 x N] (+)= Act^T-view . dZ^T-view over the 128 points of the tile (both operands MN-major)
@@ -372,58 +403,69 @@ __device__ __forceinline__ void store_ones_chunk(uint8_t* base, int term_stride,
   for (int t = 1; t < BT; ++t) *reinterpret_cast<uint4*>(base + (size_t)t * term_stride + off) = make_uint4(0, 0, 0, 0);
 }
 
-// dZ_prev = dH (TMEM) gated by the ReLU mask of the previous layer -> split -> G tile
+// dZ_prev = dH (TMEM) gated by the ReLU mask of the previous layer -> split -> G tile (this thread's columns)
 template <int W>
-__device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, const uint32_t* __restrict__ mask_words,
-                                            const uint8_t* h_hi, uint8_t* g_base, int g_term, int row) {
+__device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, bool have_mask, uint32_t word, const uint8_t* h_hi,
+                                            uint8_t* g_base, int g_term, int row, int half) {
+  using CS = ColSplit<W>;
+  if (!CS::active(half)) return;
+  const int cb = CS::base(half);
+  float v[CS::cols];
 #pragma unroll
-  for (int c0 = 0; c0 < W; c0 += 16) {
-    float v[16];
-    tmem_ld16(tmem_row + c0, v);
-    tmem_ld_wait();
-    const uint32_t word = mask_words ? mask_words[c0 >> 5] : 0u;
+  for (int c0 = 0; c0 < CS::cols; c0 += 16) tmem_ld16(tmem_row + cb + c0, v + c0);
+  tmem_ld_wait();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int chunk = (c0 >> 3) + half;
-      float u[8];
-      if (mask_words) {
+  for (int c = 0; c < CS::cols / 8; ++c) {
+    const int chunk = (cb >> 3) + c;
+    float u[8];
+    if (have_mask) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = ((word >> ((c0 + half * 8 + i) & 31)) & 1u) ? v[half * 8 + i] : 0.f;
-      } else {  // no saved masks: gate on the recomputed activation
-        const uint4 hv = *reinterpret_cast<const uint4*>(h_hi + (size_t)chunk * CH + (size_t)row * 16);
-        const __nv_bfloat16* hbv = reinterpret_cast<const __nv_bfloat16*>(&hv);
+      for (int i = 0; i < 8; ++i) u[i] = ((word >> (c * 8 + i)) & 1u) ? v[c * 8 + i] : 0.f;
+    } else {  // no saved masks: gate on the recomputed activation
+      const uint4 hv = *reinterpret_cast<const uint4*>(h_hi + (size_t)chunk * CH + (size_t)row * 16);
+      const __nv_bfloat16* hbv = reinterpret_cast<const __nv_bfloat16*>(&hv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = __bfloat162float(hbv[i]) > 0.f ? v[half * 8 + i] : 0.f;
-      }
-      store_chunk_terms<BT>(g_base, g_term, TP, chunk, row, u);
+      for (int i = 0; i < 8; ++i) u[i] = __bfloat162float(hbv[i]) > 0.f ? v[c * 8 + i] : 0.f;
     }
+    store_chunk_terms<BT>(g_base, g_term, chunk, row, u);
   }
 }
 
 template <int IN, int W, int NL, bool NEED_DX>
-__global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                        const uint32_t* __restrict__ relu_mask, int64_t N,
-                                                        TcParams prm, float* __restrict__ dx) {
+__global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         const uint32_t* __restrict__ relu_mask, int64_t N,
+                                                         TcParams prm, float* __restrict__ dx) {
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcBwdSmem<IN, W, NL>;
   constexpr int MW = W >= 32 ? W / 32 : 1;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int XP = IN / 2;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & (TP - 1), half = tid >> 7;
   float* bias = reinterpret_cast<float*>(sm + L::bias);
   uint8_t* a0 = sm + L::a0;
   uint8_t* h1 = sm + L::h1;
   uint8_t* h2 = sm + L::h2;
   uint8_t* gb = sm + L::g;
-  float* stage = reinterpret_cast<float*>(sm + L::g);
   uint8_t* hlast = NL == 3 ? h2 : h1;
   const uint32_t bar = smem_u32(sm + L::bar);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 8);
 
+  const int64_t tiles = (N + TP - 1) / TP;
+  // operands fetched one tile ahead: this thread's half input row, and (column half 0) the point's dy row
+  float xr[XP];
+  float dyr[OUTP];
+  auto prefetch = [&](int64_t t) {
+    const int64_t r = t * TP + row;
+    load_row_part<XP>(x, r, prm.x_stride, prm.in_dim, r < N, half * XP, xr);
+    if (half == 0) load_row_part<OUTP>(dy, r, prm.out_dim, prm.out_dim, r < N, 0, dyr);
+  };
+  prefetch(blockIdx.x);
+
   // zero the whole operand area once: padding chunks / over-read regions must hold finite values
-  for (int i = tid; i < (L::bar - L::a0) / 16; i += TP) reinterpret_cast<uint4*>(sm + L::a0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (L::bar - L::a0) / 16; i += NTH) reinterpret_cast<uint4*>(sm + L::a0)[i] = make_uint4(0, 0, 0, 0);
   load_weight_terms<W, IN, BT>(prm.w[0], W, prm.in_dim, sm + L::w1);
   if constexpr (NL == 3) load_weight_terms<W, W, BT>(prm.w[1], W, W, sm + L::w2);
   load_weight_terms<OUTP, W, BT>(prm.w[NL - 1], prm.out_dim, W, sm + L::w3);
-  for (int i = tid; i < W; i += TP) {
+  for (int i = tid; i < W; i += NTH) {
     bias[i] = __ldg(prm.b[0] + i);
     if constexpr (NL == 3) bias[W + i] = __ldg(prm.b[1] + i);
   }
@@ -435,43 +477,33 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
   if (warp == 0) tmem_alloc<L::tcols>(smem_u32((const void*)tmem_slot));
   __syncthreads();
   // "ones" chunks (bias-gradient rows) are constant across tiles
-  store_ones_chunk(a0, L::a0_term, IN / 8, tid);
-  store_ones_chunk(h1, L::h_term, W / 8, tid);
-  if constexpr (NL == 3) store_ones_chunk(h2, L::h_term, W / 8, tid);
+  if (half == 0) {
+    store_ones_chunk(a0, L::a0_term, IN / 8, row);
+    store_ones_chunk(h1, L::h_term, W / 8, row);
+    if constexpr (NL == 3) store_ones_chunk(h2, L::h_term, W / 8, row);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t phase = 0;
   uint32_t dw_acc = 0;  // 0 on the first tile (overwrite), 1 afterwards (accumulate)
-  const int sstride = prm.in_dim | 1;
 
-  const int64_t tiles = (N + TP - 1) / TP;
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
-    uint32_t mwords[2 * MW];
-#pragma unroll
-    for (int i = 0; i < 2 * MW; ++i) mwords[i] = 0;
-    if (relu_mask && tid < rows) {
-#pragma unroll
-      for (int i = 0; i < (NL - 1) * MW; ++i) mwords[i] = __ldg(relu_mask + (row0 + tid) * (NL - 1) * MW + i);
+    // this thread's word (its 32 columns) of the ReLU masks of hidden layer 1 and of the last hidden layer
+    uint32_t m_first = 0, m_last = 0;
+    const bool have_mask = relu_mask != nullptr;
+    if (have_mask && row < rows) {
+      const uint32_t* mp = relu_mask + (row0 + row) * (NL - 1) * MW + (W >= 64 ? half : 0);
+      m_first = __ldg(mp);
+      m_last = __ldg(mp + (NL - 2) * MW);
     }
-    const uint32_t* m_first = relu_mask ? mwords : nullptr;             // mask of hidden layer 1
-    const uint32_t* m_last = relu_mask ? mwords + (NL - 2) * MW : nullptr;  // mask of the last hidden layer
-    {
-      float xr[IN];
-      load_input_row<IN>(x, row0 + tid, prm.in_dim, tid < rows, xr);
 #pragma unroll
-      for (int c = 0; c < IN / 8; ++c) {
-        float u[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = xr[c * 8 + i];
-        store_chunk_terms<BT>(a0, L::a0_term, TP, c, tid, u);
-      }
-    }
+    for (int c = 0; c < XP / 8; ++c) store_chunk_terms<BT>(a0, L::a0_term, half * (XP / 8) + c, row, xr + c * 8);
     fence_async_smem();
     __syncthreads();
     // ---------------- forward recompute (activation VALUES; gating below uses the forward's masks)
@@ -482,7 +514,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     }
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias, h1, L::h_term, tid, nullptr);
+    hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias, h1, L::h_term, row, half, nullptr);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -494,7 +526,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
       }
       mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias + W, h2, L::h_term, tid, nullptr);
+      hidden_epilogue<W, BT>(tmem_row + L::c_acc, bias + W, h2, L::h_term, row, half, nullptr);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -507,28 +539,25 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     // ---------------- dZ_out = dy * act'(z)  -> G tile (16 features = 2 chunks)
-    {
+    if (half == 0) {
       float z[16];
       tmem_ld16(tmem_row + L::c_acc, z);
       tmem_ld_wait();
-      float u0[8], u1[8];
+      float u[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float gv = 0.f;
-        if (tid < rows && j < prm.out_dim) {
-          gv = __ldg(dy + (row0 + tid) * prm.out_dim + j);
-          const float zz = z[j] + bias[2 * W + j];
-          if (prm.out_act == 1) {
-            const float sg = 1.f / (1.f + expf(-zz));
-            gv *= sg * (1.f - sg);
-          } else if (prm.out_act == 2) {
-            gv *= expf(fminf(fmaxf(zz, -15.f), 15.f));
-          }
+        float gv = dyr[j];  // zero beyond out_dim and for rows past N
+        const float zz = z[j] + bias[2 * W + j];
+        if (prm.out_act == 1) {
+          const float sg = 1.f / (1.f + expf(-zz));
+          gv *= sg * (1.f - sg);
+        } else if (prm.out_act == 2) {
+          gv *= expf(fminf(fmaxf(zz, -15.f), 15.f));
         }
-        if (j < 8) u0[j] = gv; else u1[j - 8] = gv;
+        u[j] = gv;
       }
-      store_chunk_terms<BT>(gb, L::g_term, TP, 0, tid, u0);
-      store_chunk_terms<BT>(gb, L::g_term, TP, 1, tid, u1);
+      store_chunk_terms<BT>(gb, L::g_term, 0, row, u);
+      store_chunk_terms<BT>(gb, L::g_term, 1, row, u + 8);
     }
     fence_async_smem();
     tc_fence_before();
@@ -540,9 +569,10 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
       issue_dh<W, OUTP, OUTP>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w3));
       mma_commit(bar);
     }
+    if (t + gridDim.x < tiles) prefetch(t + gridDim.x);  // xr and dyr are both consumed by now
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    dh_epilogue<W>(tmem_row + L::c_acc, m_last, hlast, gb, L::g_term, tid);  // G = dZ of the last hidden layer
+    dh_epilogue<W>(tmem_row + L::c_acc, have_mask, m_last, hlast, gb, L::g_term, row, half);  // G = dZ of the last hidden layer
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -555,7 +585,7 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
       }
       mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      dh_epilogue<W>(tmem_row + L::c_acc, m_first, h1, gb, L::g_term, tid);  // dZ1
+      dh_epilogue<W>(tmem_row + L::c_acc, have_mask, m_first, h1, gb, L::g_term, row, half);  // dZ1
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
@@ -571,23 +601,25 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     if constexpr (NEED_DX) {
-      // dX rows: TMEM -> registers -> this thread's row of dx (whole rows, so every written sector is full)
-      float* dst = dx + (row0 + tid) * prm.in_dim;
-      const bool vec = prm.in_dim == IN && (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
+      // dX rows: TMEM -> registers -> this thread's columns of its dx row (whole 64-byte runs)
+      using CX = ColSplit<IN>;
+      if (CX::active(half)) {
+        const int cb = CX::base(half);
+        float* dst = dx + (row0 + row) * prm.x_stride + cb;
+        const bool vec = (prm.x_stride & 3) == 0 && IN <= prm.x_stride && (reinterpret_cast<uintptr_t>(dx) & 15) == 0;
+        float v[CX::cols];
 #pragma unroll
-      for (int c0 = 0; c0 < IN; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_row + L::c_acc + c0, v);
+        for (int c0 = 0; c0 < CX::cols; c0 += 16) tmem_ld16(tmem_row + L::c_acc + cb + c0, v + c0);
         tmem_ld_wait();
-        if (tid < rows) {
+        if (row < rows) {
           if (vec) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4)
-              *reinterpret_cast<float4*>(dst + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            for (int i = 0; i < CX::cols; i += 4)
+              *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < prm.in_dim) dst[c0 + i] = v[i];
+            for (int i = 0; i < CX::cols; ++i)
+              if (cb + i < prm.in_dim) dst[i] = v[i];
           }
         }
       }
@@ -598,37 +630,47 @@ __global__ void __launch_bounds__(TP) mlp_tc_bwd_kernel(const float* __restrict_
   // ---------------- flush dW^T / db accumulators (lane = input feature, ones row = bias gradient)
   if (dw_acc) {
     tc_fence_after();
+    using CS = ColSplit<W>;
+    if (CS::active(half)) {
+      const int cb = CS::base(half);
 #pragma unroll 1
-    for (int c0 = 0; c0 < W; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_row + L::c_dw1 + c0, v);
-      tmem_ld_wait();
-      if (tid < prm.in_dim) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(prm.dw[0] + (size_t)(c0 + i) * prm.in_dim + tid, v[i]);
-      } else if (tid == IN) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(prm.db[0] + c0 + i, v[i]);
-      }
-      if constexpr (NL == 3) {
-        tmem_ld16(tmem_row + L::c_dw2 + c0, v);
+      for (int c0 = cb; c0 < cb + CS::cols; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem_row + L::c_dw1 + c0, v);
         tmem_ld_wait();
-        if (tid < W) {
+        if (row < prm.in_dim) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(prm.dw[1] + (size_t)(c0 + i) * W + tid, v[i]);
-        } else if (tid == W) {
+          for (int i = 0; i < 16; ++i) atomicAdd(prm.dw[0] + (size_t)(c0 + i) * prm.in_dim + row, v[i]);
+        } else if (row == IN) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(prm.db[1] + c0 + i, v[i]);
+          for (int i = 0; i < 16; ++i) atomicAdd(prm.db[0] + c0 + i, v[i]);
+        }
+        if constexpr (NL == 3) {
+          tmem_ld16(tmem_row + L::c_dw2 + c0, v);
+          tmem_ld_wait();
+          if (row < W) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(prm.dw[1] + (size_t)(c0 + i) * W + row, v[i]);
+          } else if (row == W) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(prm.db[1] + c0 + i, v[i]);
+          }
         }
       }
     }
-    float v[16];
-    tmem_ld16(tmem_row + L::c_dw3, v);
-    tmem_ld_wait();
-    if (tid < W) {
-      for (int o = 0; o < prm.out_dim; ++o) atomicAdd(prm.dw[NL - 1] + (size_t)o * W + tid, v[o]);
-    } else if (tid == W) {
-      for (int o = 0; o < prm.out_dim; ++o) atomicAdd(prm.db[NL - 1] + o, v[o]);
+    if (half == 0) {
+      float v[16];
+      tmem_ld16(tmem_row + L::c_dw3, v);
+      tmem_ld_wait();
+      if (row < W) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+          if (o < prm.out_dim) atomicAdd(prm.dw[NL - 1] + (size_t)o * W + row, v[o]);
+      } else if (row == W) {
+#pragma unroll
+        for (int o = 0; o < 16; ++o)
+          if (o < prm.out_dim) atomicAdd(prm.db[NL - 1] + o, v[o]);
+      }
     }
     tc_fence_before();
   }
@@ -645,26 +687,25 @@ static int launch_tc_bwd(const float* x, const float* dy, const uint32_t* mask, 
   using L = TcBwdSmem<IN, W, NL>;
   static_assert(L::total <= 227 * 1024, "backward tile set does not fit in shared memory");
   const int64_t tiles = (N + TP - 1) / TP;
-  // resident CTAs per SM: bounded by shared memory and by the 512 TMEM columns
-  const int per_sm = max(1, min(min(4, 512 / L::tcols), (224 * 1024) / (L::total + 1024)));
-  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * per_sm);
+  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
   if (dx) {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, TP, L::total, st>>>(x, dy, mask, N, prm, dx);
+    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx);
   } else {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, TP, L::total, st>>>(x, dy, mask, N, prm, dx);
+    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx);
   }
   return check_launch("mlp_tc_bwd_kernel");
 }
 
-static int fill_tc(TcParams& prm, int in_dim, int width, int out_dim, int n_layers, const float* const* w,
-                   const float* const* b, int out_act) {
+static int fill_tc(TcParams& prm, int in_dim, int x_stride, int width, int out_dim, int n_layers,
+                   const float* const* w, const float* const* b, int out_act) {
   TN_REQUIRE(w && b, TN_EINVAL, "mlp_tc: null weight pointer table");
   TN_REQUIRE(n_layers == 2 || n_layers == 3, TN_EINVAL, "mlp_tc: n_layers=%d not in {2,3}", n_layers);
   TN_REQUIRE(in_dim >= 1 && in_dim <= 64, TN_EINVAL, "mlp_tc: in_dim=%d not in [1,64]", in_dim);
+  TN_REQUIRE(x_stride == 0 || x_stride >= in_dim, TN_EINVAL, "mlp_tc: x_stride=%d < in_dim=%d", x_stride, in_dim);
   TN_REQUIRE(width == 16 || width == 64, TN_EINVAL, "mlp_tc: width=%d not in {16,64}", width);
   TN_REQUIRE(out_dim >= 1 && out_dim <= 16, TN_EINVAL, "mlp_tc: out_dim=%d not in [1,16]", out_dim);
   TN_REQUIRE(out_act >= 0 && out_act <= 2, TN_EINVAL, "mlp_tc: out_act=%d", out_act);
@@ -674,6 +715,7 @@ static int fill_tc(TcParams& prm, int in_dim, int width, int out_dim, int n_laye
     prm.b[i] = b[i];
   }
   prm.in_dim = in_dim; prm.out_dim = out_dim; prm.out_act = out_act;
+  prm.x_stride = x_stride ? x_stride : in_dim;
   return TN_OK;
 }
 
@@ -700,11 +742,11 @@ using namespace tn;
     }                                                                                    \
   } while (0)
 
-extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, int out_dim, int n_layers,
-                             const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
-                             uint32_t* relu_mask_out, void* stream) {
+extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int x_stride, int width, int out_dim,
+                             int n_layers, const float* const* w_host_ptrs, const float* const* b_host_ptrs,
+                             int out_act, float* y, uint32_t* relu_mask_out, void* stream) {
   TcParams prm = {};
-  int rc = fill_tc(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
+  int rc = fill_tc(prm, in_dim, x_stride, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
   if (N == 0) return TN_OK;
   TN_REQUIRE(x && y && N > 0, TN_EINVAL, "mlp_tc_fwd: bad x/y/N");
@@ -713,11 +755,11 @@ extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int width, i
 }
 
 extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim,
-                             int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
+                             int x_stride, int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
                              const float* const* b_host_ptrs, int out_act, float* dx, float* const* dw_host_ptrs,
                              float* const* db_host_ptrs, void* stream) {
   TcParams prm = {};
-  int rc = fill_tc(prm, in_dim, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
+  int rc = fill_tc(prm, in_dim, x_stride, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
   if (N == 0) return TN_OK;
   TN_REQUIRE(x && dy && N > 0 && dw_host_ptrs && db_host_ptrs, TN_EINVAL, "mlp_tc_bwd: bad x/dy/N/grad tables");

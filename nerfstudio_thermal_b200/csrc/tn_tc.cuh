@@ -95,7 +95,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // the same warp
 }
 
 // 16 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "

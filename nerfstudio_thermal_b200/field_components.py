@@ -166,7 +166,12 @@ class MLP(FieldComponent):
                 f"in_dim={in_dim} num_layers={num_layers} width={layer_width} out_dim={self.out_dim}")
 
     def forward(self, in_tensor: Tensor) -> Tensor:
-        flat = in_tensor.reshape(-1, self.in_dim)
+        # rows may arrive padded to a multiple of 4 floats (fused_ops.field_split emits 63 -> 64): the kernel
+        # reads them in place and ignores the padding
+        cols = in_tensor.shape[-1]
+        if cols != self.in_dim and cols != (self.in_dim + 3) // 4 * 4:
+            raise ValueError(f"MLP expects {self.in_dim} input features, got {cols}")
+        flat = in_tensor.reshape(-1, cols)
         y = ops.mlp(flat, [l.weight for l in self.layers], [l.bias for l in self.layers], self._out_act,
                     sinks=self.grad_sinks)
         return y.view(*in_tensor.shape[:-1], self.out_dim)

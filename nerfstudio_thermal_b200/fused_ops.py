@@ -16,29 +16,32 @@ class _FieldSplitFn(torch.autograd.Function):
         emb_dim = 0 if emb_ray is None else emb_ray.shape[-1]
         n = rays * samples
         density = torch.empty((n,), device=h.device)
-        x = torch.empty((n, 16 + geo_dim + emb_dim), device=h.device)
+        in_dim = 16 + geo_dim + emb_dim
+        x_stride = (in_dim + 3) // 4 * 4  # rows padded to whole 16-byte runs (63 -> 64) for the MLP's tile loads
+        x = torch.empty((n, x_stride), device=h.device)
         call("tn_field_split_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, h.shape[-1], geo_dim, emb_dim,
-             float(scale), ptr(density), ptr(x), stream())
-        ctx.dims = (rays, samples, geo_dim, emb_dim, float(scale))
+             x_stride, float(scale), ptr(density), ptr(x), stream())
+        ctx.dims = (rays, samples, geo_dim, emb_dim, float(scale), x_stride)
         ctx.save_for_backward(h, sel)
         return density, x
 
     @staticmethod
     def backward(ctx, d_density, dx):
         h, sel = ctx.saved_tensors
-        rays, samples, geo_dim, emb_dim, scale = ctx.dims
+        rays, samples, geo_dim, emb_dim, scale, x_stride = ctx.dims
         dh = torch.empty_like(h)
         want_emb = emb_dim > 0 and ctx.needs_input_grad[3] and dx is not None
         demb = torch.empty((rays, emb_dim), device=h.device) if want_emb else None
         call("tn_field_split_bwd", ptr(h), ptr(sel), ptr(None if d_density is None else _f32c(d_density)),
-             ptr(None if dx is None else _f32c(dx)), rays, samples, h.shape[-1], geo_dim, emb_dim, scale, ptr(dh),
-             ptr(demb), stream())
+             ptr(None if dx is None else _f32c(dx)), rays, samples, h.shape[-1], geo_dim, emb_dim, x_stride, scale,
+             ptr(dh), ptr(demb), stream())
         return dh, None, None, demb, None, None, None, None
 
 
 def field_split(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Optional[Tensor], rays: int, samples: int, geo_dim: int,
                 scale: float) -> Tuple[Tensor, Tensor]:
-    """h[R*S,1+geo] -> (density[R*S], head input [R*S, 16+geo+emb]).  fields/nerfacto_field.py:221-228, 335-344."""
+    """h[R*S,1+geo] -> (density[R*S], head input [R*S, pad4(16+geo+emb)], zero padded: `ops.mlp` takes the padded
+    rows as they are).  fields/nerfacto_field.py:221-228, 335-344."""
     return _FieldSplitFn.apply(h, sel, sh, emb_ray, rays, samples, geo_dim, scale)
 
 

@@ -164,7 +164,10 @@ class _MlpFn(torch.autograd.Function):
         ws = [_f32c(t) for t in wb[0::2]]
         bs = [_f32c(t) for t in wb[1::2]]
         ctx.sinks = sinks
-        n, in_dim = x.shape
+        n, x_stride = x.shape
+        in_dim = ws[0].shape[1]  # x may carry padding columns beyond in_dim (a 63-wide input stored 64 wide)
+        if x_stride < in_dim:
+            raise ValueError(f"mlp: input has {x_stride} columns, first layer expects {in_dim}")
         width, out_dim, nl = ws[0].shape[0], ws[-1].shape[0], len(ws)
         y = torch.empty((n, out_dim), device=x.device)
         tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
@@ -172,10 +175,11 @@ class _MlpFn(torch.autograd.Function):
         if MLP_BACKEND["fwd"] == "tc":
             if MLP_BACKEND["bwd"] == "tc" and any(ctx.needs_input_grad):
                 mask = torch.empty((n, nl - 1, max(1, width // 32)), device=x.device, dtype=torch.int32)
-            call("tn_mlp_tc_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
-                 ptr(mask), stream(), tag=tag)
+            call("tn_mlp_tc_fwd", ptr(x), n, in_dim, x_stride, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act,
+                 ptr(y), ptr(mask), stream(), tag=tag)
         else:
-            call("tn_mlp_fwd", ptr(x), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
+            xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
+            call("tn_mlp_fwd", ptr(xd), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
                  stream(), tag=tag)
         ctx.out_act = out_act
         ctx.nl = nl
@@ -187,7 +191,8 @@ class _MlpFn(torch.autograd.Function):
         saved = ctx.saved_tensors
         x, mask, nl = saved[0], saved[1], ctx.nl
         ws, bs = list(saved[2:2 + nl]), list(saved[2 + nl:])
-        n, in_dim = x.shape
+        n, x_stride = x.shape
+        in_dim = ws[0].shape[1]
         width, out_dim = ws[0].shape[0], ws[-1].shape[0]
         sinks = ctx.sinks
         if sinks is not None:  # accumulate straight into the parameters' (flat-buffer) gradients
@@ -195,14 +200,25 @@ class _MlpFn(torch.autograd.Function):
         else:
             dws = [torch.zeros_like(w) for w in ws]
             dbs = [torch.zeros_like(b) for b in bs]
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # the tensor-core kernel writes whole 16/32/64-wide rows (zeros in the padding columns); any other
+            # padding is never touched by a kernel and must already be zero
+            tile_w = 16 if in_dim <= 16 else (32 if in_dim <= 32 else 64)
+            covered = x_stride == in_dim or (MLP_BACKEND["bwd"] == "tc" and x_stride == tile_w)
+            dx = torch.empty_like(x) if covered else torch.zeros_like(x)
         tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
         if MLP_BACKEND["bwd"] == "tc":
-            call("tn_mlp_tc_bwd", ptr(x), ptr(_f32c(dy)), ptr(mask), n, in_dim, width, out_dim, nl, ptr_array(ws),
-                 ptr_array(bs), ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+            call("tn_mlp_tc_bwd", ptr(x), ptr(_f32c(dy)), ptr(mask), n, in_dim, x_stride, width, out_dim, nl,
+                 ptr_array(ws), ptr_array(bs), ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
         else:
-            call("tn_mlp_bwd", ptr(x), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
-                 ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+            xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
+            dxd = dx if x_stride == in_dim or dx is None else torch.empty_like(xd)
+            call("tn_mlp_bwd", ptr(xd), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
+                 ctx.out_act, ptr(dxd), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+            if dx is not None and dxd is not dx:
+                dx.zero_()
+                dx[:, :in_dim] = dxd
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [None, None] if sinks is not None else [dw, db]

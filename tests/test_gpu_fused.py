@@ -40,8 +40,11 @@ def test_field_split_fwd_bwd(emb_dim):
     eg = emb.detach().to(DEV).requires_grad_(True) if emb_dim else None
     dens, x = fused_ops.field_split(hg, sel.to(DEV), sh.to(DEV), eg, R, S, geo, 0.7)
     close(dens, dens_ref[:, 0], 1e-6, 1e-5)
-    assert torch.equal(x.cpu(), x_ref.detach())
-    ((dens * gd.to(DEV)).sum() + (x * gx.to(DEV)).sum()).backward()
+    in_dim = x_ref.shape[1]
+    assert x.shape[1] == (in_dim + 3) // 4 * 4  # rows padded to whole 16-byte runs for the MLP's tile loads
+    assert torch.equal(x[:, :in_dim].cpu(), x_ref.detach())
+    assert torch.count_nonzero(x[:, in_dim:]) == 0
+    ((dens * gd.to(DEV)).sum() + (x[:, :in_dim] * gx.to(DEV)).sum()).backward()
     close(hg.grad, h.grad, 1e-5, 1e-5)
     if emb_dim:
         close(eg.grad, emb.grad, 1e-5, 1e-5)
