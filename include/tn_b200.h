@@ -243,6 +243,34 @@ int tn_density_l1(const float* d, const float* d2, const float* dt, const float*
                   float thermal_grad_mult, float rgb_grad_mult, float* partial_out, int n_partial, float* g_d,
                   float* g_d2, float* g_dt, float* g_d2t, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Optimiser step over the flat buffers.
+ * ------------------------------------------------------------------------------------------------ */
+#define TN_ADAM_MAX_GROUPS 16
+#define TN_ADAM_HYPER 8
+/* replaces: engine/optimizers.py:172-180 (Optimizers.optimizer_step_all: one torch.optim.Adam.step per group),
+ * :150-163 (optimizer_scaler_step_all: GradScaler.step = skip on inf/nan) and engine/schedulers.py:109-142
+ * (ExponentialDecayScheduler: per-group LambdaLR), for the groups of configs/method_configs.py:274-301.
+ * params/grads/exp_avg/exp_avg_sq: flat fp32 device buffers of n elements (16-byte aligned).  Group i covers
+ * elements [group_begin_host[i], group_end_host[i]) (ordered, disjoint; elements of no group are left alone) and
+ * group_hyper_host[i*8 ..] = {lr_init, lr_final (<=0: lr_init), lr_pre_warmup, eps, weight_decay, warmup_steps,
+ * max_steps (0: constant lr), ramp (0 linear, 1 cosine)}.  The step number t (1-based, as torch's state['step']
+ * after the increment) is read from step_dev when non-NULL (so the call can live in a CUDA graph), else step_host;
+ * the learning rate used is lr_init * lr_lambda(t-1), evaluated on the device in double.  Dense update exactly as
+ * torch.optim.Adam (amsgrad off): m = lerp(m,g,1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m /
+ * (sqrt(v)/sqrt(1-b2^t) + eps).  inv_scale_dev: NULL or device float multiplying the gradients (GradScaler);
+ * found_inf_dev: NULL or device float, non-zero = skip the update; zero_grads: clear grads after reading them. */
+int tn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 const int64_t* group_begin_host, const int64_t* group_end_host, const float* group_hyper_host,
+                 int n_groups, double beta1, double beta2, const int32_t* step_dev, int step_host,
+                 const float* inv_scale_dev, const float* found_inf_dev, int zero_grads, void* stream);
+/* replaces: torch.cuda.amp.GradScaler.unscale_'s inf check (used by engine/optimizers.py:150-163):
+ * found_inf_dev[0] = 1 if any grads[i] * inv_scale is not finite, else 0. */
+int tn_grad_unscale_check(const float* grads, int64_t n, const float* inv_scale_dev, float* found_inf_dev,
+                          void* stream);
+/* counter_dev[0] += value (the device-side step counter read by tn_adam_step inside a captured graph). */
+int tn_counter_add(int32_t* counter_dev, int value, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

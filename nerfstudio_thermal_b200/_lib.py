@@ -6,7 +6,7 @@ entry point raises `TnLibraryError`.  Build it with `python -c "import __graft_e
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_double, POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 import torch
 
@@ -61,6 +61,10 @@ _SIGNATURES = {
     "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
+    "tn_adam_step": [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_float), c_int, c_double,
+                     c_double, _P, c_int, _P, _P, c_int, _P],
+    "tn_grad_unscale_check": [_P, c_int64, _P, _P, _P],
+    "tn_counter_add": [_P, c_int, _P],
 }
 _RESTYPES = {"tn_last_error_string": c_char_p, "tn_build_arch": c_char_p}
 

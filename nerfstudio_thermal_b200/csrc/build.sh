@@ -24,6 +24,7 @@ build tn_mlp.cu
 build tn_mlp_tc.cu
 build tn_fused.cu
 build tn_model.cu
+build tn_optim.cu
 build tn_api.cu
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libtn_b200.so" "$OBJ"/*.o -lcudart

@@ -37,44 +37,63 @@ struct TcParams {
   int in_dim, out_dim, out_act, x_stride;
 };
 
-// 8 consecutive features (one 16-byte chunk) of row r into the NT term tiles of a 128-row operand.
-// x = t[0] + t[1] + ... (bf16 terms, each the rounding of what the previous ones left); two features per cvt.
+// x = t[0] + t[1] + ... as bf16 terms.  Every term but the last of a two-term split is a TRUNCATION (the top 16
+// bits of the running remainder: integer ops only, and the subtraction that forms the next remainder is exact);
+// three truncated terms hold 8+8+8 = all 24 mantissa bits of an fp32, so the forward split is exact.  The last
+// term of the two-term (backward) split is rounded to nearest instead (x ~ 17 bits).
 template <int NT>
-__device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride, int chunk, int r, const float* v) {
-  uint32_t w[NT][4];
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t (&w)[NT]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float a = v[2 * i], b = v[2 * i + 1];
-#pragma unroll
-    for (int k = 0; k < NT; ++k) {
+  for (int k = 0; k < NT; ++k) {
+    if (k == NT - 1 && NT < 3) {
       const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);  // .x (low half, lower address) = a
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(&p);
-      w[k][i] = u;
+      w[k] = *reinterpret_cast<const uint32_t*>(&p);
+    } else {
+      const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+      w[k] = __byte_perm(ua, ub, 0x7632);  // {hi16(a) in the low half, hi16(b) in the high half}
       if (k + 1 < NT) {
-        a -= __uint_as_float(u << 16);
-        b -= __uint_as_float(u & 0xffff0000u);
+        a -= __uint_as_float(ua & 0xffff0000u);
+        b -= __uint_as_float(ub & 0xffff0000u);
       }
     }
   }
+}
+
+// 8 consecutive features (one 16-byte chunk) of row r into the NT term tiles of a 128-row operand
+template <int NT>
+__device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride, int chunk, int r, const float* v) {
+  uint32_t w[4][NT];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_pair<NT>(v[2 * i], v[2 * i + 1], w[i]);
   const size_t off = (size_t)chunk * CH + (size_t)r * 16;
 #pragma unroll
   for (int k = 0; k < NT; ++k)
-    *reinterpret_cast<uint4*>(base + (size_t)k * term_stride + off) = make_uint4(w[k][0], w[k][1], w[k][2], w[k][3]);
+    *reinterpret_cast<uint4*>(base + (size_t)k * term_stride + off) = make_uint4(w[0][k], w[1][k], w[2][k], w[3][k]);
 }
 
-// nn.Linear weight [n_real][k_real] (row-major fp32) -> NT operand tiles with NP rows, KP features
+// nn.Linear weight [n_real][k_real] (row-major fp32) -> NT operand tiles with NP rows, KP features.
+// All global loads of a matrix are issued before the first is consumed (one L2 round trip per matrix).
 template <int NP, int KP, int NT>
 __device__ __forceinline__ void load_weight_terms(const float* __restrict__ w, int n_real, int k_real, uint8_t* base) {
-  for (int i = threadIdx.x; i < NP * KP; i += NTH) {
-    const int n = i / KP, k = i - n * KP;
-    float v = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
-    const size_t off = (size_t)(k >> 3) * NP * 16 + (size_t)n * 16 + (k & 7) * 2;
+  static_assert((NP * KP) % NTH == 0, "weight tile must be a whole number of passes");
+  constexpr int ITERS = NP * KP / NTH;
+  float v[ITERS];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const __nv_bfloat16 s = __float2bfloat16_rn(v);
-      v -= __bfloat162float(s);
-      *reinterpret_cast<__nv_bfloat16*>(base + (size_t)t * NP * KP * 2 + off) = s;
-    }
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = threadIdx.x + it * NTH;
+    const int n = i / KP, k = i - n * KP;
+    v[it] = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int i = threadIdx.x + it * NTH;
+    const int n = i / KP, k = i - n * KP;
+    const size_t off = (size_t)(k >> 3) * NP * 16 + (size_t)n * 16 + (k & 7) * 2;
+    uint32_t t[NT];
+    split_pair<NT>(v[it], 0.f, t);
+#pragma unroll
+    for (int q = 0; q < NT; ++q)
+      *reinterpret_cast<uint16_t*>(base + (size_t)q * NP * KP * 2 + off) = (uint16_t)(t[q] & 0xffffu);
   }
 }
 

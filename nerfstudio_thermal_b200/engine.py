@@ -8,8 +8,10 @@ never allocates or synchronises, jitter comes from torch's graph-safe Philox gen
 losses avoid boolean indexing.
 
 Mirrors what `Trainer.train_iteration` + `VanillaPipeline.get_train_loss_dict` drive in the reference
-(engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304), minus optimizer/scheduler/GradScaler (unchanged
-host code in the reference; the optimizer reads the gradients from `grads.flat` / `param.grad`).
+(engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304).  The optimiser + scheduler step is optional: with
+`optimizer=` the fused Adam launch (`optim.FusedAdam`) runs right after the backward -- inside the captured graph
+on one GPU, after the gradient all-reduce on several -- otherwise any optimiser can read the gradients from
+`grads.flat` / `param.grad`.
 """
 from typing import Dict, List, Optional
 
@@ -18,6 +20,7 @@ from torch import Tensor
 
 from . import parallel
 from .model import ThermalNerfactoModel
+from .optim import AdamGroupConfig, FusedAdam
 from .rays import RayBundle
 
 BATCH_KEYS = ("origins", "directions", "pixel_area", "camera_indices", "image", "is_thermal")
@@ -32,13 +35,17 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model: ThermalNerfactoModel, example_batch: Dict[str, Tensor], use_graph: bool = True,
-                 warmup: int = 3, group=None):
+                 warmup: int = 3, group=None, optimizer: Optional[Dict[str, AdamGroupConfig]] = None):
         self.model = model
         self.device = model.device
         assert self.device.type == "cuda", "the hot path runs on CUDA only (no CPU fallback)"
         self.group = group
         self.grads = parallel.FlatGradBuffer.from_param_groups(model.get_param_groups(), device=self.device)
         self.grads.attach_sinks(model)
+        # parameters move into their flat buffer BEFORE anything is captured (the graph bakes in addresses)
+        self.optimizer = FusedAdam(self.grads, optimizer) if optimizer is not None else None
+        world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
+        self._adam_in_graph = self.optimizer is not None and world == 1
         self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
         self._load(example_batch)
         self.losses: Dict[str, Tensor] = {}
@@ -50,26 +57,30 @@ class GraphedTrainStep:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(max(warmup, 2)):  # allocator / cudaFuncSetAttribute / host-constant caches warm
-                    self._eager()
+                    self._eager(apply_optimizer=False)  # warm-up must not move the parameters
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
+            self.grads.zero_()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._eager()
+                self._eager(apply_optimizer=True, captured=True)
             torch.cuda.synchronize(self.device)
 
     def _load(self, batch: Dict[str, Tensor]) -> None:
         for k in BATCH_KEYS:
             self.static[k].copy_(batch[k], non_blocking=True)
 
-    def _eager(self) -> None:
+    def _eager(self, apply_optimizer: bool = True, captured: bool = False) -> None:
         s = self.static
-        self.grads.zero_()
+        if not (captured and self._adam_in_graph):  # the in-graph Adam pass leaves the gradients cleared
+            self.grads.zero_()
         bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
                            camera_indices=s["camera_indices"])
         _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
         self.total = sum(self.losses.values())
         self.total.backward()
+        if apply_optimizer and self._adam_in_graph:
+            self.optimizer.step(zero_grads=captured)
 
     def step(self, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
         if batch is not None:
@@ -79,6 +90,8 @@ class GraphedTrainStep:
         else:
             self._eager()
         self.grads.all_reduce_mean(self.group)
+        if self.optimizer is not None and not self._adam_in_graph:
+            self.optimizer.step()
         return self.total
 
 

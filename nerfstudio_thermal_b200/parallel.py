@@ -23,7 +23,7 @@ from torch import Tensor, nn
 class FlatGradBuffer:
     """All gradients of a module in one contiguous fp32 buffer, laid out group by group."""
 
-    def __init__(self, params: Iterable[nn.Parameter], device=None):
+    def __init__(self, params: Iterable[nn.Parameter], device=None, group_of: Optional[Dict[int, str]] = None):
         seen, self.params = set(), []
         for p in params:
             if p.requires_grad and p.numel() > 0 and id(p) not in seen:
@@ -38,11 +38,42 @@ class FlatGradBuffer:
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+        # named groups = contiguous element ranges [begin, end) (alignment padding inside a group included)
+        self.group_ranges: Dict[str, Tuple[int, int]] = {}
+        self._group_members: Dict[str, List[Tuple[nn.Parameter, int]]] = {}
+        if group_of:
+            for p, off in zip(self.params, self.offsets):
+                name = group_of[id(p)]
+                b, _ = self.group_ranges.get(name, (off, off))
+                self.group_ranges[name] = (b, off + (p.numel() + 3) // 4 * 4)
+                self._group_members.setdefault(name, []).append((p, off))
+        self.flat_params: Optional[Tensor] = None
 
     @classmethod
     def from_param_groups(cls, groups: Dict[str, List[nn.Parameter]], order: Optional[List[str]] = None, device=None):
         names = order if order is not None else list(groups)
-        return cls([p for n in names for p in groups[n]], device=device)
+        group_of: Dict[int, str] = {}
+        for n in names:
+            for p in groups[n]:
+                group_of.setdefault(id(p), n)  # a parameter listed twice belongs to its first group
+        return cls([p for n in names for p in groups[n]], device=device, group_of=group_of)
+
+    def group_params(self, name: str) -> List[Tuple[nn.Parameter, int]]:
+        """(parameter, element offset) of every parameter of a named group, in buffer order."""
+        return self._group_members.get(name, [])
+
+    def flatten_params(self) -> Tensor:
+        """Move every parameter into one flat fp32 buffer with the layout of the gradient buffer (`param.data`
+        become views of it; values are kept).  Element i of the parameter, gradient and optimiser-state buffers
+        then belongs to the same scalar, which is what the fused optimiser kernel needs."""
+        if self.flat_params is None:
+            flat = torch.zeros_like(self.flat)
+            for p, off in zip(self.params, self.offsets):
+                view = flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+            self.flat_params = flat
+        return self.flat_params
 
     def attach_sinks(self, module: nn.Module) -> int:
         """Let every HashEncoding of `module` scatter its table gradient directly into this buffer (the
