@@ -146,20 +146,21 @@ int tn_weights_bwd(const float* sigma, const float* deltas, const float* dw, int
 
 /* replaces: model_components/renderers.py:118-133 (+:292-307 RGBT), :509 (accumulation), :547-557 (median
  * depth), :558-572 (expected depth before the batch-global clip of :574).
- * weights[R,S], colour[R,S,C] (C <= 4), starts/ends [R,S].
+ * weights[R,S], colour[R,S,C] (C <= 4), starts/ends [R,S] with t_stride floats between rows (0 = S; the
+ * two pointers may be bins and bins+1 of one [R,S+1] bin-edge array with t_stride = S+1).
  * bg_mode: 0 none ("random": no blending), 1 last_sample, 2 constant bg_host[C].
  * eval_mode != 0 applies nan_to_num to colour and clamps the composite to [0,1] (renderers.py:238-245).
  * Any output pointer may be NULL.  steps_minmax_out: float[2] updated with atomic min/max of
  * (starts+ends)/2 over the launch (caller initialises to +inf/-inf) for the :574 clip. */
 int tn_render_fwd(const float* weights, const float* colour, const float* starts, const float* ends,
-                  int64_t R, int S, int C, int bg_mode, const float* bg_host, int eval_mode,
+                  int64_t R, int S, int t_stride, int C, int bg_mode, const float* bg_host, int eval_mode,
                   float* rgb_out, float* acc_out, float* depth_median_out, float* depth_expected_out,
                   float* steps_minmax_out, void* stream);
 /* Gradients of rgb_out / acc_out / unclipped expected depth -> dweights[R,S], dcolour[R,S,C]
  * (overwritten).  d_rgb/d_acc/d_depth may each be NULL (= zero). */
 int tn_render_bwd(const float* weights, const float* colour, const float* starts, const float* ends,
-                  const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S, int C,
-                  int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream);
+                  const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S, int t_stride,
+                  int C, int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Glue fusions between the field kernels, and the per-ray losses.
@@ -242,6 +243,21 @@ int tn_pixel_losses(const float* rgb, const float* thermal, const float* image, 
 int tn_density_l1(const float* d, const float* d2, const float* dt, const float* d2t, int64_t N, float value_mult,
                   float thermal_grad_mult, float rgb_grad_mult, float* partial_out, int n_partial, float* g_d,
                   float* g_d2, float* g_dt, float* g_d2t, void* stream);
+/* replaces: cameras/camera_optimizers.py:188-194 (get_loss_dict) and :200-204 (get_metrics_dict).  pose[num_cameras,6].
+ * out3 = {(mean|t_i| * trans_penalty + mean|w_i| * rot_penalty) * penalty_scale, |T|_F, |W|_F}. */
+int tn_camera_reg_fwd(const float* pose, int num_cameras, float trans_penalty, float rot_penalty,
+                      float penalty_scale, float* out3, void* stream);
+/* dpose_out[num_cameras,6] (overwritten) = upstream_dev[0] * d out3[0] / d pose (zero rows where a norm is zero,
+ * as torch's norm backward). */
+int tn_camera_reg_bwd(const float* pose, const float* upstream_dev, int num_cameras, float trans_penalty,
+                      float rot_penalty, float penalty_scale, float* dpose_out, void* stream);
+/* replaces: the loss-dictionary arithmetic of models/thermal_nerfacto.py:284-388 + engine/trainer.py:479
+ * (`functools.reduce(torch.add, loss_dict.values())`).  term_host_ptrs[k]: device pointer of scalar term k, which
+ * belongs to dictionary entry slot_host[k] in [0, n_slots);
+ * out[1+j] = sum_{k: slot k = j} scale[k] * term_k (the dictionary values), out[0] = their sum (the total loss). */
+#define TN_MAX_LOSS_TERMS 16
+int tn_loss_sum(const float* const* term_host_ptrs, const float* scale_host, const int* slot_host, int n_terms,
+                int n_slots, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimiser step over the flat buffers.

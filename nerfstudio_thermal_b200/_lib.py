@@ -45,8 +45,8 @@ _SIGNATURES = {
     "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],
     "tn_weights_fwd": [_P, _P, c_int64, c_int, _P, _P],
     "tn_weights_bwd": [_P, _P, _P, c_int64, c_int, _P, _P],
-    "tn_render_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int, _P, _P, _P, _P, _P, _P],
-    "tn_render_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), _P, _P, _P],
+    "tn_render_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), c_int, _P, _P, _P, _P, _P, _P],
+    "tn_render_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), _P, _P, _P],
     "tn_field_split_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
     "tn_field_split_bwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_float, _P, _P, _P],
     "tn_density_act_fwd": [_P, c_int, _P, c_int64, c_float, _P, _P],
@@ -61,6 +61,9 @@ _SIGNATURES = {
     "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
+    "tn_camera_reg_fwd": [_P, c_int, c_float, c_float, c_float, _P, _P],
+    "tn_camera_reg_bwd": [_P, _P, c_int, c_float, c_float, c_float, _P, _P],
+    "tn_loss_sum": [_FPP, POINTER(c_float), POINTER(c_int), c_int, c_int, _P, _P],
     "tn_adam_step": [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_float), c_int, c_double,
                      c_double, _P, c_int, _P, _P, c_int, _P],
     "tn_grad_unscale_check": [_P, c_int64, _P, _P, _P],

@@ -208,6 +208,72 @@ __global__ void density_l1_kernel(const float* __restrict__ d, const float* __re
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ camera regulariser
+// cameras/camera_optimizers.py:188-204: out[0] = (mean_i |t_i| * trans_pen + mean_i |w_i| * rot_pen) * scale,
+// out[1] = |T|_F, out[2] = |W|_F (the two metrics).  One CTA: the pose table is a few hundred rows.
+__global__ void __launch_bounds__(256) camera_reg_fwd_kernel(const float* __restrict__ pose, int C, float trans_pen,
+                                                             float rot_pen, float scale, float* __restrict__ out) {
+  __shared__ float red[4][8];
+  float st = 0.f, sw = 0.f, qt = 0.f, qw = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) {
+    const float* p = pose + 6 * i;
+    const float t2 = p[0] * p[0] + p[1] * p[1] + p[2] * p[2], w2 = p[3] * p[3] + p[4] * p[4] + p[5] * p[5];
+    st += sqrtf(t2); sw += sqrtf(w2); qt += t2; qw += w2;
+  }
+  st = warp_sum(st); sw = warp_sum(sw); qt = warp_sum(qt); qw = warp_sum(qw);
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    red[0][w] = st; red[1][w] = sw; red[2][w] = qt; red[3][w] = qw;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b += red[1][w]; c += red[2][w]; d += red[3][w]; }
+    out[0] = (a / (float)C * trans_pen + b / (float)C * rot_pen) * scale;
+    out[1] = sqrtf(c);
+    out[2] = sqrtf(d);
+  }
+}
+// dpose[i] (overwritten) = g * scale / C * (trans_pen * t_i/|t_i| , rot_pen * w_i/|w_i|), zero where the norm is zero
+__global__ void camera_reg_bwd_kernel(const float* __restrict__ pose, const float* __restrict__ g, int C,
+                                      float trans_pen, float rot_pen, float scale, float* __restrict__ dpose) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const float* p = pose + 6 * i;
+  const float gs = g[0] * scale / (float)C;
+  const float nt = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const float nw = sqrtf(p[3] * p[3] + p[4] * p[4] + p[5] * p[5]);
+  const float ct = nt > 0.f ? gs * trans_pen / nt : 0.f, cw = nw > 0.f ? gs * rot_pen / nw : 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dpose[6 * i + k] = ct * p[k];
+    dpose[6 * i + 3 + k] = cw * p[3 + k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ loss assembly
+// out[0] = sum_k scale[k] * *term[k]; out[1 + j] = sum over the terms of dictionary entry j (slot[k] == j)
+// (K scalar loss terms living anywhere on the device)
+struct TermPtrs {
+  const float* p[TN_MAX_LOSS_TERMS];
+  float scale[TN_MAX_LOSS_TERMS];
+  int slot[TN_MAX_LOSS_TERMS];
+};
+__global__ void loss_sum_kernel(TermPtrs t, int K, int n_slots, float* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int j = 0; j < n_slots; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k)
+        if (t.slot[k] == j) acc += t.scale[k] * t.p[k][0];
+      out[1 + j] = acc;
+      total += acc;
+    }
+    out[0] = total;
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -255,4 +321,37 @@ extern "C" int tn_density_l1(const float* d, const float* d2, const float* dt, c
   density_l1_kernel<<<n_partial, 256, 0, (cudaStream_t)stream>>>(d, d2, dt, d2t, N, value_mult, thermal_grad_mult,
                                                                rgb_grad_mult, partial_out, g_d, g_d2, g_dt, g_d2t);
   return check_launch("density_l1_kernel");
+}
+
+extern "C" int tn_camera_reg_fwd(const float* pose, int num_cameras, float trans_penalty, float rot_penalty,
+                                 float penalty_scale, float* out3, void* stream) {
+  TN_REQUIRE(pose && out3 && num_cameras >= 1, TN_EINVAL, "camera_reg_fwd: bad arguments");
+  camera_reg_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pose, num_cameras, trans_penalty, rot_penalty,
+                                                            penalty_scale, out3);
+  return check_launch("camera_reg_fwd_kernel");
+}
+
+extern "C" int tn_camera_reg_bwd(const float* pose, const float* upstream_dev, int num_cameras, float trans_penalty,
+                                 float rot_penalty, float penalty_scale, float* dpose_out, void* stream) {
+  TN_REQUIRE(pose && upstream_dev && dpose_out && num_cameras >= 1, TN_EINVAL, "camera_reg_bwd: bad arguments");
+  camera_reg_bwd_kernel<<<(num_cameras + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      pose, upstream_dev, num_cameras, trans_penalty, rot_penalty, penalty_scale, dpose_out);
+  return check_launch("camera_reg_bwd_kernel");
+}
+
+extern "C" int tn_loss_sum(const float* const* term_host_ptrs, const float* scale_host, const int* slot_host,
+                           int n_terms, int n_slots, float* out, void* stream) {
+  TN_REQUIRE(term_host_ptrs && scale_host && slot_host && out && n_terms >= 1 && n_terms <= TN_MAX_LOSS_TERMS &&
+                 n_slots >= 1 && n_slots <= n_terms,
+             TN_EINVAL, "loss_sum: n_terms=%d (max %d) n_slots=%d", n_terms, TN_MAX_LOSS_TERMS, n_slots);
+  TermPtrs t = {};
+  for (int k = 0; k < n_terms; ++k) {
+    TN_REQUIRE(term_host_ptrs[k] && slot_host[k] >= 0 && slot_host[k] < n_slots, TN_EINVAL,
+               "loss_sum: term %d is null or has slot outside [0,%d)", k, n_slots);
+    t.p[k] = term_host_ptrs[k];
+    t.scale[k] = scale_host[k];
+    t.slot[k] = slot_host[k];
+  }
+  loss_sum_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(t, n_terms, n_slots, out);
+  return check_launch("loss_sum_kernel");
 }

@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) weights_bwd_kernel(const fl
 template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) render_fwd_kernel(
     const float* __restrict__ w, const float* __restrict__ col, const float* __restrict__ starts,
-    const float* __restrict__ ends, int64_t R, int S, int bg_mode, float4 bg, int eval_mode, float* __restrict__ rgb_out,
+    const float* __restrict__ ends, int64_t R, int S, int TS, int bg_mode, float4 bg, int eval_mode,
+    float* __restrict__ rgb_out,
     float* __restrict__ acc_out, float* __restrict__ med_out, float* __restrict__ exp_out, float* __restrict__ minmax) {
   const int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_fwd_kernel(
     }
     acc += wv;
     if (need_steps) {
-      const float step = ok ? (__ldg(starts + r * S + s) + __ldg(ends + r * S + s)) / 2.f : 0.f;
+      const float step = ok ? (__ldg(starts + r * TS + s) + __ldg(ends + r * TS + s)) / 2.f : 0.f;
       num += wv * step;
       if (ok) { smin = fminf(smin, step); smax = fmaxf(smax, step); }
       const double incl = warp_incl_scan((double)wv, lane) + carry;
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_fwd_kernel(
     if (need_steps) {
       if (med_out) {
         const int idx = min(below_half, S - 1);
-        med_out[r] = (__ldg(starts + r * S + idx) + __ldg(ends + r * S + idx)) / 2.f;
+        med_out[r] = (__ldg(starts + r * TS + idx) + __ldg(ends + r * TS + idx)) / 2.f;
       }
       if (exp_out) exp_out[r] = num / (acc + 1e-10f);
       if (minmax) {  // steps are >= 0 in practice; the int trick below is valid for any sign
@@ -188,7 +189,7 @@ template <int C>
 __global__ void __launch_bounds__(32 * kWarpsPerCta) render_bwd_kernel(
     const float* __restrict__ w, const float* __restrict__ col, const float* __restrict__ starts,
     const float* __restrict__ ends, const float* __restrict__ d_rgb, const float* __restrict__ d_acc,
-    const float* __restrict__ d_depth, int64_t R, int S, int bg_mode, float4 bg, float* __restrict__ dw,
+    const float* __restrict__ d_depth, int64_t R, int S, int TS, int bg_mode, float4 bg, float* __restrict__ dw,
     float* __restrict__ dcol) {
   const int64_t r = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_bwd_kernel(
   for (int s = lane; s < S; s += 32) {
     const float wv = __ldg(w + r * S + s);
     acc += wv;
-    if (d_depth) num += wv * ((__ldg(starts + r * S + s) + __ldg(ends + r * S + s)) / 2.f);
+    if (d_depth) num += wv * ((__ldg(starts + r * TS + s) + __ldg(ends + r * TS + s)) / 2.f);
   }
   acc = warp_sum(acc);
   num = warp_sum(num);
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_bwd_kernel(
       if (dcol) dcol[(r * S + s) * C + c] = gc;
     }
     if (d_depth) {
-      const float step = (__ldg(starts + r * S + s) + __ldg(ends + r * S + s)) / 2.f;
+      const float step = (__ldg(starts + r * TS + s) + __ldg(ends + r * TS + s)) / 2.f;
       gw += gd * (step / den - num / (den * den));
     }
     if (dw) dw[r * S + s] = gw;
@@ -318,7 +319,8 @@ extern "C" int tn_weights_bwd(const float* sigma, const float* deltas, const flo
 }
 
 extern "C" int tn_render_fwd(const float* weights, const float* colour, const float* starts, const float* ends,
-                             int64_t R, int S, int C, int bg_mode, const float* bg_host, int eval_mode, float* rgb_out,
+                             int64_t R, int S, int t_stride, int C, int bg_mode, const float* bg_host, int eval_mode,
+                             float* rgb_out,
                              float* acc_out, float* depth_median_out, float* depth_expected_out,
                              float* steps_minmax_out, void* stream) {
   TN_REQUIRE(weights, TN_EINVAL, "render_fwd: weights is null");
@@ -328,6 +330,8 @@ extern "C" int tn_render_fwd(const float* weights, const float* colour, const fl
   TN_REQUIRE(starts || !(depth_median_out || depth_expected_out || steps_minmax_out), TN_EINVAL,
              "render_fwd: depth outputs need starts/ends");
   TN_REQUIRE(bg_mode >= 0 && bg_mode <= 2 && (bg_mode != 2 || bg_host), TN_EINVAL, "render_fwd: bad bg_mode");
+  TN_REQUIRE(t_stride == 0 || t_stride >= S, TN_EINVAL, "render_fwd: t_stride=%d < S=%d", t_stride, S);
+  const int TS = t_stride ? t_stride : S;
   if (R == 0) return TN_OK;
   float4 bg = make_float4(0, 0, 0, 0);
   if (bg_mode == 2) {
@@ -337,7 +341,7 @@ extern "C" int tn_render_fwd(const float* weights, const float* colour, const fl
   }
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_RF(CC)                                                                                                     \
-  render_fwd_kernel<CC><<<ray_blocks(R), 32 * kWarpsPerCta, 0, st>>>(weights, colour, starts, ends, R, S, bg_mode, bg, \
+  render_fwd_kernel<CC><<<ray_blocks(R), 32 * kWarpsPerCta, 0, st>>>(weights, colour, starts, ends, R, S, TS, bg_mode, bg, \
                                                                     eval_mode, rgb_out, acc_out, depth_median_out,     \
                                                                     depth_expected_out, steps_minmax_out)
   switch (C) {
@@ -352,13 +356,15 @@ extern "C" int tn_render_fwd(const float* weights, const float* colour, const fl
 }
 
 extern "C" int tn_render_bwd(const float* weights, const float* colour, const float* starts, const float* ends,
-                             const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S, int C,
-                             int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream) {
+                             const float* d_rgb, const float* d_acc, const float* d_depth, int64_t R, int S,
+                             int t_stride, int C, int bg_mode, const float* bg_host, float* dweights, float* dcolour, void* stream) {
   TN_REQUIRE(weights, TN_EINVAL, "render_bwd: weights is null");
   TN_REQUIRE(R >= 0 && S >= 1 && C >= 0 && C <= 4, TN_EINVAL, "render_bwd: bad R=%lld S=%d C=%d", (long long)R, S, C);
   TN_REQUIRE(C == 0 || colour, TN_EINVAL, "render_bwd: colour is null");
   TN_REQUIRE(!d_depth || (starts && ends), TN_EINVAL, "render_bwd: d_depth needs starts/ends");
   TN_REQUIRE(bg_mode >= 0 && bg_mode <= 2 && (bg_mode != 2 || bg_host), TN_EINVAL, "render_bwd: bad bg_mode");
+  TN_REQUIRE(t_stride == 0 || t_stride >= S, TN_EINVAL, "render_bwd: t_stride=%d < S=%d", t_stride, S);
+  const int TS = t_stride ? t_stride : S;
   if (R == 0) return TN_OK;
   float4 bg = make_float4(0, 0, 0, 0);
   if (bg_mode == 2) {
@@ -369,7 +375,7 @@ extern "C" int tn_render_bwd(const float* weights, const float* colour, const fl
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_RB(CC)                                                                                                   \
   render_bwd_kernel<CC><<<ray_blocks(R), 32 * kWarpsPerCta, 0, st>>>(weights, colour, starts, ends, d_rgb, d_acc,    \
-                                                                    d_depth, R, S, bg_mode, bg, dweights, dcolour)
+                                                                    d_depth, R, S, TS, bg_mode, bg, dweights, dcolour)
   switch (C) {
     case 0: TN_RB(0); break;
     case 1: TN_RB(1); break;

@@ -77,7 +77,8 @@ class GraphedTrainStep:
         bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
                            camera_indices=s["camera_indices"])
         _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
-        self.total = sum(self.losses.values())
+        total = getattr(self.losses, "total", None)
+        self.total = total if total is not None else sum(self.losses.values())
         self.total.backward()
         if apply_optimizer and self._adam_in_graph:
             self.optimizer.step(zero_grads=captured)

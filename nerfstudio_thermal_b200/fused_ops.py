@@ -1,10 +1,12 @@
 """torch.autograd bindings of the glue fusions and per-ray loss kernels (csrc/tn_fused.cu)."""
 from typing import Optional, Tuple
 
+import ctypes
+
 import torch
 from torch import Tensor
 
-from ._lib import call, ptr, stream
+from ._lib import call, float_array, ptr, ptr_array, stream
 from .ops import _f32c
 
 
@@ -186,20 +188,33 @@ class _PixelLossesFn(torch.autograd.Function):
              None, None, stream())
         ctx.has_thermal = thermal is not None
         ctx.save_for_backward(rgb, thermal, image, is_thermal)
-        return losses
+        ctx.set_materialize_grads(False)
+        return tuple(losses.unbind(0))  # four scalars: indexing a vector would cost a zeros+copy per term backward
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, *gs):
         rgb, thermal, image, is_thermal = ctx.saved_tensors
         d_rgb = torch.empty_like(rgb)
         d_th = torch.empty_like(thermal) if ctx.has_thermal else None
+        zero = _zero_scalar(rgb.device)
+        g = torch.stack([zero if t is None else t.reshape(()) for t in gs])
         call("tn_pixel_losses", ptr(rgb), ptr(thermal), ptr(image), ptr(is_thermal), rgb.shape[0], ptr(_f32c(g)), None,
              ptr(d_rgb), ptr(d_th), stream())
         return d_rgb, (None if d_th is None else d_th.view(-1, 1)), None, None
 
 
-def pixel_losses(rgb: Tensor, thermal: Optional[Tensor], image: Tensor, is_thermal: Tensor) -> Tensor:
-    """[rgb MSE, thermal MSE, tv_pixel, cross_channel] (un-multiplied) for a patch-ordered batch.
+_ZERO = {}
+
+
+def _zero_scalar(device) -> Tensor:
+    k = str(device)
+    if k not in _ZERO:
+        _ZERO[k] = torch.zeros((), device=device)
+    return _ZERO[k]
+
+
+def pixel_losses(rgb: Tensor, thermal: Optional[Tensor], image: Tensor, is_thermal: Tensor) -> Tuple[Tensor, ...]:
+    """(rgb MSE, thermal MSE, tv_pixel, cross_channel) scalars (un-multiplied) for a patch-ordered batch.
     models/thermal_nerfacto.py:286-354; rgb[R,3], thermal[R,1] or None, image[R,3], is_thermal[R]."""
     return _PixelLossesFn.apply(rgb, thermal, image, is_thermal)
 
@@ -283,3 +298,80 @@ def interlevel_loss_level(w_fine: Tensor, c_fine: Tensor, w_prop: Tensor, c_prop
     """mean(lossfun_outer(c_fine, w_fine, c_prop, w_prop)); the fine histogram carries no gradient.
     model_components/losses.py:87-103, 117-135."""
     return _InterlevelFn.apply(w_fine.detach(), c_fine.detach(), w_prop, c_prop.detach())
+
+
+class _CameraRegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, trans_pen, rot_pen, scale):
+        pose = _f32c(pose)
+        out = torch.empty((3,), device=pose.device)
+        call("tn_camera_reg_fwd", ptr(pose), pose.shape[0], float(trans_pen), float(rot_pen), float(scale), ptr(out),
+             stream())
+        ctx.coef = (float(trans_pen), float(rot_pen), float(scale))
+        ctx.save_for_backward(pose)
+        ctx.set_materialize_grads(False)
+        reg, tn_, rn_ = out.unbind(0)
+        ctx.mark_non_differentiable(tn_, rn_)
+        return reg, tn_, rn_
+
+    @staticmethod
+    def backward(ctx, g, _gt, _gr):
+        (pose,) = ctx.saved_tensors
+        if g is None:
+            return None, None, None, None
+        dpose = torch.empty_like(pose)
+        call("tn_camera_reg_bwd", ptr(pose), ptr(_f32c(g)), pose.shape[0], *ctx.coef, ptr(dpose), stream())
+        return dpose, None, None, None
+
+
+def camera_regularizer(pose: Tensor, trans_pen: float, rot_pen: float, scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """(regulariser, |translations|_F, |rotations|_F) of a CameraOptimizer's pose table in one launch.
+    cameras/camera_optimizers.py:188-194, 200-204."""
+    return _CameraRegFn.apply(pose, trans_pen, rot_pen, scale)
+
+
+_SCALE_CACHE = {}
+
+
+class _LossSumFn(torch.autograd.Function):
+    """Dictionary values (sums of scale_k * term_k over the terms of an entry) and their total in one launch; the
+    backward hands every term its slice of ONE vector product instead of a chain of scalar multiplies."""
+
+    @staticmethod
+    def forward(ctx, scales, slots, *terms):
+        terms = [_f32c(t) for t in terms]
+        k, n_slots = len(terms), max(slots) + 1
+        dev = terms[0].device
+        out = torch.empty((1 + n_slots,), device=dev)
+        call("tn_loss_sum", ptr_array(terms), float_array(scales), (ctypes.c_int * k)(*slots), k, n_slots, ptr(out),
+             stream())
+        key = (tuple(scales), str(dev))
+        if key not in _SCALE_CACHE:
+            _SCALE_CACHE[key] = torch.tensor(scales, dtype=torch.float32).to(dev)
+        ctx.scales, ctx.slots = _SCALE_CACHE[key], slots
+        ctx.set_materialize_grads(False)
+        return tuple(out.unbind(0))
+
+    @staticmethod
+    def backward(ctx, g_total, *g_slot):
+        gv = (ctx.scales * g_total).unbind(0) if g_total is not None else [None] * len(ctx.slots)
+        outs = []
+        for i, j in enumerate(ctx.slots):  # an entry differentiated on its own adds its share
+            t, g = gv[i], g_slot[j]
+            if g is not None:
+                t = ctx.scales[i] * g if t is None else t + ctx.scales[i] * g
+            outs.append(t)
+        return (None, None, *outs)
+
+
+def loss_sum(entries) -> Tuple[Tensor, dict]:
+    """entries: [(name, scalar term, scale)], names may repeat -> (total, {name: sum of scale * term}).
+    models/thermal_nerfacto.py:284-388 multiplies every loss term by its config weight and engine/trainer.py:479
+    adds the dictionary up -- two tiny launches per term each way; here one launch each way."""
+    names = []
+    for n, _, _ in entries:
+        if n not in names:
+            names.append(n)
+    out = _LossSumFn.apply(tuple(float(s) for _, _, s in entries), tuple(names.index(n) for n, _, _ in entries),
+                           *[t for _, t, _ in entries])
+    return out[0], dict(zip(names, out[1:]))

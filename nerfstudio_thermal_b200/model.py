@@ -72,6 +72,7 @@ class CameraOptimizer(nn.Module):
         self.register_buffer("_frozen", frozen, persistent=False)
         self.register_buffer("_frozen_u8", frozen.to(torch.uint8), persistent=False)
         self.fused = True  # single-kernel apply_to_raybundle on CUDA (the torch expression is kept in forward())
+        self._reg_cache = None
 
     def forward(self, indices: Tensor) -> Tensor:
         if self.config.mode == "off":
@@ -98,7 +99,19 @@ class CameraOptimizer(nn.Module):
             raybundle.origins = raybundle.origins + c[:, :3, 3]
             raybundle.directions = torch.bmm(c[:, :3, :3], raybundle.directions[..., None]).squeeze(-1)
 
+    def _reg_and_norms(self):
+        """(regulariser, |t|_F, |w|_F) of the pose table from one launch (fused_ops.camera_regularizer)."""
+        c = self.config
+        return fused_ops.camera_regularizer(self.pose_adjustment, c.trans_l2_penalty, c.rot_l2_penalty, c.penalty_scale)
+
     def get_loss_dict(self, loss_dict: dict) -> None:
+        if self.config.mode != "off" and self.fused and self.pose_adjustment.is_cuda:
+            # get_metrics_dict of the same step (get_train_loss_dict calls it first) already launched the kernel
+            cached, self._reg_cache = self._reg_cache, None
+            reg = cached[0] if (cached is not None and cached[0].requires_grad == torch.is_grad_enabled()) \
+                else self._reg_and_norms()[0]
+            loss_dict[f"camera_opt_regularizer{self.suffix}"] = reg
+            return
         if self.config.mode != "off":
             loss_dict[f"camera_opt_regularizer{self.suffix}"] = (
                 self.pose_adjustment[:, :3].norm(dim=-1).mean() * self.config.trans_l2_penalty
@@ -106,6 +119,12 @@ class CameraOptimizer(nn.Module):
             ) * self.config.penalty_scale
 
     def get_metrics_dict(self, metrics_dict: dict) -> None:
+        if self.config.mode != "off" and self.fused and self.pose_adjustment.is_cuda:
+            self._reg_cache = self._reg_and_norms()
+            _, tn_, rn_ = self._reg_cache
+            metrics_dict[f"camera_opt_translation{self.suffix}"] = tn_
+            metrics_dict[f"camera_opt_rotation{self.suffix}"] = rn_
+            return
         if self.config.mode != "off":
             metrics_dict[f"camera_opt_translation{self.suffix}"] = self.pose_adjustment[:, :3].norm()
             metrics_dict[f"camera_opt_rotation{self.suffix}"] = self.pose_adjustment[:, 3:].norm()
@@ -195,6 +214,27 @@ class ThermalNerfactoModelConfig:
 
     def setup(self, **kwargs) -> "ThermalNerfactoModel":
         return ThermalNerfactoModel(self, **kwargs)
+
+
+class LossDict(dict):
+    """The loss dictionary of get_loss_dict plus `.total`, the sum of its values (engine/trainer.py:479)."""
+
+    total: Optional[Tensor] = None
+
+
+def _assemble_losses(entries, fused: bool) -> LossDict:
+    tensors = [t for _, t, _ in entries if torch.is_tensor(t)]
+    if fused and len(tensors) == len(entries) and all(t.is_cuda and t.numel() == 1 for t in tensors) \
+            and 1 <= len(entries) <= 16:
+        total, values = fused_ops.loss_sum([(k, t.reshape(()), w) for k, t, w in entries])
+        out = LossDict(values)
+        out.total = total
+        return out
+    out = LossDict()
+    for k, t, w in entries:
+        out[k] = out.get(k, 0) + w * t
+    out.total = sum(out.values())
+    return out
 
 
 # ------------------------------------------------------------------------------------------ model
@@ -349,9 +389,12 @@ class ThermalNerfactoModel(nn.Module):
         if bg_per_ray is None and weights.dim() == 3:
             # the four renderer calls below (models/nerfacto.py:316-320) read the same weights: one launch
             r_, s_ = weights.shape[0], weights.shape[1]
+            lay = ray_samples._layout
+            in_place = lay is not None and lay.ebins.shape == (r_, s_ + 1)
             rgb, accumulation, depth, exp_raw, minmax = ops.render(
-                weights.reshape(r_, s_), colour, ray_samples.frustums.starts, ray_samples.frustums.ends,
-                bg_mode=bg_mode, bg=bg_const, eval_mode=not self.training, want_depth=True)
+                weights.reshape(r_, s_), colour, None if in_place else ray_samples.frustums.starts,
+                None if in_place else ray_samples.frustums.ends, bg_mode=bg_mode, bg=bg_const,
+                eval_mode=not self.training, want_depth=True, bins=lay.ebins if in_place else None)
             expected_depth = torch.clamp(exp_raw, minmax[0], minmax[1])  # batch-global clip, renderers.py:574
         else:
             rgb = renderer(rgb=colour, weights=weights)
@@ -463,9 +506,11 @@ class ThermalNerfactoModel(nn.Module):
         return metrics_dict
 
     def get_loss_dict(self, outputs, batch, metrics_dict=None) -> Dict[str, Tensor]:
-        """models/thermal_nerfacto.py:284-388."""
+        """models/thermal_nerfacto.py:284-388.  Every entry is (config weight) x (term); the terms are collected
+        first and weighted + totalled by one launch (`fused_ops.loss_sum`) -- the returned dict carries the sum
+        the trainer would form (engine/trainer.py:479) as `.total`."""
         c = self.config
-        loss_dict = {}
+        entries: List[Tuple[str, Tensor, float]] = []  # (key, un-weighted term, weight); keys may repeat
         image = batch["image"].to(self.device)
         is_thermal = batch["is_thermal"].to(self.device)
         fused_pixels = (self.fuse_losses and c.background_color != "random" and image.shape[-1] == 3
@@ -474,9 +519,9 @@ class ThermalNerfactoModel(nn.Module):
             # rgb / thermal MSE, tv_pixel and cross_channel terms (:315-354) in one launch each way
             thermal = outputs["rgb_thermal"] if c.density_mode != "rgb_only" else None
             pl = fused_ops.pixel_losses(outputs["rgb"], thermal, image, is_thermal)
-            loss_dict["rgb_loss"] = pl[0]
+            entries.append(("rgb_loss", pl[0], 1.0))
             if c.density_mode != "rgb_only":
-                loss_dict["thermal_loss"] = c.thermal_loss_mult * pl[1]
+                entries.append(("thermal_loss", pl[1], c.thermal_loss_mult))
         else:
             if c.density_mode != "rgb_only":
                 pred = torch.cat((outputs["rgb"], outputs["rgb_thermal"]), dim=1)
@@ -485,46 +530,49 @@ class ThermalNerfactoModel(nn.Module):
             pred_rgb, gt_rgb = self.renderer_rgbt.blend_background_for_loss_computation(
                 pred_image=pred, pred_accumulation=outputs["accumulation"], gt_image=image, is_thermal=is_thermal)
             is_rgb = (1 - is_thermal)[:, None]
-            loss_dict["rgb_loss"] = self.rgb_loss(gt_rgb[..., :3] * is_rgb, pred_rgb[..., :3] * is_rgb)
+            entries.append(("rgb_loss", self.rgb_loss(gt_rgb[..., :3] * is_rgb, pred_rgb[..., :3] * is_rgb), 1.0))
             if c.density_mode != "rgb_only":
                 th = is_thermal[:, None]
-                loss_dict["thermal_loss"] = c.thermal_loss_mult * self.rgb_loss(gt_rgb[..., 3:] * th,
-                                                                              pred_rgb[..., 3:] * th)
+                entries.append(("thermal_loss", self.rgb_loss(gt_rgb[..., 3:] * th, pred_rgb[..., 3:] * th),
+                                c.thermal_loss_mult))
         if c.density_mode == "separate" and c.density_loss_mult > 0:
             m, r = c.density_loss_mult, c.rgb_density_loss_mult
             d, d2, dt, d2t = (outputs["density"], outputs["density2"], outputs["density_thermal"],
                               outputs["density2_thermal"])
             if self.fuse_losses:  # the four L1 terms and their stop-gradient pattern (:328-344) in one launch
-                loss_dict["density_loss"] = fused_ops.density_l1(d, d2, dt, d2t, m, r)
+                entries.append(("density_loss", fused_ops.density_l1(d, d2, dt, d2t, m, r), 1.0))
             elif r == 1:
-                loss_dict["density_loss"] = m * self.density_loss(d2, dt) + m * self.density_loss(d, d2t)
+                entries.append(("density_loss", self.density_loss(d2, dt) + self.density_loss(d, d2t), m))
             else:  # asymmetric stop-gradient pattern, :336-344
-                loss_dict["density_loss"] = (m * self.density_loss(d2.detach(), dt)
-                                             + m * self.density_loss(d.detach(), d2t)
-                                             + r * m * self.density_loss(d2, dt.detach())
-                                             + r * m * self.density_loss(d, d2t.detach()))
+                entries.append(("density_loss", self.density_loss(d2.detach(), dt) + self.density_loss(d.detach(), d2t)
+                                + r * self.density_loss(d2, dt.detach()) + r * self.density_loss(d, d2t.detach()), m))
         if c.density_mode != "rgb_only" and c.tv_pixel_loss_mult > 0:
-            loss_dict["tv_pixel_loss"] = c.tv_pixel_loss_mult * (
-                pl[2] if fused_pixels else tv_pixel_loss(pred_rgb[..., 3:], is_thermal))
+            entries.append(("tv_pixel_loss", pl[2] if fused_pixels else tv_pixel_loss(pred_rgb[..., 3:], is_thermal),
+                            c.tv_pixel_loss_mult))
         if c.density_mode != "rgb_only" and c.cross_channel_loss_mult > 0:
-            loss_dict["cross_channel_loss"] = c.cross_channel_loss_mult * (
-                pl[3] if fused_pixels else cross_channel_loss(pred_rgb[..., 3:], gt_rgb[..., :3], is_thermal))
+            entries.append(("cross_channel_loss", pl[3] if fused_pixels
+                            else cross_channel_loss(pred_rgb[..., 3:], gt_rgb[..., :3], is_thermal),
+                            c.cross_channel_loss_mult))
         if self.training:
-            loss_dict["interlevel_loss"] = 0
-            loss_dict["distortion_loss"] = 0
             assert metrics_dict is not None and "distortion" in metrics_dict
             for s in self.output_suffixes:
-                loss_dict["interlevel_loss"] += c.interlevel_loss_mult * interlevel_loss(
-                    outputs[f"weights_list{s}"], outputs[f"ray_samples_list{s}"])
+                entries.append(("interlevel_loss", interlevel_loss(outputs[f"weights_list{s}"],
+                                                                   outputs[f"ray_samples_list{s}"]),
+                                c.interlevel_loss_mult))
+            for s in self.output_suffixes:
                 # reference quirk kept: the SUMMED distortion metric is added once per suffix (:368)
-                loss_dict["distortion_loss"] += c.distortion_loss_mult * metrics_dict["distortion"]
-            self.camera_optimizer.get_loss_dict(loss_dict)
-            if c.density_mode == "separate":
-                self.camera_optimizer_thermal.get_loss_dict(loss_dict)
-        self.shared_camera_optimizer.get_loss_dict(loss_dict)
+                entries.append(("distortion_loss", metrics_dict["distortion"], c.distortion_loss_mult))
+        cams = [self.camera_optimizer] if self.training else []
+        if self.training and c.density_mode == "separate":
+            cams.append(self.camera_optimizer_thermal)
+        cams.append(self.shared_camera_optimizer)
         if c.density_mode == "separate":
-            self.shared_camera_optimizer_thermal.get_loss_dict(loss_dict)
-        return loss_dict
+            cams.append(self.shared_camera_optimizer_thermal)
+        for cam in cams:
+            tmp: Dict[str, Tensor] = {}
+            cam.get_loss_dict(tmp)
+            entries.extend((k, v, 1.0) for k, v in tmp.items())
+        return _assemble_losses(entries, self.fuse_losses)
 
     def get_train_loss_dict(self, ray_bundle: RayBundle, batch: Dict[str, Tensor], **fw):
         """VanillaPipeline.get_train_loss_dict body, pipelines/base_pipeline.py:291-304."""

@@ -332,14 +332,21 @@ def sample_weights(sigma: Tensor, deltas: Tensor) -> Tensor:
 
 class _RenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weights, colour, starts, ends, bg_mode, bg, eval_mode, want_depth):
+    def forward(ctx, weights, colour, starts, ends, bg_mode, bg, eval_mode, want_depth, bins):
         weights = _f32c(weights)
         r, s = weights.shape
         c = 0 if colour is None else colour.shape[-1]
         dev = weights.device
         colour_c = None if colour is None else _f32c(colour).view(r, s, c)
-        starts_c = None if starts is None else _f32c(starts).view(r, s)
-        ends_c = None if ends is None else _f32c(ends).view(r, s)
+        if bins is not None:  # starts = bins[:, :-1], ends = bins[:, 1:] read in place (row stride S+1)
+            bins = _f32c(bins)
+            assert bins.shape == (r, s + 1)
+            starts_c = ends_c = None
+            p_st, p_en, ts = ptr(bins), ptr(bins) + 4, s + 1
+        else:
+            starts_c = None if starts is None else _f32c(starts).view(r, s)
+            ends_c = None if ends is None else _f32c(ends).view(r, s)
+            p_st, p_en, ts = ptr(starts_c), ptr(ends_c), 0
         rgb = torch.empty((r, c), device=dev) if c else None
         acc = torch.empty((r, 1), device=dev)
         med = exp = minmax = None
@@ -349,40 +356,45 @@ class _RenderFn(torch.autograd.Function):
             # cached device constant + clone: no host->device copy at call time (CUDA-graph capture safe)
             minmax = _host_linspace(("minmax",), lambda: torch.tensor([float("inf"), float("-inf")]), dev).clone()
         bg_arr = float_array(bg) if bg is not None else None
-        call("tn_render_fwd", ptr(weights), ptr(colour_c), ptr(starts_c), ptr(ends_c), r, s, c, bg_mode, bg_arr,
+        call("tn_render_fwd", ptr(weights), ptr(colour_c), p_st, p_en, r, s, ts, c, bg_mode, bg_arr,
              int(eval_mode), ptr(rgb), ptr(acc), ptr(med), ptr(exp), ptr(minmax), stream())
         ctx.bg_mode, ctx.bg, ctx.c = bg_mode, bg, c
-        ctx.save_for_backward(weights, colour_c, starts_c, ends_c)
+        ctx.save_for_backward(weights, colour_c, starts_c, ends_c, bins)
         outs = (rgb, acc, med, exp, minmax)
         ctx.mark_non_differentiable(*[o for o in (med, minmax) if o is not None])
         return outs
 
     @staticmethod
     def backward(ctx, d_rgb, d_acc, _d_med, d_exp, _d_mm):
-        weights, colour, starts, ends = ctx.saved_tensors
+        weights, colour, starts, ends, bins = ctx.saved_tensors
         r, s = weights.shape
         c = ctx.c
+        if bins is not None:
+            p_st, p_en, ts = ptr(bins), ptr(bins) + 4, s + 1
+        else:
+            p_st, p_en, ts = ptr(starts), ptr(ends), 0
         dw = torch.empty_like(weights) if ctx.needs_input_grad[0] else None
         dcol = torch.empty_like(colour) if (c and ctx.needs_input_grad[1]) else None
         bg_arr = float_array(ctx.bg) if ctx.bg is not None else None
         d_rgb = None if (d_rgb is None or not c) else _f32c(d_rgb)
         d_acc = None if d_acc is None else _f32c(d_acc)
         d_exp = None if d_exp is None else _f32c(d_exp)
-        call("tn_render_bwd", ptr(weights), ptr(colour), ptr(starts), ptr(ends), ptr(d_rgb), ptr(d_acc), ptr(d_exp), r,
-             s, c, ctx.bg_mode, bg_arr, ptr(dw), ptr(dcol), stream())
-        return dw, dcol, None, None, None, None, None, None
+        call("tn_render_bwd", ptr(weights), ptr(colour), p_st, p_en, ptr(d_rgb), ptr(d_acc), ptr(d_exp), r,
+             s, ts, c, ctx.bg_mode, bg_arr, ptr(dw), ptr(dcol), stream())
+        return dw, dcol, None, None, None, None, None, None, None
 
 
 def render(weights: Tensor, colour: Optional[Tensor], starts: Optional[Tensor], ends: Optional[Tensor], *,
            bg_mode: int = BG_NONE, bg: Optional[Sequence[float]] = None, eval_mode: bool = False,
-           want_depth: bool = False):
-    """Fused renderer reductions over one launch.
+           want_depth: bool = False, bins: Optional[Tensor] = None):
+    """Fused renderer reductions over one launch.  `bins` [R,S+1] may replace starts/ends (= bins[:, :-1] and
+    bins[:, 1:], read in place).
 
     Returns (rgb [R,C] | None, accumulation [R,1], median depth [R,1] | None,
              UNCLIPPED expected depth [R,1] | None, (min,max) of sample midpoints [2] | None).
     """
     return _RenderFn.apply(weights, colour, starts, ends, bg_mode, None if bg is None else tuple(bg), eval_mode,
-                           want_depth)
+                           want_depth, bins)
 
 
 def library_info() -> str:

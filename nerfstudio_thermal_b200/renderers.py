@@ -180,11 +180,17 @@ class DepthRenderer(nn.Module):
         if self.method not in ("median", "expected"):
             raise NotImplementedError(f"Method {self.method} not implemented")
         lead, s = weights.shape[:-2], weights.shape[-2]
-        starts = ray_samples.frustums.starts.reshape(-1, s)
-        ends = ray_samples.frustums.ends.reshape(-1, s)
+        lay = getattr(ray_samples, "_layout", None)
+        if lay is not None and lay.ebins.shape[-1] == s + 1 and len(lead) == 1:
+            starts = ends = None  # sampler-made samples: the kernel reads the bin edges in place
+            bins = lay.ebins
+        else:
+            starts = ray_samples.frustums.starts.reshape(-1, s)
+            ends = ray_samples.frustums.ends.reshape(-1, s)
+            bins = None
         w = weights.reshape(-1, s)
         if self.method == "median":
-            _, _, med, _, _ = ops.render(w.detach(), None, starts, ends, want_depth=True)
+            _, _, med, _, _ = ops.render(w.detach(), None, starts, ends, want_depth=True, bins=bins)
             return med.view(*lead, 1)
-        _, _, _, exp, minmax = ops.render(w, None, starts, ends, want_depth=True)
+        _, _, _, exp, minmax = ops.render(w, None, starts, ends, want_depth=True, bins=bins)
         return torch.clamp(exp, minmax[0], minmax[1]).view(*lead, 1)

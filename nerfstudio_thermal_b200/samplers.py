@@ -34,7 +34,19 @@ class _PiecewiseSpacing:
 
     def __init__(self, nears: Tensor, fars: Tensor):
         self.nears, self.fars = nears, fars
-        self.s_near, self.s_far = self.fn(nears), self.fn(fars)
+        self._s = None  # spacing-domain near/far: only the torch path (__call__) needs them
+
+    @property
+    def s_near(self) -> Tensor:
+        if self._s is None:
+            self._s = (self.fn(self.nears), self.fn(self.fars))
+        return self._s[0]
+
+    @property
+    def s_far(self) -> Tensor:
+        if self._s is None:
+            self._s = (self.fn(self.nears), self.fn(self.fars))
+        return self._s[1]
 
     @staticmethod
     def fn(x: Tensor) -> Tensor:

@@ -227,7 +227,7 @@ def test_pixel_losses_kernel(with_thermal):
     for i, k in enumerate(keys):
         if k in ref:
             close(pl[i], ref[k] / mults[i], 1e-7, 1e-5)
-    (pl * up.to(DEV)).sum().backward()
+    (torch.stack(pl) * up.to(DEV)).sum().backward()
     close(rg.grad, rgb.grad, 1e-8, 1e-4)
     if with_thermal:
         close(tg.grad, th.grad, 1e-8, 1e-4)
