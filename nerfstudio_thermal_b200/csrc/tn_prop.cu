@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(kPts, 4) prop_fwd_kernel(const float* __restri
 }
 
 constexpr int kStageRows = 2 * PH + 2 * PMAXL + 1;  // dh[16] | g*h[16] | feat[<=16] | g
-constexpr int kStageStride = kPts + 1;              // odd stride: conflict-free column reads
+constexpr int kStageStride = kPts + 4;              // rows 16-byte aligned; 8 rows x 4 floats cover all 32 banks
 
 template <int L, bool NEED_DX>
-__global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
+__global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
     const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ ebins,
     const float* __restrict__ table, LevelScales sc, int log2T, int n_coarse, const float* __restrict__ w1,
     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, float scale,
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
     float* __restrict__ d_dirs) {
   __shared__ PropWeights sw;
   __shared__ float s_scale[TN_MAX_LEVELS];
-  __shared__ float stage[kStageRows * kStageStride];
+  __shared__ __align__(16) float stage[kStageRows * kStageStride];
   constexpr int IN = 2 * L;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < TN_MAX_LEVELS) s_scale[tid] = sc.s[tid];
@@ -291,14 +291,25 @@ __global__ void __launch_bounds__(kPts, 3) prop_bwd_kernel(
         } else {
           a = stage + (2 * PH + 2 * PMAXL) * kStageStride;     // db2 = sum g
         }
-        float sum = 0.f;
+        // rows are read four points at a time (LDS.128): two loads feed four FMAs
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* a4 = reinterpret_cast<const float4*>(a);
         if (b) {
+          const float4* b4 = reinterpret_cast<const float4*>(b);
 #pragma unroll 8
-          for (int q = 0; q < kPts; ++q) sum = fmaf(a[q], b[q], sum);
+          for (int q = 0; q < kPts / 4; ++q) {
+            const float4 x = a4[q], y = b4[q];
+            s4.x = fmaf(x.x, y.x, s4.x); s4.y = fmaf(x.y, y.y, s4.y);
+            s4.z = fmaf(x.z, y.z, s4.z); s4.w = fmaf(x.w, y.w, s4.w);
+          }
         } else {
 #pragma unroll 8
-          for (int q = 0; q < kPts; ++q) sum += a[q];
+          for (int q = 0; q < kPts / 4; ++q) {
+            const float4 x = a4[q];
+            s4.x += x.x; s4.y += x.y; s4.z += x.z; s4.w += x.w;
+          }
         }
+        const float sum = (s4.x + s4.y) + (s4.z + s4.w);
         if (half == 0) acc0 += sum; else acc1 += sum;
       }
     }
@@ -381,7 +392,7 @@ extern "C" int tn_prop_density_bwd(const float* origins, const float* directions
     if (l < L && l == n_coarse && scales_host[l] <= 96.f) ++n_coarse;
   }
   const int64_t N = R * S;
-  const unsigned grid = (unsigned)min((N + kPts - 1) / kPts, (int64_t)kNumSMs * 3);
+  const unsigned grid = (unsigned)min((N + kPts - 1) / kPts, (int64_t)kNumSMs * 4);
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_PB(LL, ...)                                                                 \
   do {                                                                                 \

@@ -24,6 +24,7 @@ class _FieldSplitFn(torch.autograd.Function):
         call("tn_field_split_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, h.shape[-1], geo_dim, emb_dim,
              x_stride, float(scale), ptr(density), ptr(x), stream())
         ctx.dims = (rays, samples, geo_dim, emb_dim, float(scale), x_stride)
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(h, sel)
         return density, x
 
@@ -158,6 +159,7 @@ class _CameraOptFn(torch.autograd.Function):
              ptr(oo), ptr(dd), stream())
         ctx.shared = int(shared)
         ctx.save_for_backward(pose, frozen, cam, directions)
+        ctx.set_materialize_grads(False)
         return oo, dd
 
     @staticmethod

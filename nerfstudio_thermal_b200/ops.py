@@ -359,6 +359,7 @@ class _RenderFn(torch.autograd.Function):
         call("tn_render_fwd", ptr(weights), ptr(colour_c), p_st, p_en, r, s, ts, c, bg_mode, bg_arr,
              int(eval_mode), ptr(rgb), ptr(acc), ptr(med), ptr(exp), ptr(minmax), stream())
         ctx.bg_mode, ctx.bg, ctx.c = bg_mode, bg, c
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(weights, colour_c, starts_c, ends_c, bins)
         outs = (rgb, acc, med, exp, minmax)
         ctx.mark_non_differentiable(*[o for o in (med, minmax) if o is not None])
