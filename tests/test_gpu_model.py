@@ -165,3 +165,34 @@ def test_model_vs_oracle_fresh_seed_default_sizes():
         ref = oracle.thermal_nerfacto_forward(sd, ocfg, o, d, cams, training=False)
     for k in ("rgb", "rgb_thermal", "accumulation", "accumulation_thermal", "expected_depth", "removal"):
         assert max_abs(out[k], ref[k]) <= 1e-3, (k, max_abs(out[k], ref[k]))
+
+
+@pytest.mark.parametrize("mode,rays", [("shared", 8192), ("separate", 4096)])
+def test_full_size_batch_equals_oracle_on_a_slice(mode, rays):
+    """BASELINE configs[1] / configs[3] sizes (default grids, 4096 / 8192 rays): rays are independent, so the outputs
+    of the full batch restricted to 48 rays must equal the oracle run on those 48 rays alone (eval mode: no jitter).
+    expected_depth is left out: its clip is global over the batch (renderers.py:574)."""
+    torch.manual_seed(321)
+    cfg = tn.ThermalNerfactoModelConfig(density_mode=mode)
+    model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if k.endswith("hash_table"):
+                p.mul_(300.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    gen = torch.Generator().manual_seed(9)
+    cams = (torch.arange(rays // 4) % 8).repeat_interleave(4)[:, None]
+    o = torch.randn(rays, 3, generator=gen) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(rays, 3, generator=gen), dim=-1)
+    with torch.no_grad():
+        out = model(tn.RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(rays, 1, device=DEV),
+                                 camera_indices=cams.to(DEV)))
+    sl = torch.arange(0, rays, rays // 48)[:48]
+    ocfg = oracle.OracleConfig(density_mode=mode, is_thermal_cameras=(0, 0, 0, 0, 1, 1, 1, 1))
+    with torch.no_grad():
+        ref = oracle.thermal_nerfacto_forward(sd, ocfg, o[sl], d[sl], cams[sl], training=False)
+    keys = ["rgb", "rgb_thermal", "accumulation"] + (["accumulation_thermal", "removal"] if mode == "separate" else [])
+    for k in keys:
+        assert max_abs(out[k][sl.to(DEV)], ref[k]) <= 1e-3, (k, max_abs(out[k][sl.to(DEV)], ref[k]))
+    assert out["rgb"].shape == (rays, 3) and torch.isfinite(out["rgb"]).all()
