@@ -104,15 +104,19 @@ class FlatGradBuffer:
         base = self.flat.untyped_storage().data_ptr()
         return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
 
-    def all_reduce_mean(self, group=None, async_op: bool = False):
-        """Average the gradients over the ranks of `group` (DDP semantics, base_pipeline.py:282)."""
+    def all_reduce_mean(self, group=None, async_op: bool = False, begin: int = 0, end: Optional[int] = None):
+        """Average the gradients (elements [begin, end) of the buffer; default all) over the ranks of `group`
+        (DDP semantics, base_pipeline.py:282)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)
+        part = self.flat if (begin == 0 and end is None) else self.flat[begin:end]
+        if part.numel() == 0:
+            return None
         if dist.get_backend(group) == "nccl":
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)
-        self.flat.div_(world)
+            return dist.all_reduce(part, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=False)
+        part.div_(world)
         return work
 
 
