@@ -352,7 +352,8 @@ struct TcBwdSmem {
   static constexpr int w2 = w1 + BT * IN * W * 2;
   static constexpr int w3 = w2 + (NL == 3 ? BT * W * W * 2 : 0);
   static constexpr int bias = w3 + BT * W * OUTP * 2;
-  static constexpr int a0 = bias + (2 * W + OUTP) * 4;           // BT terms, (IN/8 + 1) chunks each
+  static constexpr int oh = bias + (2 * W + OUTP) * 4;           // one-hot "ray slot" chunk (head mode), 1 term
+  static constexpr int a0 = oh + CH;                             // BT terms, (IN/8 + 1) chunks each
   static constexpr int a0_term = (IN / 8 + 1) * CH;
   static constexpr int h1 = a0 + BT * a0_term;                   // BT terms, (W/8 + 1) chunks each
   static constexpr int h_term = (W / 8 + 1) * CH;
@@ -368,8 +369,10 @@ struct TcBwdSmem {
   static constexpr int c_dw1 = c_acc + acc_cols;
   static constexpr int c_dw2 = c_dw1 + W;
   static constexpr int c_dw3 = c_dw2 + (NL == 3 ? W : 0);
-  static constexpr int cols_used = c_dw3 + OUTP;
-  static constexpr int tcols = cols_used <= 32 ? 32 : cols_used <= 64 ? 64 : cols_used <= 128 ? 128 : 256;
+  static constexpr int c_ray = c_dw3 + OUTP;                     // head mode: per-ray sums of dZ1 (lane = ray slot)
+  static constexpr int cols_used = c_ray + (IN == 64 && NL == 3 ? W : 0);
+  static constexpr int tcols = cols_used <= 32 ? 32 : cols_used <= 64 ? 64 : cols_used <= 128 ? 128
+                               : cols_used <= 256 ? 256 : 512;
   // resident CTAs per SM: bounded by shared memory and by the 512 TMEM columns (and held to in registers)
   static constexpr int per_sm_smem = (224 * 1024) / (total + 1024);
   static constexpr int per_sm_tmem = 512 / tcols;
@@ -396,11 +399,31 @@ __device__ __forceinline__ void issue_dw(uint32_t tmem_d, uint32_t act_base, uin
       }
 }
 
-// D[128 x NIN] = dZ[128 x KOUT] . Wtile  (Wtile has NP rows = out features, NIN input features)
-template <int NIN, int KOUT, int NP>
+// D[128 x N] = OneHot^T-view . dZ^T-view: row s of D = sum of dZ over the tile's points whose ray slot is s.
+// The one-hot operand is a single chunk (8 "features" = slots); the MMA's remaining 120 M rows over-read the
+// operand tiles that follow it in shared memory (finite values, results unused).
+template <int N>
+__device__ __forceinline__ void issue_ray_sums(uint32_t tmem_d, uint32_t onehot_base, uint32_t dz_base,
+                                               uint32_t dz_term) {
+  constexpr uint32_t idesc = instr_desc_bf16(TP, N, true, true);
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < BT; ++j)
+#pragma unroll
+    for (int q = 0; q < TP / 16; ++q) {
+      const uint64_t ad = smem_desc(onehot_base + q * 256, 128, CH);
+      const uint64_t bd = smem_desc(dz_base + j * dz_term + q * 256, 128, CH);
+      mma_bf16(tmem_d, ad, bd, idesc, acc);
+      acc = 1;
+    }
+}
+
+// D[128 x NIN] = dZ[128 x KOUT] . Wtile  (Wtile has NP rows = out features; NIN of its WIN input features, starting
+// at the feature the caller offset w_base to)
+template <int NIN, int KOUT, int NP, int WIN = NIN>
 __device__ __forceinline__ void issue_dh(uint32_t tmem_d, uint32_t dz_base, uint32_t dz_term, uint32_t w_base) {
   constexpr uint32_t idesc = instr_desc_bf16(TP, NIN, false, true);
-  constexpr uint32_t w_term = NP * NIN * 2;
+  constexpr uint32_t w_term = NP * WIN * 2;
   uint32_t acc = 0;
 #pragma unroll
   for (int i = 0; i < BT; ++i)
@@ -450,10 +473,28 @@ __device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, bool have_mask, u
   }
 }
 
-template <int IN, int W, int NL, bool NEED_DX>
-__global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                                         const uint32_t* __restrict__ relu_mask, int64_t N,
-                                                         TcParams prm, float* __restrict__ dx) {
+// Head mode (the colour head of a NerfactoField, fields/nerfacto_field.py:221-228, 335-348): instead of dX the
+// kernel emits what the layers before the head need --
+//   dh[p, 0]    = d_density[p] * scale * sel[p] * exp(clamp(h[p,0]))      (trunc_exp * selector backward)
+//   dh[p, 1:16] = dX[p, 16:31]                                            (the geometry features' slice of the input)
+//   dz1_ray[r]  += sum over the samples p of ray r of dZ1[p]              (first-layer pre-activation gradients; the
+//                  appearance-embedding gradient is dz1_ray . W1[:, 31:63], one tiny product per step)
+// so neither dX[N,64] nor a separate split/reduce pass touches HBM.
+struct HeadIO {
+  const float* h;          // [N,16] density-MLP output
+  const float* sel;        // [N]
+  const float* d_density;  // [N] or null
+  float* dh;               // [N,16]
+  float* dz1_ray;          // [R,64], accumulated
+  float scale;
+  int S;                   // samples per ray (>= 19: a 128-point tile touches at most 8 rays)
+};
+
+template <int IN, int W, int NL, bool NEED_DX, bool HEAD = false>
+__global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ dy, const uint32_t* __restrict__ relu_mask, int64_t N,
+    TcParams prm, float* __restrict__ dx, HeadIO hd) {
+  static_assert(!HEAD || (IN == 64 && W == 64 && NL == 3), "head mode is the 63-64-64-c colour head");
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcBwdSmem<IN, W, NL>;
   constexpr int MW = W >= 32 ? W / 32 : 1;
@@ -480,7 +521,7 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   prefetch(blockIdx.x);
 
   // zero the whole operand area once: padding chunks / over-read regions must hold finite values
-  for (int i = tid; i < (L::bar - L::a0) / 16; i += NTH) reinterpret_cast<uint4*>(sm + L::a0)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (L::bar - L::oh) / 16; i += NTH) reinterpret_cast<uint4*>(sm + L::oh)[i] = make_uint4(0, 0, 0, 0);
   load_weight_terms<W, IN, BT>(prm.w[0], W, prm.in_dim, sm + L::w1);
   if constexpr (NL == 3) load_weight_terms<W, W, BT>(prm.w[1], W, W, sm + L::w2);
   load_weight_terms<OUTP, W, BT>(prm.w[NL - 1], prm.out_dim, W, sm + L::w3);
@@ -523,6 +564,23 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
     }
 #pragma unroll
     for (int c = 0; c < XP / 8; ++c) store_chunk_terms<BT>(a0, L::a0_term, half * (XP / 8) + c, row, xr + c * 8);
+    float hd_h0 = 0.f, hd_sel = 0.f, hd_dd = 0.f;
+    if constexpr (HEAD) {
+      if (half == 0) {
+        uint4 oh = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows) {
+          const int64_t p = row0 + row;
+          hd_h0 = __ldg(hd.h + p * 16);
+          hd_sel = __ldg(hd.sel + p);
+          hd_dd = hd.d_density ? __ldg(hd.d_density + p) : 0.f;
+          const int slot = (int)(p / hd.S - row0 / hd.S);  // 0..7
+          const uint32_t one = 0x3F80u << (16 * (slot & 1));  // bf16 1.0 in the slot's half word
+          oh.x = (slot >> 1) == 0 ? one : 0u; oh.y = (slot >> 1) == 1 ? one : 0u;
+          oh.z = (slot >> 1) == 2 ? one : 0u; oh.w = (slot >> 1) == 3 ? one : 0u;
+        }
+        *reinterpret_cast<uint4*>(sm + L::oh + (size_t)row * 16) = oh;
+      }
+    }
     fence_async_smem();
     __syncthreads();
     // ---------------- forward recompute (activation VALUES; gating below uses the forward's masks)
@@ -613,13 +671,45 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
     if (tid == 0) {
       tc_fence_after();
       issue_dw<W>(tmem + L::c_dw1, smem_u32(a0), L::a0_term, smem_u32(gb), L::g_term, dw_acc);
-      if constexpr (NEED_DX) issue_dh<IN, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1));
+      if constexpr (HEAD) {
+        issue_ray_sums<W>(tmem + L::c_ray, smem_u32(sm + L::oh), smem_u32(gb), L::g_term);
+        // dX restricted to input features 16..31 (geometry features + the first embedding column)
+        issue_dh<16, W, W, IN>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1) + 2 * (W * 16));
+      } else if constexpr (NEED_DX) {
+        issue_dh<IN, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1));
+      }
       mma_commit(bar);
     }
     dw_acc = 1;
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
-    if constexpr (NEED_DX) {
+    if constexpr (HEAD) {
+      if (half == 0) {  // dh row = [density backward | dX[16:31]]
+        float v[16];
+        tmem_ld16(tmem_row + L::c_acc, v);
+        tmem_ld_wait();
+        if (row < rows) {
+          const float dh0 = hd_dd * hd.scale * hd_sel * expf(fminf(fmaxf(hd_h0, -15.f), 15.f));
+          float4* dst = reinterpret_cast<float4*>(hd.dh + (row0 + row) * 16);
+          dst[0] = make_float4(dh0, v[0], v[1], v[2]);
+          dst[1] = make_float4(v[3], v[4], v[5], v[6]);
+          dst[2] = make_float4(v[7], v[8], v[9], v[10]);
+          dst[3] = make_float4(v[11], v[12], v[13], v[14]);
+        }
+      }
+      if ((warp & 3) == 0) {  // warps 0 and 4 read TMEM lanes 0..31 = ray slots; each takes 32 of the 64 columns
+        float r[32];
+        tmem_ld16(tmem + L::c_ray + half * 32, r);
+        tmem_ld16(tmem + L::c_ray + half * 32 + 16, r + 16);
+        tmem_ld_wait();
+        const int64_t r0 = row0 / hd.S, r_last = (row0 + rows - 1) / hd.S;
+        if (row < 8 && r0 + row <= r_last) {
+          float* dst = hd.dz1_ray + (r0 + row) * W + half * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + i, r[i]);
+        }
+      }
+    } else if constexpr (NEED_DX) {
       // dX rows: TMEM -> registers -> this thread's columns of its dx row (whole 64-byte runs)
       using CX = ColSplit<IN>;
       if (CX::active(half)) {
@@ -707,16 +797,28 @@ static int launch_tc_bwd(const float* x, const float* dy, const uint32_t* mask, 
   static_assert(L::total <= 227 * 1024, "backward tile set does not fit in shared memory");
   const int64_t tiles = (N + TP - 1) / TP;
   const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
+  const HeadIO none = {};
   if (dx) {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, true>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx);
+    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx, none);
   } else {
     auto k = mlp_tc_bwd_kernel<IN, W, NL, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
-    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx);
+    k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, dx, none);
   }
   return check_launch("mlp_tc_bwd_kernel");
+}
+
+static int launch_head_bwd(const float* x, const float* dy, const uint32_t* mask, int64_t N, const TcParams& prm,
+                           const HeadIO& hd, cudaStream_t st) {
+  using L = TcBwdSmem<64, 64, 3>;
+  auto k = mlp_tc_bwd_kernel<64, 64, 3, true, true>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  const int64_t tiles = (N + TP - 1) / TP;
+  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
+  k<<<grid, NTH, L::total, st>>>(x, dy, mask, N, prm, nullptr, hd);
+  return check_launch("mlp_tc_bwd_kernel(head)");
 }
 
 static int fill_tc(TcParams& prm, int in_dim, int x_stride, int width, int out_dim, int n_layers,
@@ -789,4 +891,28 @@ extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* re
   }
   cudaStream_t st = (cudaStream_t)stream;
   TN_TC_DISPATCH(launch_tc_bwd, x, dy, relu_mask, N, prm, dx, st);
+}
+
+extern "C" int tn_field_head_bwd(const float* x, int x_stride, const float* dy, const uint32_t* relu_mask,
+                                 const float* h, const float* sel, const float* d_density, int64_t R, int S,
+                                 int in_dim, int out_dim, float density_scale, const float* const* w_host_ptrs,
+                                 const float* const* b_host_ptrs, int out_act, float* dh_out, float* dz1_ray,
+                                 float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream) {
+  TcParams prm = {};
+  int rc = fill_tc(prm, in_dim, x_stride, 64, out_dim, 3, w_host_ptrs, b_host_ptrs, out_act);
+  if (rc) return rc;
+  TN_REQUIRE(in_dim > 32 && in_dim <= 64, TN_EINVAL, "field_head_bwd: in_dim=%d (the head kernel is the 64-wide tile)",
+             in_dim);
+  TN_REQUIRE(R >= 0 && S >= 19, TN_EINVAL, "field_head_bwd: S=%d < 19 (a 128-point tile must touch at most 8 rays)", S);
+  if (R == 0) return TN_OK;
+  TN_REQUIRE(x && dy && h && sel && dh_out && dz1_ray && dw_host_ptrs && db_host_ptrs, TN_EINVAL,
+             "field_head_bwd: null pointer");
+  TN_REQUIRE(aligned(dh_out, 16), TN_EALIGN, "field_head_bwd: dh_out must be 16-byte aligned");
+  for (int i = 0; i < 3; ++i) {
+    TN_REQUIRE(dw_host_ptrs[i] && db_host_ptrs[i], TN_EINVAL, "field_head_bwd: null grad pointer for layer %d", i);
+    prm.dw[i] = dw_host_ptrs[i];
+    prm.db[i] = db_host_ptrs[i];
+  }
+  HeadIO hd = {h, sel, d_density, dh_out, dz1_ray, density_scale, S};
+  return launch_head_bwd(x, dy, relu_mask, R * (int64_t)S, prm, hd, (cudaStream_t)stream);
 }

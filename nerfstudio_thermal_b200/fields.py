@@ -172,9 +172,18 @@ class NerfactoField(Field):
                 emb_ray = self.embedding_appearance.mean(dim=0)[None, :].expand(rays, -1)
             else:
                 emb_ray = torch.zeros((rays, self.appearance_embedding_dim), device=x.device)
-        density, head_in = fused_ops.field_split(h, selector, sh, emb_ray, rays, samples, self.geo_feat_dim,
-                                                 self.average_init_density)
-        rgb = self.mlp_head(head_in).view(rays, samples, -1)
+        head = self.mlp_head
+        if emb_ray is not None and fused_ops.field_head_supported(h.shape[-1], self.geo_feat_dim, emb_ray.shape[-1],
+                                                                  samples, head):
+            # split + concatenation + colour head as one autograd node (one backward kernel)
+            density, rgb = fused_ops.field_head(h, selector, sh, emb_ray, rays, samples, self.geo_feat_dim,
+                                                self.average_init_density, [l.weight for l in head.layers],
+                                                [l.bias for l in head.layers], head._out_act, sinks=head.grad_sinks)
+            rgb = rgb.view(rays, samples, -1)
+        else:
+            density, head_in = fused_ops.field_split(h, selector, sh, emb_ray, rays, samples, self.geo_feat_dim,
+                                                     self.average_init_density)
+            rgb = head(head_in).view(rays, samples, -1)
         return {FieldHeadNames.RGB: rgb, FieldHeadNames.DENSITY: density.view(rays, samples, 1)}
 
     def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None):

@@ -250,3 +250,47 @@ def test_density_l1_kernel(rgb_mult):
     got.backward()
     for a, b in zip(gs, ts):
         close(a.grad, b.grad, 1e-12, 1e-5)
+
+
+@pytest.mark.parametrize("rays,samples,out_dim", [(37, 48, 3), (11, 19, 1), (64, 256, 4)])
+def test_field_head_fused_backward_equals_unfused(rays, samples, out_dim):
+    """_FieldHeadFn (one backward kernel: restricted dX, density backward and per-ray dZ1 sums by a one-hot MMA) against
+    the unfused composition field_split -> ops.mlp, which the goldens pin."""
+    from nerfstudio_thermal_b200 import ops
+    torch.manual_seed(rays)
+    n, geo, emb_dim = rays * samples, 15, 32
+    h = (torch.randn(n, 16, device=DEV) * 1.5).requires_grad_(True)
+    sel = (torch.rand(n, device=DEV) > 0.2).float()
+    sh = torch.randn(rays, 16, device=DEV)
+    emb = torch.randn(rays, emb_dim, device=DEV).requires_grad_(True)
+    dims = [63, 64, 64, out_dim]
+    ws = [(torch.randn(dims[i + 1], dims[i], device=DEV) / dims[i] ** 0.5).requires_grad_(True) for i in range(3)]
+    bs = [(torch.randn(dims[i + 1], device=DEV) * 0.1).requires_grad_(True) for i in range(3)]
+    gd, gy = torch.randn(n, device=DEV), torch.randn(n, out_dim, device=DEV)
+
+    def run(fused):
+        for t in [h, emb, *ws, *bs]:
+            t.grad = None
+        if fused:
+            dens, y = fused_ops.field_head(h, sel, sh, emb, rays, samples, geo, 0.9, ws, bs, ops.ACT_SIGMOID)
+        else:
+            dens, x = fused_ops.field_split(h, sel, sh, emb, rays, samples, geo, 0.9)
+            y = ops.mlp(x, ws, bs, ops.ACT_SIGMOID)
+        ((dens * gd).sum() + (y * gy).sum()).backward()
+        return dens.detach(), y.detach(), [t.grad.clone() for t in [h, emb, *ws, *bs]]
+
+    d0, y0, g0 = run(False)
+    d1, y1, g1 = run(True)
+    assert torch.equal(d0, d1) and torch.equal(y0, y1)  # same forward kernels
+    names = ["h", "emb", "w1", "w2", "w3", "b1", "b2", "b3"]
+    for name, a, b in zip(names, g0, g1):
+        rel = ((a - b).double().norm() / (a.double().norm() + 1e-30)).item()
+        assert rel <= 2e-4, (name, rel)
+    # density-only gradient (no colour gradient reaches the head)
+    for t in [h, emb, *ws, *bs]:
+        t.grad = None
+    dens, _ = fused_ops.field_head(h, sel, sh, emb, rays, samples, geo, 0.9, ws, bs, ops.ACT_SIGMOID)
+    (dens * gd).sum().backward()
+    ref = gd * 0.9 * sel * torch.exp(h.detach()[:, 0].clamp(-15, 15))
+    close(h.grad[:, 0], ref, 1e-6, 1e-5)
+    assert torch.count_nonzero(h.grad[:, 1:]) == 0
