@@ -178,16 +178,23 @@ int tn_field_split_fwd(const float* h, const float* sel, const float* sh, const 
 int tn_field_split_bwd(const float* h, const float* sel, const float* d_density, const float* dx, int64_t R, int S,
                        int h_width, int geo_dim, int emb_dim, int x_stride, float density_scale, float* dh_out,
                        float* demb_ray_out, void* stream);
-/* The backward of (field_split + colour-head MLP) as ONE tensor-core kernel: replaces the autograd of
- * fields/nerfacto_field.py:221-228 + :335-348 (split / trunc_exp / selector / concatenation / mlp_head).
- * x[R*S, x_stride] = the head input built by tn_field_split_fwd, dy[R*S, out_dim], relu_mask = the head forward's
- * masks, h[R*S,16] = density-MLP output, sel[R*S], d_density[R*S] (may be NULL); head weights as tn_mlp_tc_bwd
- * (63 -> 64 -> 64 -> out_dim).  Outputs: dh_out[R*S,16] (overwritten) = [d_density*scale*sel*exp(clamp(h0)) |
- * dX[:,16:31]]; dz1_ray[R,64] (ACCUMULATED: zero it first) = per-ray sums of the first-layer pre-activation
- * gradients -- the appearance-embedding gradient is dz1_ray . W1[:, 16+geo:]; dW/db accumulated as in
- * tn_mlp_tc_bwd.  Needs S >= 19 (a 128-point tile touches at most 8 rays). */
-int tn_field_head_bwd(const float* x, int x_stride, const float* dy, const uint32_t* relu_mask, const float* h,
-                      const float* sel, const float* d_density, int64_t R, int S, int in_dim, int out_dim,
+/* The colour head of a NerfactoField with its input assembly, one tensor-core kernel each way: replaces
+ * fields/nerfacto_field.py:221-228 (split, trunc_exp, selector) + :335-348 (concatenation, mlp_head) and their autograd.
+ * h[R*S,16] = density-MLP output (column 0 raw density, 1..15 geometry features), sel[R*S], sh[R,16] (per-ray SH
+ * basis), emb_ray[R,32] (per-ray appearance embedding); head weights 63 -> 64 -> 64 -> out_dim (nn.Linear layout,
+ * host tables of device pointers as tn_mlp_tc_fwd).  The 63-wide head input [sh | geo | emb] is assembled in
+ * registers per 128-point tile and never stored.
+ * forward: density_out[R*S] = density_scale * exp(h0) * sel; y[R*S,out_dim]; relu_mask_out uint32[R*S,2,2] or NULL. */
+int tn_field_head_fwd(const float* h, const float* sel, const float* sh, const float* emb_ray, int64_t R, int S,
+                      int out_dim, float density_scale, const float* const* w_host_ptrs,
+                      const float* const* b_host_ptrs, int out_act, float* density_out, float* y,
+                      uint32_t* relu_mask_out, void* stream);
+/* backward: dy[R*S,out_dim], d_density[R*S] (may be NULL) -> dh_out[R*S,16] (overwritten) =
+ * [d_density*scale*sel*exp(clamp(h0)) | dX[:,16:31]]; dz1_ray[R,64] (ACCUMULATED: zero it first) = per-ray sums of
+ * the first-layer pre-activation gradients -- the appearance-embedding gradient is dz1_ray . W1[:, 31:63]; dW/db
+ * accumulated as in tn_mlp_tc_bwd.  Needs S >= 19 (a 128-point tile touches at most 8 rays). */
+int tn_field_head_bwd(const float* dy, const uint32_t* relu_mask, const float* h, const float* sel, const float* sh,
+                      const float* emb_ray, const float* d_density, int64_t R, int S, int out_dim,
                       float density_scale, const float* const* w_host_ptrs, const float* const* b_host_ptrs,
                       int out_act, float* dh_out, float* dz1_ray, float* const* dw_host_ptrs,
                       float* const* db_host_ptrs, void* stream);

@@ -61,8 +61,9 @@ _SIGNATURES = {
     "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
-    "tn_field_head_bwd": [_P, c_int, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_float, _FPP, _FPP, c_int, _P, _P,
-                          _FPP, _FPP, _P],
+    "tn_field_head_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, _FPP, _FPP, c_int, _P, _P, _P, _P],
+    "tn_field_head_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _FPP, _FPP, c_int, _P, _P, _FPP,
+                          _FPP, _P],
     "tn_camera_reg_fwd": [_P, c_int, c_float, c_float, c_float, _P, _P],
     "tn_camera_reg_bwd": [_P, _P, c_int, c_float, c_float, c_float, _P, _P],
     "tn_loss_sum": [_FPP, POINTER(c_float), POINTER(c_int), c_int, c_int, _P, _P],

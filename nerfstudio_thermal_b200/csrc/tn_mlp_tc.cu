@@ -144,6 +144,53 @@ __device__ __forceinline__ void load_row_part(const float* __restrict__ x, int64
   }
 }
 
+// Head mode input: the colour head's 63-wide row [SH16 | geo15 | appearance32] (fields/nerfacto_field.py:335-344) is
+// never materialised -- each thread assembles its 32 columns from the per-ray SH basis, the density-MLP output and
+// the per-ray appearance embedding (all whole 16-byte loads).
+struct HeadIn {
+  const float* sh;   // [R,16]
+  const float* h;    // [N,16]: column 0 = raw density, 1..15 = geometry features
+  const float* emb;  // [R,32]
+  int S;             // samples per ray
+};
+// columns half*32 .. half*32+31 of the head input of point p; h0 receives h[p,0] (half 0 only)
+__device__ __forceinline__ void load_head_part(const HeadIn& g, int64_t p, bool valid, int half, float (&v)[32],
+                                               float& h0) {
+  h0 = 0.f;
+  if (!valid) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+    return;
+  }
+  const int64_t r = p / g.S;
+  if (half == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(g.sh + r * 16);
+    const float4* h4 = reinterpret_cast<const float4*>(g.h + p * 16);
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 a = __ldg(s4 + i), b = __ldg(h4 + i);
+      v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+      t[4 * i] = b.x; t[4 * i + 1] = b.y; t[4 * i + 2] = b.z; t[4 * i + 3] = b.w;
+    }
+    h0 = t[0];
+#pragma unroll
+    for (int k = 0; k < 15; ++k) v[16 + k] = t[k + 1];
+    v[31] = __ldg(g.emb + r * 32);
+  } else {
+    const float4* e4 = reinterpret_cast<const float4*>(g.emb + r * 32);
+    float t[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = __ldg(e4 + i);
+      t[4 * i] = a.x; t[4 * i + 1] = a.y; t[4 * i + 2] = a.z; t[4 * i + 3] = a.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 31; ++k) v[k] = t[k + 1];
+    v[31] = 0.f;
+  }
+}
+
 // columns of a W-wide layer handled by one of the two threads of a point
 template <int W>
 struct ColSplit {
@@ -200,9 +247,20 @@ struct TcSmem {
   static constexpr int per_sm = per_sm_raw < 1 ? 1 : (per_sm_raw > 4 ? 4 : per_sm_raw);
 };
 
-template <int IN, int W, int NL>
-__global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_kernel(const float* __restrict__ x, int64_t N, TcParams prm,
-                                                         float* __restrict__ y, uint32_t* __restrict__ relu_mask) {
+// forward-side extras of head mode: the density (trunc_exp * selector, fields/nerfacto_field.py:227-228) leaves from
+// the same kernel, since the thread that loads h[p, 1:16] holds h[p, 0] anyway
+struct HeadFwd {
+  HeadIn in;
+  const float* sel;    // [N]
+  float* density_out;  // [N]
+  float scale;
+};
+
+template <int IN, int W, int NL, bool HEAD = false>
+__global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_kernel(
+    const float* __restrict__ x, int64_t N, TcParams prm, float* __restrict__ y, uint32_t* __restrict__ relu_mask,
+    HeadFwd hf) {
+  static_assert(!HEAD || (IN == 64 && W == 64 && NL == 3), "head mode is the 63-64-64-c colour head");
   extern __shared__ __align__(128) uint8_t sm[];
   using L = TcSmem<IN, W, NL>;
   constexpr int TCOLS = W >= 64 ? 64 : 32;
@@ -216,8 +274,13 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
 
   const int64_t tiles = (N + TP - 1) / TP;
   float xr[XP];  // this thread's half of its point's input row: fetched one tile ahead
-  load_row_part<XP>(x, (int64_t)blockIdx.x * TP + row, prm.x_stride, prm.in_dim,
-                    (int64_t)blockIdx.x * TP + row < N, half * XP, xr);
+  float xh0 = 0.f;  // head mode: h[p, 0] of that row
+  auto fetch = [&](int64_t t) {
+    const int64_t p = t * TP + row;
+    if constexpr (HEAD) load_head_part(hf.in, p, p < N, half, xr, xh0);
+    else load_row_part<XP>(x, p, prm.x_stride, prm.in_dim, p < N, half * XP, xr);
+  };
+  fetch(blockIdx.x);
 
   load_weight_terms<W, IN, FT>(prm.w[0], W, prm.in_dim, sm + L::w1);
   if constexpr (NL == 3) load_weight_terms<W, W, FT>(prm.w[1], W, W, sm + L::w2);
@@ -247,6 +310,10 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
     // ---- input tile: split the prefetched half row and write the A0 operand chunks
 #pragma unroll
     for (int c = 0; c < XP / 8; ++c) store_chunk_terms<FT>(act, L::act_term, half * (XP / 8) + c, row, xr + c * 8);
+    if constexpr (HEAD) {
+      if (half == 0 && row < rows)
+        hf.density_out[row0 + row] = hf.scale * expf(xh0) * __ldg(hf.sel + row0 + row);
+    }
     fence_async_smem();
     __syncthreads();  // A0 visible to the async proxy
     // ---- layer 1
@@ -255,10 +322,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       issue_layer<W, IN, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
-    {  // next tile's input rows: in flight while this tile computes
-      const int64_t rn = (t + gridDim.x) * TP + row;
-      if (t + gridDim.x < tiles) load_row_part<XP>(x, rn, prm.x_stride, prm.in_dim, rn < N, half * XP, xr);
-    }
+    if (t + gridDim.x < tiles) fetch(t + gridDim.x);  // next tile's input rows: in flight while this tile computes
     mbar_wait(bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -331,8 +395,19 @@ static int launch_tc_fwd(const float* x, int64_t N, const TcParams& prm, float* 
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
   const int64_t tiles = (N + TP - 1) / TP;
   const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
-  k<<<grid, NTH, L::total, st>>>(x, N, prm, y, mask);
+  k<<<grid, NTH, L::total, st>>>(x, N, prm, y, mask, HeadFwd{});
   return check_launch("mlp_tc_fwd_kernel");
+}
+
+static int launch_head_fwd(int64_t N, const TcParams& prm, float* y, uint32_t* mask, const HeadFwd& hf,
+                           cudaStream_t st) {
+  using L = TcSmem<64, 64, 3>;
+  auto k = mlp_tc_fwd_kernel<64, 64, 3, true>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
+  const int64_t tiles = (N + TP - 1) / TP;
+  const unsigned grid = (unsigned)min(tiles, (int64_t)kNumSMs * L::per_sm);
+  k<<<grid, NTH, L::total, st>>>(nullptr, N, prm, y, mask, hf);
+  return check_launch("mlp_tc_fwd_kernel(head)");
 }
 
 // ------------------------------------------------------------------------------------------------ backward
@@ -481,6 +556,7 @@ __device__ __forceinline__ void dh_epilogue(uint32_t tmem_row, bool have_mask, u
 //                  appearance-embedding gradient is dz1_ray . W1[:, 31:63], one tiny product per step)
 // so neither dX[N,64] nor a separate split/reduce pass touches HBM.
 struct HeadIO {
+  HeadIn in;               // the head input is re-assembled, not read
   const float* h;          // [N,16] density-MLP output
   const float* sel;        // [N]
   const float* d_density;  // [N] or null
@@ -513,9 +589,11 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   // operands fetched one tile ahead: this thread's half input row, and (column half 0) the point's dy row
   float xr[XP];
   float dyr[OUTP];
+  float xh0 = 0.f;  // head mode: h[p, 0] of the prefetched row
   auto prefetch = [&](int64_t t) {
     const int64_t r = t * TP + row;
-    load_row_part<XP>(x, r, prm.x_stride, prm.in_dim, r < N, half * XP, xr);
+    if constexpr (HEAD) load_head_part(hd.in, r, r < N, half, xr, xh0);
+    else load_row_part<XP>(x, r, prm.x_stride, prm.in_dim, r < N, half * XP, xr);
     if (half == 0) load_row_part<OUTP>(dy, r, prm.out_dim, prm.out_dim, r < N, 0, dyr);
   };
   prefetch(blockIdx.x);
@@ -570,7 +648,7 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
         uint4 oh = make_uint4(0u, 0u, 0u, 0u);
         if (row < rows) {
           const int64_t p = row0 + row;
-          hd_h0 = __ldg(hd.h + p * 16);
+          hd_h0 = xh0;
           hd_sel = __ldg(hd.sel + p);
           hd_dd = hd.d_density ? __ldg(hd.d_density + p) : 0.f;
           const int slot = (int)(p / hd.S - row0 / hd.S);  // 0..7
@@ -893,26 +971,47 @@ extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* re
   TN_TC_DISPATCH(launch_tc_bwd, x, dy, relu_mask, N, prm, dx, st);
 }
 
-extern "C" int tn_field_head_bwd(const float* x, int x_stride, const float* dy, const uint32_t* relu_mask,
-                                 const float* h, const float* sel, const float* d_density, int64_t R, int S,
-                                 int in_dim, int out_dim, float density_scale, const float* const* w_host_ptrs,
+static int fill_head(TcParams& prm, int out_dim, const float* const* w, const float* const* b, int out_act, int64_t R,
+                     int S, const float* h, const float* sel, const float* sh, const float* emb_ray) {
+  int rc = fill_tc(prm, 63, 64, 64, out_dim, 3, w, b, out_act);
+  if (rc) return rc;
+  TN_REQUIRE(R >= 0 && S >= 1, TN_EINVAL, "field_head: bad R=%lld S=%d", (long long)R, S);
+  TN_REQUIRE(R == 0 || (h && sel && sh && emb_ray), TN_EINVAL, "field_head: null pointer");
+  TN_REQUIRE(aligned(h, 16) && aligned(sh, 16) && aligned(emb_ray, 16), TN_EALIGN,
+             "field_head: h / sh / emb_ray must be 16-byte aligned");
+  return TN_OK;
+}
+
+extern "C" int tn_field_head_fwd(const float* h, const float* sel, const float* sh, const float* emb_ray, int64_t R,
+                                 int S, int out_dim, float density_scale, const float* const* w_host_ptrs,
+                                 const float* const* b_host_ptrs, int out_act, float* density_out, float* y,
+                                 uint32_t* relu_mask_out, void* stream) {
+  TcParams prm = {};
+  int rc = fill_head(prm, out_dim, w_host_ptrs, b_host_ptrs, out_act, R, S, h, sel, sh, emb_ray);
+  if (rc) return rc;
+  if (R == 0) return TN_OK;
+  TN_REQUIRE(density_out && y, TN_EINVAL, "field_head_fwd: null output");
+  HeadFwd hf = {{sh, h, emb_ray, S}, sel, density_out, density_scale};
+  return launch_head_fwd(R * (int64_t)S, prm, y, relu_mask_out, hf, (cudaStream_t)stream);
+}
+
+extern "C" int tn_field_head_bwd(const float* dy, const uint32_t* relu_mask, const float* h, const float* sel,
+                                 const float* sh, const float* emb_ray, const float* d_density, int64_t R, int S,
+                                 int out_dim, float density_scale, const float* const* w_host_ptrs,
                                  const float* const* b_host_ptrs, int out_act, float* dh_out, float* dz1_ray,
                                  float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream) {
   TcParams prm = {};
-  int rc = fill_tc(prm, in_dim, x_stride, 64, out_dim, 3, w_host_ptrs, b_host_ptrs, out_act);
+  int rc = fill_head(prm, out_dim, w_host_ptrs, b_host_ptrs, out_act, R, S, h, sel, sh, emb_ray);
   if (rc) return rc;
-  TN_REQUIRE(in_dim > 32 && in_dim <= 64, TN_EINVAL, "field_head_bwd: in_dim=%d (the head kernel is the 64-wide tile)",
-             in_dim);
-  TN_REQUIRE(R >= 0 && S >= 19, TN_EINVAL, "field_head_bwd: S=%d < 19 (a 128-point tile must touch at most 8 rays)", S);
+  TN_REQUIRE(S >= 19, TN_EINVAL, "field_head_bwd: S=%d < 19 (a 128-point tile must touch at most 8 rays)", S);
   if (R == 0) return TN_OK;
-  TN_REQUIRE(x && dy && h && sel && dh_out && dz1_ray && dw_host_ptrs && db_host_ptrs, TN_EINVAL,
-             "field_head_bwd: null pointer");
+  TN_REQUIRE(dy && dh_out && dz1_ray && dw_host_ptrs && db_host_ptrs, TN_EINVAL, "field_head_bwd: null pointer");
   TN_REQUIRE(aligned(dh_out, 16), TN_EALIGN, "field_head_bwd: dh_out must be 16-byte aligned");
   for (int i = 0; i < 3; ++i) {
     TN_REQUIRE(dw_host_ptrs[i] && db_host_ptrs[i], TN_EINVAL, "field_head_bwd: null grad pointer for layer %d", i);
     prm.dw[i] = dw_host_ptrs[i];
     prm.db[i] = db_host_ptrs[i];
   }
-  HeadIO hd = {h, sel, d_density, dh_out, dz1_ray, density_scale, S};
-  return launch_head_bwd(x, dy, relu_mask, R * (int64_t)S, prm, hd, (cudaStream_t)stream);
+  HeadIO hd = {{sh, h, emb_ray, S}, h, sel, d_density, dh_out, dz1_ray, density_scale, S};
+  return launch_head_bwd(nullptr, dy, relu_mask, R * (int64_t)S, prm, hd, (cudaStream_t)stream);
 }

@@ -49,40 +49,33 @@ def field_split(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Optional[Tensor], r
 
 
 class _FieldHeadFn(torch.autograd.Function):
-    """field_split + colour-head MLP as one autograd node whose backward is ONE kernel (tn_field_head_bwd): the
-    head-input gradient dX[N,64] never reaches HBM and no separate split / per-ray reduction pass runs."""
+    """A NerfactoField's colour head with its input assembly as one autograd node: ONE tensor-core kernel each way
+    (tn_field_head_fwd / _bwd).  Neither the 63-wide head input nor its gradient ever reaches HBM."""
 
     @staticmethod
-    def forward(ctx, h, sel, sh, emb_ray, rays, samples, geo_dim, scale, out_act, sinks, *wb):
-        from . import ops
+    def forward(ctx, h, sel, sh, emb_ray, rays, samples, scale, out_act, sinks, *wb):
         h, sel, sh, emb_ray = _f32c(h), _f32c(sel), _f32c(sh), _f32c(emb_ray)
         ws = [_f32c(t) for t in wb[0::2]]
         bs = [_f32c(t) for t in wb[1::2]]
-        emb_dim = emb_ray.shape[-1]
-        n = rays * samples
-        in_dim = 16 + geo_dim + emb_dim
-        x_stride = (in_dim + 3) // 4 * 4
+        n, out_dim = rays * samples, ws[-1].shape[0]
         density = torch.empty((n,), device=h.device)
-        x = torch.empty((n, x_stride), device=h.device)
-        call("tn_field_split_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, h.shape[-1], geo_dim, emb_dim,
-             x_stride, float(scale), ptr(density), ptr(x), stream())
-        out_dim = ws[-1].shape[0]
         y = torch.empty((n, out_dim), device=h.device)
-        mask = torch.empty((n, 2, 2), device=h.device, dtype=torch.int32)
-        call("tn_mlp_tc_fwd", ptr(x), n, in_dim, x_stride, 64, out_dim, 3, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
-             ptr(mask), stream(), tag=f"[{in_dim}-64x2-{out_dim}]")
-        ctx.dims = (rays, samples, geo_dim, emb_dim, float(scale), in_dim, x_stride, out_dim, out_act)
+        need_mask = any(ctx.needs_input_grad)
+        mask = torch.empty((n, 2, 2), device=h.device, dtype=torch.int32) if need_mask else None
+        call("tn_field_head_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, out_dim, float(scale),
+             ptr_array(ws), ptr_array(bs), out_act, ptr(density), ptr(y), ptr(mask), stream(), tag=f"[63-64x2-{out_dim}]")
+        ctx.dims = (rays, samples, float(scale), out_dim, out_act)
         ctx.sinks = sinks
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(h, sel, x, mask, *ws, *bs)
+        ctx.save_for_backward(h, sel, sh, emb_ray, mask, *ws, *bs)
         return density, y
 
     @staticmethod
     def backward(ctx, d_density, dy):
         saved = ctx.saved_tensors
-        h, sel, x, mask = saved[:4]
-        ws, bs = list(saved[4:7]), list(saved[7:10])
-        rays, samples, geo_dim, emb_dim, scale, in_dim, x_stride, out_dim, out_act = ctx.dims
+        h, sel, sh, emb_ray, mask = saved[:5]
+        ws, bs = list(saved[5:8]), list(saved[8:11])
+        rays, samples, scale, out_dim, out_act = ctx.dims
         if dy is None:
             dy = torch.zeros((rays * samples, out_dim), device=h.device)
         sinks = ctx.sinks
@@ -92,15 +85,15 @@ class _FieldHeadFn(torch.autograd.Function):
             dws, dbs = [torch.zeros_like(w) for w in ws], [torch.zeros_like(b) for b in bs]
         dh = torch.empty_like(h)
         dz1_ray = torch.zeros((rays, 64), device=h.device)
-        call("tn_field_head_bwd", ptr(x), x_stride, ptr(_f32c(dy)), ptr(mask), ptr(h), ptr(sel),
-             ptr(None if d_density is None else _f32c(d_density)), rays, samples, in_dim, out_dim, scale,
-             ptr_array(ws), ptr_array(bs), out_act, ptr(dh), ptr(dz1_ray), ptr_array(dws), ptr_array(dbs), stream(),
-             tag=f"[{in_dim}-64x2-{out_dim}]")
-        demb = dz1_ray @ ws[0][:, 16 + geo_dim:in_dim] if ctx.needs_input_grad[3] else None
+        call("tn_field_head_bwd", ptr(_f32c(dy)), ptr(mask), ptr(h), ptr(sel), ptr(sh), ptr(emb_ray),
+             ptr(None if d_density is None else _f32c(d_density)), rays, samples, out_dim, scale, ptr_array(ws),
+             ptr_array(bs), out_act, ptr(dh), ptr(dz1_ray), ptr_array(dws), ptr_array(dbs), stream(),
+             tag=f"[63-64x2-{out_dim}]")
+        demb = dz1_ray @ ws[0][:, 31:63] if ctx.needs_input_grad[3] else None
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [None, None] if sinks is not None else [dw, db]
-        return (dh, None, None, demb, None, None, None, None, None, None, *grads)
+        return (dh, None, None, demb, None, None, None, None, None, *grads)
 
 
 def field_head(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Tensor, rays: int, samples: int, geo_dim: int,
@@ -111,14 +104,15 @@ def field_head(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Tensor, rays: int, s
     wb = []
     for w, b in zip(weights, biases):
         wb += [w, b]
-    return _FieldHeadFn.apply(h, sel, sh, emb_ray, rays, samples, geo_dim, scale, out_act, sinks, *wb)
+    assert geo_dim == 15 and emb_ray.shape[-1] == 32 and h.shape[-1] == 16, "see field_head_supported"
+    return _FieldHeadFn.apply(h, sel, sh, emb_ray, rays, samples, scale, out_act, sinks, *wb)
 
 
 def field_head_supported(h_width: int, geo_dim: int, emb_dim: int, samples: int, head) -> bool:
     """Shapes the fused head backward handles: 16-wide density-MLP output, a 64-wide 3-layer head whose input
     (16 + geo + emb) fills the 64-column tile, and at most 8 rays per 128-point tile."""
     from . import ops
-    return (h_width == 16 and geo_dim == 15 and 32 < 16 + geo_dim + emb_dim <= 64 and emb_dim > 0 and samples >= 19
+    return (h_width == 16 and geo_dim == 15 and emb_dim == 32 and samples >= 19
             and len(head.layers) == 3 and head.layers[0].weight.shape[0] == 64 and head.layers[1].weight.shape == (64, 64)
             and head.layers[2].weight.shape[0] <= 16 and head._out_act is not None
             and ops.MLP_BACKEND == {"fwd": "tc", "bwd": "tc"})
