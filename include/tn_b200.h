@@ -98,17 +98,20 @@ int tn_mlp_bwd(const float* x, const float* dy, int64_t N, int in_dim, int width
  * x_stride: floats between consecutive rows of x (and of dx); 0 = in_dim.  A stride that is a multiple of 4
  *   with 16-byte aligned x lets a tile read whole 16-byte runs (a 63-wide input padded to 64: columns
  *   [in_dim, x_stride) are ignored on read and written as zeros in dx when x_stride <= 64);
+ * row_mul / out_scale: every output row is multiplied by out_scale * row_mul[p] (row_mul NULL = 1) after the
+ *   activation -- with out_act = 2 and a 1-row last layer this is average_init_density * trunc_exp(z) * selector
+ *   (fields/nerfacto_field.py:227-228) as the MLP's epilogue;
  * relu_mask_out: NULL, or uint32[N, n_layers-1, max(1,width/32)] receiving bit j of hidden layer l = (z_lj > 0). */
 int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int x_stride, int width, int out_dim, int n_layers,
-                  const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act, float* y,
-                  uint32_t* relu_mask_out, void* stream);
+                  const float* const* w_host_ptrs, const float* const* b_host_ptrs, int out_act,
+                  const float* row_mul, float out_scale, float* y, uint32_t* relu_mask_out, void* stream);
 /* Backward on the tensor cores as well (arguments as tn_mlp_bwd): activations recomputed per tile, dH = dZ.W
  * and dW^T += A^T.dZ as tcgen05 MMAs, dW/db accumulators resident in TMEM across the tiles of a persistent CTA
  * and flushed once with atomics.  relu_mask: the forward's masks (NULL: gate on the recomputed activations). */
 int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim, int x_stride,
                   int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
-                  const float* const* b_host_ptrs, int out_act, float* dx, float* const* dw_host_ptrs,
-                  float* const* db_host_ptrs, void* stream);
+                  const float* const* b_host_ptrs, int out_act, const float* row_mul, float out_scale, float* dx,
+                  float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream);
 
 /* Real spherical-harmonics basis, 4 levels (16 components).
  *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */

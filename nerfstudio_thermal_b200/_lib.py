@@ -38,8 +38,9 @@ _SIGNATURES = {
     "tn_contract_points_bwd": [_P, _P, c_int64, _P, _P],
     "tn_mlp_fwd": [_P, c_int64, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _P],
     "tn_mlp_bwd": [_P, _P, c_int64, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _FPP, _FPP, _P],
-    "tn_mlp_tc_fwd": [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _P, _P],
-    "tn_mlp_tc_bwd": [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _FPP, _FPP, _P],
+    "tn_mlp_tc_fwd": [_P, c_int64, c_int, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, c_float, _P, _P, _P],
+    "tn_mlp_tc_bwd": [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, c_float, _P, _FPP,
+                      _FPP, _P],
     "tn_sh4": [_P, c_int64, _P, _P],
     "tn_piecewise_bins": [_P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, _P],
     "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],

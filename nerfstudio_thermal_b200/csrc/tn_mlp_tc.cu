@@ -35,6 +35,8 @@ struct TcParams {
   float* dw[3];
   float* db[3];
   int in_dim, out_dim, out_act, x_stride;
+  const float* row_mul;  // optional [N]: every output row is multiplied by out_scale * row_mul[p] after the activation
+  float out_scale;       // (density = average_init_density * trunc_exp(z) * selector as the epilogue of the density MLP)
 };
 
 // x = t[0] + t[1] + ... as bf16 terms.  Every term but the last of a two-term split is a TRUNCATION (the top 16
@@ -360,12 +362,13 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       tmem_ld_wait();
       if (row < rows) {
         float* dst = y + (row0 + row) * prm.out_dim;
+        const float om = prm.out_scale * (prm.row_mul ? __ldg(prm.row_mul + row0 + row) : 1.f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float z = v[j] + bias[2 * W + j];
           if (prm.out_act == 1) z = 1.f / (1.f + expf(-z));
           else if (prm.out_act == 2) z = expf(z);
-          v[j] = z;
+          v[j] = z * om;
         }
         if (prm.out_dim == 16 && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
 #pragma unroll
@@ -699,9 +702,10 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
       tmem_ld16(tmem_row + L::c_acc, z);
       tmem_ld_wait();
       float u[16];
+      const float om = prm.out_scale * ((prm.row_mul && row < rows) ? __ldg(prm.row_mul + row0 + row) : 1.f);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float gv = dyr[j];  // zero beyond out_dim and for rows past N
+        float gv = dyr[j] * om;  // zero beyond out_dim and for rows past N
         const float zz = z[j] + bias[2 * W + j];
         if (prm.out_act == 1) {
           const float sg = 1.f / (1.f + expf(-zz));
@@ -915,6 +919,8 @@ static int fill_tc(TcParams& prm, int in_dim, int x_stride, int width, int out_d
   }
   prm.in_dim = in_dim; prm.out_dim = out_dim; prm.out_act = out_act;
   prm.x_stride = x_stride ? x_stride : in_dim;
+  prm.row_mul = nullptr;
+  prm.out_scale = 1.f;
   return TN_OK;
 }
 
@@ -943,10 +949,13 @@ using namespace tn;
 
 extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int x_stride, int width, int out_dim,
                              int n_layers, const float* const* w_host_ptrs, const float* const* b_host_ptrs,
-                             int out_act, float* y, uint32_t* relu_mask_out, void* stream) {
+                             int out_act, const float* row_mul, float out_scale, float* y, uint32_t* relu_mask_out,
+                             void* stream) {
   TcParams prm = {};
   int rc = fill_tc(prm, in_dim, x_stride, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
+  prm.row_mul = row_mul;
+  prm.out_scale = out_scale;
   if (N == 0) return TN_OK;
   TN_REQUIRE(x && y && N > 0, TN_EINVAL, "mlp_tc_fwd: bad x/y/N");
   cudaStream_t st = (cudaStream_t)stream;
@@ -955,11 +964,13 @@ extern "C" int tn_mlp_tc_fwd(const float* x, int64_t N, int in_dim, int x_stride
 
 extern "C" int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, int64_t N, int in_dim,
                              int x_stride, int width, int out_dim, int n_layers, const float* const* w_host_ptrs,
-                             const float* const* b_host_ptrs, int out_act, float* dx, float* const* dw_host_ptrs,
-                             float* const* db_host_ptrs, void* stream) {
+                             const float* const* b_host_ptrs, int out_act, const float* row_mul, float out_scale,
+                             float* dx, float* const* dw_host_ptrs, float* const* db_host_ptrs, void* stream) {
   TcParams prm = {};
   int rc = fill_tc(prm, in_dim, x_stride, width, out_dim, n_layers, w_host_ptrs, b_host_ptrs, out_act);
   if (rc) return rc;
+  prm.row_mul = row_mul;
+  prm.out_scale = out_scale;
   if (N == 0) return TN_OK;
   TN_REQUIRE(x && dy && N > 0 && dw_host_ptrs && db_host_ptrs, TN_EINVAL, "mlp_tc_bwd: bad x/dy/N/grad tables");
   for (int i = 0; i < n_layers; ++i) {

@@ -149,6 +149,25 @@ class NerfactoField(Field):
         density = fused_ops.density_act(h_flat, selector, self.average_init_density).view(*shape, 1)
         return density, base_mlp_out
 
+    def get_density_only(self, ray_samples: RaySamples) -> Tensor:
+        """get_density(...)[0] without the geometry features: only row 0 of the density MLP's last layer is evaluated
+        and `average_init_density * trunc_exp(.) * selector` (:227-228) is that kernel's epilogue.  Used for the
+        cross-field density terms (models/thermal_nerfacto.py:447-458), which discard everything else."""
+        mlp = self.mlp_base.model[1]
+        if mlp._out_act != ops.ACT_NONE or len(mlp.layers) < 2:
+            return self.get_density(ray_samples)[0]
+        x, selector = self._grid_coordinates(ray_samples)
+        feats = self.mlp_base.model[0](x)
+        ws = [l.weight for l in mlp.layers[:-1]] + [mlp.layers[-1].weight[:1]]
+        bs = [l.bias for l in mlp.layers[:-1]] + [mlp.layers[-1].bias[:1]]
+        sinks = None
+        if mlp.grad_sinks is not None:
+            lw, lb = mlp.grad_sinks[-1]
+            sinks = [*mlp.grad_sinks[:-1], (lw[:1], lb[:1])]
+        density = ops.mlp(feats, ws, bs, ops.ACT_TRUNC_EXP, sinks=sinks, row_mul=selector,
+                          out_scale=self.average_init_density)
+        return density.view(*ray_samples.frustums.shape, 1)
+
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
         """Field.forward (fields/base_field.py:114-133).  For samples that carry a per-ray layout the density
         activation, the geo/SH/appearance concatenation (:335-344) and its backward run as one kernel each

@@ -457,8 +457,8 @@ class ThermalNerfactoModel(nn.Module):
             if c.density_loss_mult > 0 or not self.training:
                 # cross-field densities for the density regulariser (:447-458).  The reference runs the full
                 # field forward here and throws the colour away; only the density is evaluated.
-                outputs["density2"] = self.field.get_density(ray_samples_thermal)[0]
-                outputs["density2_thermal"] = self.field_thermal.get_density(ray_samples)[0]
+                outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
+                outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
 
             if not self.training:
                 # "removal" renders (:460-487).  The reference recomputes both field forwards on the very same

@@ -159,8 +159,10 @@ MLP_BACKEND = {"fwd": "tc", "bwd": "tc"}
 
 class _MlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, out_act, sinks, *wb):
+    def forward(ctx, x, out_act, sinks, row_mul, out_scale, *wb):
         x = _f32c(x)
+        row_mul = None if row_mul is None else _f32c(row_mul).view(-1)
+        ctx.out_scale = float(out_scale)
         ws = [_f32c(t) for t in wb[0::2]]
         bs = [_f32c(t) for t in wb[1::2]]
         ctx.sinks = sinks
@@ -176,21 +178,22 @@ class _MlpFn(torch.autograd.Function):
             if MLP_BACKEND["bwd"] == "tc" and any(ctx.needs_input_grad):
                 mask = torch.empty((n, nl - 1, max(1, width // 32)), device=x.device, dtype=torch.int32)
             call("tn_mlp_tc_fwd", ptr(x), n, in_dim, x_stride, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act,
-                 ptr(y), ptr(mask), stream(), tag=tag)
+                 ptr(row_mul), ctx.out_scale, ptr(y), ptr(mask), stream(), tag=tag)
         else:
+            assert row_mul is None and out_scale == 1.0, "output multipliers are a tensor-core epilogue (see mlp())"
             xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
             call("tn_mlp_fwd", ptr(xd), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
                  stream(), tag=tag)
         ctx.out_act = out_act
         ctx.nl = nl
-        ctx.save_for_backward(x, mask, *ws, *bs)
+        ctx.save_for_backward(x, mask, row_mul, *ws, *bs)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         saved = ctx.saved_tensors
-        x, mask, nl = saved[0], saved[1], ctx.nl
-        ws, bs = list(saved[2:2 + nl]), list(saved[2 + nl:])
+        x, mask, row_mul, nl = saved[0], saved[1], saved[2], ctx.nl
+        ws, bs = list(saved[3:3 + nl]), list(saved[3 + nl:])
         n, x_stride = x.shape
         in_dim = ws[0].shape[1]
         width, out_dim = ws[0].shape[0], ws[-1].shape[0]
@@ -210,7 +213,8 @@ class _MlpFn(torch.autograd.Function):
         tag = f"[{in_dim}-{width}x{nl - 1}-{out_dim}]"
         if MLP_BACKEND["bwd"] == "tc":
             call("tn_mlp_tc_bwd", ptr(x), ptr(_f32c(dy)), ptr(mask), n, in_dim, x_stride, width, out_dim, nl,
-                 ptr_array(ws), ptr_array(bs), ctx.out_act, ptr(dx), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+                 ptr_array(ws), ptr_array(bs), ctx.out_act, ptr(row_mul), ctx.out_scale, ptr(dx), ptr_array(dws),
+                 ptr_array(dbs), stream(), tag=tag)
         else:
             xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
             dxd = dx if x_stride == in_dim or dx is None else torch.empty_like(xd)
@@ -222,18 +226,26 @@ class _MlpFn(torch.autograd.Function):
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [None, None] if sinks is not None else [dw, db]
-        return (dx, None, None, *grads)
+        return (dx, None, None, None, None, *grads)
 
 
-def mlp(x: Tensor, weights: List[Tensor], biases: List[Tensor], out_act: int = ACT_NONE, sinks=None) -> Tensor:
+def mlp(x: Tensor, weights: List[Tensor], biases: List[Tensor], out_act: int = ACT_NONE, sinks=None,
+        row_mul: Optional[Tensor] = None, out_scale: float = 1.0) -> Tensor:
     """Fully fused MLP (ReLU hidden activations).  field_components/mlp.py:159-178.
 
     sinks: optional [(dW_i, db_i)] float32 tensors the backward kernel accumulates INTO (the parameters' slices of
-    a FlatGradBuffer); autograd then receives no weight gradients."""
+    a FlatGradBuffer); autograd then receives no weight gradients.
+    row_mul [N] / out_scale: the activated output rows are multiplied by out_scale * row_mul (no gradient to
+    row_mul) -- the density epilogue `average_init_density * trunc_exp(.) * selector` of the fields."""
     wb = []
     for w, b in zip(weights, biases):
         wb += [w, b]
-    return _MlpFn.apply(x, out_act, sinks, *wb)
+    if MLP_BACKEND["fwd"] == "tc" and MLP_BACKEND["bwd"] == "tc":
+        return _MlpFn.apply(x, out_act, sinks, row_mul, out_scale, *wb)
+    y = _MlpFn.apply(x, out_act, sinks, None, 1.0, *wb)
+    if row_mul is not None:
+        y = y * row_mul.detach().view(-1, 1)
+    return y if out_scale == 1.0 else y * out_scale
 
 
 def mlp_shape_supported(in_dim: int, width: int, out_dim: int, n_layers: int) -> bool:

@@ -196,3 +196,33 @@ def test_full_size_batch_equals_oracle_on_a_slice(mode, rays):
     for k in keys:
         assert max_abs(out[k][sl.to(DEV)], ref[k]) <= 1e-3, (k, max_abs(out[k][sl.to(DEV)], ref[k]))
     assert out["rgb"].shape == (rays, 3) and torch.isfinite(out["rgb"]).all()
+
+
+def test_density_only_path_equals_get_density(golden):
+    """NerfactoField.get_density_only (1-row last layer, trunc_exp * selector as the MLP epilogue) == get_density()[0],
+    values and every gradient (table, MLP weights, ray origins through the positions)."""
+    g, model = build(golden, "separate")
+    model.train()
+    b = bundle(g)
+    b = model.collider(b)
+    b.origins = b.origins.clone().requires_grad_(True)
+    rs, _, _ = model.proposal_sampler(b, density_fns=model.density_fns, jitters=[g[f"jitter{i}"].to(DEV) for i in range(3)])
+    w = torch.randn(rs.frustums.shape + (1,), device=DEV)
+    outs = []
+    for fn in (lambda: model.field.get_density(rs)[0], lambda: model.field.get_density_only(rs)):
+        model.zero_grad(set_to_none=True)
+        b.origins.grad = None
+        d = fn()
+        (d * w).sum().backward()
+        grads = {k: p.grad.clone() for k, p in model.field.named_parameters() if p.grad is not None}
+        outs.append((d.detach(), b.origins.grad.clone(), grads))
+    (d0, o0, g0), (d1, o1, g1) = outs
+    torch.testing.assert_close(d1, d0, rtol=1e-5, atol=1e-6)
+    keys = [k for k in g0 if g0[k].abs().max() > 0]
+    assert set(g1) >= set(keys) and len(keys) >= 5  # table + two layers' weights and biases
+    for k in keys:
+        a, c = g0[k], g1[k]  # rows 1..15 of the last layer are zero in both: only row 0 carries the density
+        rel = ((a - c).double().norm() / (a.double().norm() + 1e-30)).item()
+        assert rel <= 2e-4, (k, rel)
+    rel = ((o0 - o1).double().norm() / (o0.double().norm() + 1e-30)).item()
+    assert rel <= 2e-4, rel
