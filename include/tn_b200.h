@@ -45,15 +45,19 @@ const char* tn_build_arch(void);          /* "sm_100a" */
  * table_dtype: 0 = float32, 1 = float16 (derived cache of the fp32 parameter; out stays float32).
  * idx_out: NULL, or int32[N,L,8] receiving the eight table rows per (point, level) in the reference's
  *   corner order hashed_0..hashed_7 (encodings.py:431-438) -- the bit-exactness test hook.
+ * jac_out: NULL, or float32[L, N, F, 3] receiving d out[n, l*F+f] / d x[n, :] (exclusive with idx_out): handed
+ *   back to tn_hash_encode_bwd it saves the backward its second gather of the corner rows.
  * ------------------------------------------------------------------------------------------------ */
 int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                       int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, void* stream);
+                       int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, float* jac_out,
+                       void* stream);
 
 /* dy[N, L*F].  dtable[L*T, F] float32 is ACCUMULATED into (caller zero-fills for a fresh gradient).
- * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; needs `table`. */
+ * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; computed from `jac` (the
+ * forward's jac_out) when given, else by gathering the corner rows of `table` again. */
 int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
                        const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
-                       void* stream);
+                       const float* jac, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sample positions -> normalised grid coordinates.

@@ -28,10 +28,13 @@ __device__ __forceinline__ int tile_pos(int row, int l, int L, int F) {
 
 constexpr int kLevelBatch = 2;  // levels whose 8-corner gathers are issued back to back (16 loads in flight/thread)
 
-template <int F, bool HALF, bool WRITE_IDX>
+// JAC: also store d(feature)/d(x) (times the level scale) as jac[L][N][F][3].  The backward then needs no second
+// gather of the corner rows for dL/dx: 12*F bytes/level of streaming instead of 8 L2 gathers/level.
+template <int F, bool HALF, bool WRITE_IDX, bool JAC = false>
 __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
                                                            LevelScales sc, int64_t N, int L, int log2T,
-                                                           float* __restrict__ out, int32_t* __restrict__ idx_out) {
+                                                           float* __restrict__ out, int32_t* __restrict__ idx_out,
+                                                           float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   __shared__ float s_scale[TN_MAX_LEVELS];
   float* tile = reinterpret_cast<float*>(smem4);
@@ -87,6 +90,17 @@ __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restri
           const float f0312 = f03 * oy + f12 * my;
           const float f4756 = f47 * oy + f56 * my;
           dst[j] = f0312 * oz + f4756 * mz;
+          if constexpr (JAC) {
+            if (valid) {
+              const float sl = s_scale[l];
+              const float e03 = f[b][0][j] - f[b][3][j], e12 = f[b][1][j] - f[b][2][j];
+              const float e56 = f[b][5][j] - f[b][6][j], e47 = f[b][4][j] - f[b][7][j];
+              float* jd = jac + ((size_t)l * N + p) * (F * 3) + j * 3;
+              jd[0] = ((e03 * oy + e12 * my) * oz + (e47 * oy + e56 * my) * mz) * sl;
+              jd[1] = ((f03 - f12) * oz + (f47 - f56) * mz) * sl;
+              jd[2] = (f0312 - f4756) * sl;
+            }
+          }
         }
       }
     }
@@ -110,11 +124,11 @@ __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restri
   }
 }
 
-template <int F, bool HALF, bool NEED_DX>
+template <int F, bool HALF, bool NEED_DX, bool JAC = false>
 __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
                                                         LevelScales sc, const float* __restrict__ dy, int64_t N, int L,
                                                         int log2T, int n_coarse, float* __restrict__ dtable,
-                                                        float* __restrict__ dx) {
+                                                        float* __restrict__ dx, const float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   float* tile = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -160,7 +174,12 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
     const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
     float gc[8][F];
     float f[8][F];
-    if constexpr (NEED_DX) {
+    float jv[F * 3];
+    if constexpr (NEED_DX && JAC) {  // the forward's Jacobian of this level: one coalesced 12*F-byte read
+      const float* js = jac + ((size_t)l * N + (valid ? p : 0)) * (F * 3);
+#pragma unroll
+      for (int q = 0; q < F * 3; ++q) jv[q] = __ldg(js + q);
+    } else if constexpr (NEED_DX) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
     }
@@ -174,7 +193,9 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
       gc[1][j] = g12 * c.ox; gc[2][j] = g12 * mx;
       gc[5][j] = g56 * c.ox; gc[6][j] = g56 * mx;
       gc[4][j] = g47 * c.ox; gc[7][j] = g47 * mx;
-      if constexpr (NEED_DX) {
+      if constexpr (NEED_DX && JAC) {
+        dox += g[j] * jv[j * 3]; doy += g[j] * jv[j * 3 + 1]; doz += g[j] * jv[j * 3 + 2];
+      } else if constexpr (NEED_DX) {
         const float f03 = f[0][j] * c.ox + f[3][j] * mx;
         const float f12 = f[1][j] * c.ox + f[2][j] * mx;
         const float f56 = f[5][j] * c.ox + f[6][j] * mx;
@@ -187,7 +208,9 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
         doz += g[j] * (f0312 - f4756);
       }
     }
-    if constexpr (NEED_DX) {
+    if constexpr (NEED_DX && JAC) {
+      dx0 += dox; dx1 += doy; dx2 += doz;  // the stored Jacobian carries the level scale
+    } else if constexpr (NEED_DX) {
       dx0 += dox * scale; dx1 += doy * scale; dx2 += doz * scale;
     }
     bool issue = valid;
@@ -240,16 +263,20 @@ static int check_common(const float* x, const void* table, const float* scales_h
 
 template <int F>
 static int launch_fwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, int64_t N, int L,
-                      int log2_T, float* out, int32_t* idx_out, cudaStream_t st) {
+                      int log2_T, float* out, int32_t* idx_out, float* jac, cudaStream_t st) {
   const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
   const size_t smem = (size_t)kPts * L * F * sizeof(float);
 #define TN_FWD(H, W)                                                                                         \
   do {                                                                                                       \
     auto k = hash_fwd_kernel<F, H, W>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, idx_out);                                    \
+    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, idx_out, jac);                               \
   } while (0)
-  if (table_dtype == 0) {
+  if (jac) {  // (no index dump on this path: checked by the caller)
+    auto k = table_dtype == 0 ? hash_fwd_kernel<F, false, false, true> : hash_fwd_kernel<F, true, false, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, nullptr, jac);
+  } else if (table_dtype == 0) {
     if (idx_out) TN_FWD(false, true); else TN_FWD(false, false);
   } else {
     if (idx_out) TN_FWD(true, true); else TN_FWD(true, false);
@@ -260,16 +287,21 @@ static int launch_fwd(const float* x, const void* table, int table_dtype, const 
 
 template <int F>
 static int launch_bwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, const float* dy,
-                      int64_t N, int L, int log2_T, int n_coarse, float* dtable, float* dx, cudaStream_t st) {
+                      int64_t N, int L, int log2_T, int n_coarse, float* dtable, float* dx, const float* jac,
+                      cudaStream_t st) {
   const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
   const size_t smem = (size_t)kPts * L * F * sizeof(float);
 #define TN_BWD(H, D)                                                                                         \
   do {                                                                                                       \
     auto k = hash_bwd_kernel<F, H, D>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx);                        \
+    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac);                   \
   } while (0)
-  if (table_dtype == 0) {
+  if (jac && dx) {
+    auto k = table_dtype == 0 ? hash_bwd_kernel<F, false, true, true> : hash_bwd_kernel<F, true, true, true>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac);
+  } else if (table_dtype == 0) {
     if (dx) TN_BWD(false, true); else TN_BWD(false, false);
   } else {
     if (dx) TN_BWD(true, true); else TN_BWD(true, false);
@@ -283,27 +315,29 @@ static int launch_bwd(const float* x, const void* table, int table_dtype, const 
 using namespace tn;
 
 extern "C" int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                                  int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, void* stream) {
+                                  int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, float* jac_out,
+                                  void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
   TN_REQUIRE(out || N == 0, TN_EINVAL, "hash_encode_fwd: out is null");
   TN_REQUIRE(aligned(out, 16), TN_EALIGN, "hash_encode_fwd: out must be 16-byte aligned");
   TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_fwd: L*F=%d too large", L * F);
+  TN_REQUIRE(!(jac_out && idx_out), TN_EINVAL, "hash_encode_fwd: idx_out and jac_out are exclusive");
   if (N == 0) return TN_OK;
   LevelScales sc;
   for (int l = 0; l < TN_MAX_LEVELS; ++l) sc.s[l] = l < L ? scales_host[l] : 0.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (F) {
-    case 1: return launch_fwd<1>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
-    case 2: return launch_fwd<2>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
-    case 4: return launch_fwd<4>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
-    default: return launch_fwd<8>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, st);
+    case 1: return launch_fwd<1>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
+    case 2: return launch_fwd<2>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
+    case 4: return launch_fwd<4>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
+    default: return launch_fwd<8>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
   }
 }
 
 extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
                                   const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
-                                  void* stream) {
+                                  const float* jac, void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
   TN_REQUIRE((dy || N == 0) && dtable, TN_EINVAL, "hash_encode_bwd: null pointer");
@@ -319,9 +353,9 @@ extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_d
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (F) {
-    case 1: return launch_bwd<1>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
-    case 2: return launch_bwd<2>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
-    case 4: return launch_bwd<4>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
-    default: return launch_bwd<8>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, st);
+    case 1: return launch_bwd<1>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
+    case 2: return launch_bwd<2>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
+    case 4: return launch_bwd<4>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
+    default: return launch_bwd<8>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
   }
 }

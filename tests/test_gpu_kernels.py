@@ -361,3 +361,24 @@ def test_weights_edge_cases():
         want = osamp.sample_weights(dl[..., None], sig[..., None])[..., 0]
         got = ops.sample_weights(sig.to(DEV), dl.to(DEV))
         close(got, want, 1e-6, 1e-5)
+
+
+def test_hash_encode_saved_jacobian_path_equals_regather(monkeypatch):
+    """tn_hash_encode_fwd(jac_out) + tn_hash_encode_bwd(jac) give the same dL/dx and table gradient as the default
+    backward that gathers the corner rows again."""
+    from nerfstudio_thermal_b200 import ops
+    torch.manual_seed(3)
+    spec = ops.HashGridSpec(oracle.hash_scalings(16, 16, 2048).tolist(), 2, 12)
+    table = (torch.rand(spec.rows, 2, device="cuda") - 0.5).requires_grad_(True)
+    x = torch.rand(777, 3, device="cuda").requires_grad_(True)
+    gy = torch.randn(777, 32, device="cuda")
+    res = []
+    for flag in (False, True):
+        monkeypatch.setattr(ops, "SAVE_JACOBIAN", flag)
+        table.grad = x.grad = None
+        y = ops.hash_encode(x, table, spec)
+        (y * gy).sum().backward()
+        res.append((y.detach(), x.grad.clone(), table.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    torch.testing.assert_close(res[1][1], res[0][1], rtol=1e-4, atol=1e-4 * res[0][1].abs().max().item())
+    torch.testing.assert_close(res[1][2], res[0][2], rtol=1e-5, atol=1e-6)
