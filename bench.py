@@ -290,6 +290,17 @@ def run_render(args):
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         times[name] = ms.item() / steps
+    if args.profile_kernels and rank == 0:
+        from nerfstudio_thermal_b200 import _lib
+        _lib.STATS.reset(timing=True)
+        render_all(False)
+        torch.cuda.synchronize()
+        table = _lib.STATS.summary()
+        _lib.STATS.reset()
+        for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+            print(f"{k:58s} {n:6d} launches/step {ms:8.3f} ms/step", file=sys.stderr)
+        print(f"sum of libtn_b200 kernels {sum(ms for _, ms in table.values()):.3f} ms/step; step {times['value']:.3f} ms",
+              file=sys.stderr)
     if rank == 0:
         out_bytes = sum({"rgb": 12, "rgb_thermal": 4}.get(k, 4) for k in keys) * total_rays
         line = {
