@@ -287,6 +287,28 @@ int tn_loss_sum(const float* const* term_host_ptrs, const float* scale_host, con
                 int n_slots, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The step before the path, on the device: patch pixel sampling, collation, ray generation.
+ * ------------------------------------------------------------------------------------------------ */
+/* replaces: data/pixel_samplers.py:417-438 (PatchPixelSampler.sample_method, no mask).  u[num_patches,3] = the
+ * reference's torch.rand draw (device); indices_out int64[num_patches*patch^2, 3] = (image, row, column). */
+int tn_patch_pixel_indices(const float* u, int64_t num_patches, int patch_size, int num_images, int image_height,
+                           int image_width, int64_t* indices_out, void* stream);
+/* replaces: data/pixel_samplers.py:239-256 (collate_image_dataset_batch, without the CPU index round trip).
+ * images[num_images,H,W,channels] float32 (pixel_dtype 0) or uint8 (1, divided by 255); indices int64[R,3] (column
+ * 0 is REWRITTEN with image_idx[c] when image_idx is non-NULL); image_out[R,channels];
+ * is_thermal_out[R] = is_thermal_per_image[c] (either may be NULL). */
+int tn_gather_pixels(const void* images, int pixel_dtype, int64_t num_images, int image_height, int image_width,
+                     int channels, int64_t* indices, const int64_t* image_idx, const float* is_thermal_per_image,
+                     int64_t R, float* image_out, float* is_thermal_out, void* stream);
+/* replaces: model_components/ray_generators.py:40-55 + cameras/cameras.py:504-905 for undistorted PERSPECTIVE
+ * cameras.  ray_indices int64[R,3] = (camera, row, column); camera_to_worlds[num_cameras,3,4]; intrinsics
+ * [num_cameras,4] = (fx, fy, cx, cy).  Outputs: origins[R,3], directions[R,3] (unit), pixel_area[R],
+ * directions_norm[R] (NULL ok), camera_indices int64[R] (NULL ok). */
+int tn_generate_rays(const int64_t* ray_indices, const float* camera_to_worlds, const float* intrinsics,
+                     int64_t num_cameras, int64_t R, float* origins_out, float* directions_out,
+                     float* pixel_area_out, float* directions_norm_out, int64_t* camera_indices_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimiser step over the flat buffers.
  * ------------------------------------------------------------------------------------------------ */
 #define TN_ADAM_MAX_GROUPS 16

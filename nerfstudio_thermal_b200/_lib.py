@@ -68,6 +68,9 @@ _SIGNATURES = {
     "tn_camera_reg_fwd": [_P, c_int, c_float, c_float, c_float, _P, _P],
     "tn_camera_reg_bwd": [_P, _P, c_int, c_float, c_float, c_float, _P, _P],
     "tn_loss_sum": [_FPP, POINTER(c_float), POINTER(c_int), c_int, c_int, _P, _P],
+    "tn_patch_pixel_indices": [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P],
+    "tn_gather_pixels": [_P, c_int, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P, _P, _P],
+    "tn_generate_rays": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P],
     "tn_adam_step": [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_float), c_int, c_double,
                      c_double, _P, c_int, _P, _P, c_int, _P],
     "tn_grad_unscale_check": [_P, c_int64, _P, _P, _P],

@@ -119,6 +119,92 @@ __global__ void piecewise_bins_kernel(const float* __restrict__ unit, const floa
   ebins[i] = spacing_inv(b * sf + (1.f - b) * sn);  // :115-116
 }
 
+
+// ------------------------------------------------------------------------------------------------ ray generation (8f-3)
+// PatchPixelSampler.sample_method without a mask (data/pixel_samplers.py:417-438): patch p, pixel (yy, xx) ->
+// (floor(u0*num_images), floor(u1*(H-patch) + yy), floor(u2*(W-patch) + xx)); fp32 products as in the reference.
+__global__ void patch_indices_kernel(const float* __restrict__ u, int64_t P, int patch, int num_images, int H, int W,
+                                     int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int pp = patch * patch;
+  if (i >= P * pp) return;
+  const int64_t p = i / pp;
+  const int k = (int)(i - p * pp), yy = k / patch, xx = k - yy * patch;
+  const float c = __ldg(u + 3 * p) * (float)num_images;
+  const float y = __ldg(u + 3 * p + 1) * (float)(H - patch) + (float)yy;
+  const float x = __ldg(u + 3 * p + 2) * (float)(W - patch) + (float)xx;
+  out[3 * i] = (int64_t)floorf(c);
+  out[3 * i + 1] = (int64_t)floorf(y);
+  out[3 * i + 2] = (int64_t)floorf(x);
+}
+
+// collate (pixel_samplers.py:239-256): image[r] = images[c, y, x, :], is_thermal[r] = is_thermal_per_image[c],
+// indices[r, 0] = image_idx[c]
+template <typename PIX>
+__global__ void gather_pixels_kernel(const PIX* __restrict__ images, int64_t n_img, int H, int W, int C,
+                                     int64_t* __restrict__ indices, const int64_t* __restrict__ image_idx,
+                                     const float* __restrict__ thermal_per_image, int64_t R, float* __restrict__ image_out,
+                                     float* __restrict__ thermal_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t c = indices[3 * r], y = indices[3 * r + 1], x = indices[3 * r + 2];
+  const PIX* src = images + ((c * H + y) * W + x) * C;
+  for (int k = 0; k < C; ++k) {
+    if constexpr (sizeof(PIX) == 1) image_out[r * C + k] = (float)src[k] / 255.0f;
+    else image_out[r * C + k] = (float)src[k];
+  }
+  if (thermal_out) thermal_out[r] = thermal_per_image ? __ldg(thermal_per_image + c) : 0.f;
+  if (image_idx) indices[3 * r] = __ldg(image_idx + c);
+}
+
+// RayGenerator.forward + Cameras._generate_rays_from_coords for undistorted PERSPECTIVE cameras
+// (model_components/ray_generators.py:40-55, cameras/cameras.py:504-905): pixel centre (y+0.5, x+0.5),
+// camera-space directions for the pixel and its +1 x / +1 y neighbours, rotation by c2w, normalisation
+// (camera_utils.py:286-298), pixel_area = |d - d_x| * |d - d_y|.
+__global__ void generate_rays_kernel(const int64_t* __restrict__ indices, const float* __restrict__ c2w,
+                                     const float* __restrict__ intr, int64_t R, float* __restrict__ origins,
+                                     float* __restrict__ directions, float* __restrict__ pixel_area,
+                                     float* __restrict__ dir_norm, int64_t* __restrict__ cam_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t c = indices[3 * r];
+  const float y = (float)indices[3 * r + 1] + 0.5f, x = (float)indices[3 * r + 2] + 0.5f;
+  const float fx = __ldg(intr + 4 * c), fy = __ldg(intr + 4 * c + 1), cx = __ldg(intr + 4 * c + 2),
+              cy = __ldg(intr + 4 * c + 3);
+  const float* m = c2w + 12 * c;  // [3,4] row-major
+  const float eps = 8.881784197001252e-16f;  // np.finfo(float).eps * 4
+  // the three image-plane points; the y axis flips from OpenCV to OpenGL (cameras.py:654)
+  const float px[3] = {(x - cx) / fx, (x - cx + 1.f) / fx, (x - cx) / fx};
+  const float py[3] = {-((y - cy) / fy), -((y - cy) / fy), -((y - cy + 1.f) / fy)};
+  float d[3][3];
+  float n0 = 0.f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    float v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = (px[q] * m[4 * i] + py[q] * m[4 * i + 1]) + (-1.f) * m[4 * i + 2];
+    const float nrm = fmaxf(sqrtf((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]), eps);
+    if (q == 0) n0 = nrm;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d[q][i] = v[i] / nrm;
+  }
+  float dx2 = 0.f, dy2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a = d[0][i] - d[1][i], b = d[0][i] - d[2][i];
+    dx2 += a * a;
+    dy2 += b * b;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    origins[3 * r + i] = m[4 * i + 3];
+    directions[3 * r + i] = d[0][i];
+  }
+  pixel_area[r] = sqrtf(dx2) * sqrtf(dy2);
+  if (dir_norm) dir_norm[r] = n0;
+  if (cam_out) cam_out[r] = c;
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -178,4 +264,51 @@ extern "C" int tn_piecewise_bins(const float* unit_bins, const float* nears, con
   piecewise_bins_kernel<<<blocks_for(R * (S + 1), 256), 256, 0, (cudaStream_t)stream>>>(
       unit_bins, nears, fars, jitter, jitter_per_sample, R, S, sbins_out, ebins_out);
   return check_launch("piecewise_bins_kernel");
+}
+
+extern "C" int tn_patch_pixel_indices(const float* u, int64_t num_patches, int patch_size, int num_images,
+                                      int image_height, int image_width, int64_t* indices_out, void* stream) {
+  TN_REQUIRE(num_patches >= 0 && patch_size >= 1 && num_images >= 1 && image_height >= patch_size &&
+                 image_width >= patch_size, TN_EINVAL, "patch_pixel_indices: bad sizes");
+  if (num_patches == 0) return TN_OK;
+  TN_REQUIRE(u && indices_out, TN_EINVAL, "patch_pixel_indices: null pointer");
+  const int64_t n = num_patches * patch_size * patch_size;
+  patch_indices_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(u, num_patches, patch_size, num_images,
+                                                                           image_height, image_width, indices_out);
+  return check_launch("patch_indices_kernel");
+}
+
+extern "C" int tn_gather_pixels(const void* images, int pixel_dtype, int64_t num_images, int image_height,
+                                int image_width, int channels, int64_t* indices, const int64_t* image_idx,
+                                const float* is_thermal_per_image, int64_t R, float* image_out, float* is_thermal_out,
+                                void* stream) {
+  TN_REQUIRE(R >= 0 && num_images >= 1 && image_height >= 1 && image_width >= 1 && channels >= 1 && channels <= 4,
+             TN_EINVAL, "gather_pixels: bad sizes");
+  TN_REQUIRE(pixel_dtype == 0 || pixel_dtype == 1, TN_EINVAL, "gather_pixels: pixel_dtype=%d (0 float32, 1 uint8)",
+             pixel_dtype);
+  if (R == 0) return TN_OK;
+  TN_REQUIRE(images && indices && image_out, TN_EINVAL, "gather_pixels: null pointer");
+  if (pixel_dtype == 0)
+    gather_pixels_kernel<float><<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const float*)images, num_images, image_height, image_width, channels, indices, image_idx,
+        is_thermal_per_image, R, image_out, is_thermal_out);
+  else
+    gather_pixels_kernel<uint8_t><<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint8_t*)images, num_images, image_height, image_width, channels, indices, image_idx,
+        is_thermal_per_image, R, image_out, is_thermal_out);
+  return check_launch("gather_pixels_kernel");
+}
+
+extern "C" int tn_generate_rays(const int64_t* ray_indices, const float* camera_to_worlds, const float* intrinsics,
+                                int64_t num_cameras, int64_t R, float* origins_out, float* directions_out,
+                                float* pixel_area_out, float* directions_norm_out, int64_t* camera_indices_out,
+                                void* stream) {
+  TN_REQUIRE(R >= 0 && num_cameras >= 1, TN_EINVAL, "generate_rays: bad sizes");
+  if (R == 0) return TN_OK;
+  TN_REQUIRE(ray_indices && camera_to_worlds && intrinsics && origins_out && directions_out && pixel_area_out,
+             TN_EINVAL, "generate_rays: null pointer");
+  generate_rays_kernel<<<blocks_for(R, 256), 256, 0, (cudaStream_t)stream>>>(
+      ray_indices, camera_to_worlds, intrinsics, R, origins_out, directions_out, pixel_area_out, directions_norm_out,
+      camera_indices_out);
+  return check_launch("generate_rays_kernel");
 }

@@ -27,6 +27,22 @@ from .rays import RayBundle
 BATCH_KEYS = ("origins", "directions", "pixel_area", "camera_indices", "image", "is_thermal")
 
 
+class DeviceBatchSource:
+    """A train batch made on the device: PatchPixelSampler over the cached images in HBM + RayGenerator.
+    Given to GraphedTrainStep as `source=`, the sampling and the ray generation are captured in the step's CUDA
+    graph (torch.rand draws from the graph-registered Philox state), so a step has no host input at all.
+    Mirrors VanillaDataManager.next_train (data/datamanagers/base_datamanager.py:  pixel sampler -> ray generator)."""
+
+    def __init__(self, sampler, ray_generator, image_batch: Dict[str, Tensor]):
+        self.sampler, self.ray_generator, self.image_batch = sampler, ray_generator, image_batch
+
+    def next(self) -> Dict[str, Tensor]:
+        b = self.sampler.sample(self.image_batch)
+        rays = self.ray_generator(b["indices"])
+        return {"origins": rays.origins, "directions": rays.directions, "pixel_area": rays.pixel_area,
+                "camera_indices": rays.camera_indices, "image": b["image"], "is_thermal": b["is_thermal"]}
+
+
 class GraphedTrainStep:
     """forward + metrics + loss dict + backward (+ flat gradient all-reduce) for a fixed batch shape.
 
@@ -37,8 +53,9 @@ class GraphedTrainStep:
 
     def __init__(self, model: ThermalNerfactoModel, example_batch: Dict[str, Tensor], use_graph: bool = True,
                  warmup: int = 3, group=None, optimizer: Optional[Dict[str, AdamGroupConfig]] = None,
-                 overlap_comm: Optional[bool] = None):
+                 overlap_comm: Optional[bool] = None, source: Optional[DeviceBatchSource] = None):
         self.model = model
+        self.source = source  # batches come from the device-side sampler / ray generator instead of step(batch)
         self.device = model.device
         assert self.device.type == "cuda", "the hot path runs on CUDA only (no CPU fallback)"
         self.group = group
@@ -94,7 +111,7 @@ class GraphedTrainStep:
             self.static[k].copy_(batch[k], non_blocking=True)
 
     def _eager(self, apply_optimizer: bool = True, captured: bool = False) -> None:
-        s = self.static
+        s = self.static if self.source is None else self.source.next()
         if not (captured and self._adam_in_graph):  # the in-graph Adam pass leaves the gradients cleared
             self.grads.zero_()
         bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
