@@ -222,3 +222,31 @@ def test_flat_gradient_allreduce_gloo_world2():
         results = mgr.dict()
         mp.spawn(_ddp_worker, args=(world, port, results), nprocs=world, join=True)
         assert dict(results) == {0: "ok", 1: "ok"}
+
+
+def test_reference_checkpoint_round_trip(golden):
+    """a dict in the format of Trainer.save_checkpoint (with the pipeline's "_model." prefix, and DDP's
+    "module.") loads strict=True; what save_checkpoint writes loads back and carries the reference's key set."""
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import checkpoint
+    g = golden("model_separate.npz")
+    props = [{"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 128, "use_linear": False},
+             {"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": 256, "use_linear": False}]
+    cfg = tn.ThermalNerfactoModelConfig(density_mode="separate", log2_hashmap_size=9, proposal_net_args_list=props)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    sd["device_indicator_param"] = torch.empty(0)
+    for prefix in ("_model.", "_model.module.", "module._model."):
+        model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+        ckpt = {"step": 1234, "pipeline": {prefix + k: v for k, v in sd.items()}, "optimizers": {}, "scalers": {}}
+        ckpt["pipeline"]["datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(8, 6)  # non-model key
+        assert checkpoint.load_checkpoint(ckpt, model) == 1235
+        assert model.step == 1234
+        for k, v in model.state_dict().items():
+            assert torch.equal(v, sd[k]), k
+    out = checkpoint.save_checkpoint(1234, model)
+    assert set(out) == {"step", "pipeline", "optimizers", "schedulers", "scalers"}
+    assert set(out["pipeline"]) == {"_model." + k for k in sd}
+    model2 = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+    checkpoint.load_checkpoint(out, model2)
+    for k, v in model2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
