@@ -222,6 +222,20 @@ class ProposalNetworkSampler(Sampler):
             return owner.get_density(ray_samples)[0]
         return density_fn(ray_samples.frustums.get_positions())
 
+    def draw_jitters(self, num_rays: int, device) -> Optional[List[Optional[Tensor]]]:
+        """The stratification draws generate_ray_samples would make, in its order (one per level), so that a caller
+        can fix the random stream before reordering or overlapping the work that consumes it."""
+        out: List[Optional[Tensor]] = []
+        n = self.num_proposal_network_iterations
+        for i_level in range(n + 1):
+            s = self.num_proposal_samples_per_ray[i_level] if i_level < n else self.num_nerf_samples_per_ray
+            smp = self.initial_sampler if i_level == 0 else self.pdf_sampler
+            if not (smp.train_stratified and smp.training):
+                out.append(None)
+            else:
+                out.append(torch.rand((num_rays, 1 if smp.single_jitter else s + 1), dtype=torch.float32, device=device))
+        return None if all(j is None for j in out) else out
+
     def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None,
                              density_fns: Optional[List[Callable]] = None,
                              jitters: Optional[List[Tensor]] = None) -> Tuple[RaySamples, List, List]:

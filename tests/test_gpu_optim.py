@@ -204,3 +204,24 @@ def test_train_step_with_fused_optimizer(golden, use_graph):
         sel = g2.abs() > 1e-7
         if sel.any():
             torch.testing.assert_close(p3[k].detach()[sel], p2[k].detach()[sel], rtol=1e-4, atol=2e-5)
+
+
+def test_two_stream_branches_give_the_same_gradients_in_a_captured_step(golden):
+    """The thermal branch on a second stream (model.branch_streams: parallel arms of the captured graph, forward and
+    backward) must not change anything: same seed -> same jitter draws -> same losses and gradients as one stream."""
+    from nerfstudio_thermal_b200 import engine
+    res = []
+    for two in (False, True):
+        tn, model, batch = _small_model_and_batch(golden)
+        model.branch_streams = two
+        torch.manual_seed(77)
+        runner = engine.GraphedTrainStep(model, batch, use_graph=True)
+        for _ in range(3):
+            total = runner.step(batch)
+        res.append((float(total.detach()), runner.grads.flat.clone(), {k: float(v.detach()) for k, v in runner.losses.items()}))
+    (t0, g0, l0), (t1, g1, l1) = res
+    assert l0.keys() == l1.keys()
+    for k in l0:
+        assert l1[k] == pytest.approx(l0[k], rel=1e-5, abs=1e-9), k
+    rel = ((g0 - g1).double().norm() / g0.double().norm()).item()
+    assert rel <= 1e-5, rel
