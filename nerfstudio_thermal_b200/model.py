@@ -482,8 +482,17 @@ class ThermalNerfactoModel(nn.Module):
             if c.density_loss_mult > 0 or not self.training:
                 # cross-field densities for the density regulariser (:447-458).  The reference runs the full
                 # field forward here and throws the colour away; only the density is evaluated.
-                outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
-                outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
+                if thermal_done is not None and os.environ.get("TN_CROSS_STREAMS", "1") == "1":
+                    # the two cross-field evaluations are independent of each other as well
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
+                    outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
+                    main.wait_stream(side)
+                    outputs["density2_thermal"].record_stream(main)
+                else:
+                    outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
+                    outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
 
             if not self.training:
                 # "removal" renders (:460-487).  The reference recomputes both field forwards on the very same
