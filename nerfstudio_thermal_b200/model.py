@@ -430,34 +430,30 @@ class ThermalNerfactoModel(nn.Module):
                                        pixel_area=ray_bundle.pixel_area, camera_indices=ray_bundle.camera_indices,
                                        nears=ray_bundle.nears, fars=ray_bundle.fars, metadata=ray_bundle.metadata,
                                        times=ray_bundle.times)
-        # The RGB and the thermal branch are independent until the cross-field terms.  Most of their kernels are
-        # latency- or issue-bound and leave SMs idle, so on CUDA the thermal branch is issued on a second stream: in
-        # the captured train step the two branches (and, through autograd's stream tracking, their backwards) become
-        # parallel arms of the graph.  The jitter draws are made first, in the reference's order.
-        # (training only: the eager chunk loop of a render is GPU-bound per kernel and measured 4 % slower with it)
-        two_streams = (self.branch_streams and self.training and c.density_mode == "separate"
-                       and ray_bundle.origins.is_cuda)
-        thermal_done = None
-        if two_streams:
-            dev = ray_bundle.origins.device
-            if jitters is None:
-                jitters = self.proposal_sampler.draw_jitters(ray_bundle.origins.shape[0], dev)
-            if jitters_thermal is None:
-                jitters_thermal = self.proposal_sampler_thermal.draw_jitters(ray_bundle.origins.shape[0], dev)
-            main = torch.cuda.current_stream(dev)
-            if self._side_stream is None or self._side_stream.device != dev:
-                self._side_stream = torch.cuda.Stream(device=dev)
-            side = self._side_stream
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                thermal_done = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
-        self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
-        if self.training:
-            self.camera_optimizer.apply_to_raybundle(ray_bundle)
-        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
-                                                                            jitters=jitters)
+        separate = c.density_mode == "separate"
+        want_cross = separate and (c.density_loss_mult > 0 or not self.training)
         renderer_rgb = self.renderer_rgbt if c.density_mode == "shared" else self.renderer_rgb
-        outputs = self._get_outputs(ray_bundle, self.field, renderer_rgb, ray_samples, weights_list, ray_samples_list)
+        if self.branch_streams and self.training and separate and ray_bundle.origins.is_cuda:
+            outputs, thermal_outputs, ray_samples, ray_samples_thermal, cross = self._branches_on_streams(
+                ray_bundle, ray_bundle_thermal, jitters, jitters_thermal, want_cross)
+        else:
+            self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
+            if self.training:
+                self.camera_optimizer.apply_to_raybundle(ray_bundle)
+            ray_samples, weights_list, ray_samples_list = self.proposal_sampler(
+                ray_bundle, density_fns=self.density_fns, jitters=jitters)
+            outputs = self._get_outputs(ray_bundle, self.field, renderer_rgb, ray_samples, weights_list,
+                                        ray_samples_list)
+            thermal_outputs = ray_samples_thermal = cross = None
+            if separate:
+                ray_samples_thermal, wl_t, rsl_t = self._thermal_samples(ray_bundle_thermal, jitters_thermal)
+                thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
+                                                    ray_samples_thermal, wl_t, rsl_t)
+                if want_cross:
+                    # cross-field densities for the density regulariser (:447-458).  The reference runs the full
+                    # field forward here and throws the colour away; only the density is evaluated.
+                    cross = (self.field.get_density_only(ray_samples_thermal),
+                             self.field_thermal.get_density_only(ray_samples))
         field_rgb = outputs.pop("_field_rgb")
 
         if c.density_mode == "shared":
@@ -465,34 +461,12 @@ class ThermalNerfactoModel(nn.Module):
             outputs["rgbt"] = rgbt
             outputs["rgb"] = rgbt[..., :3]
             outputs["rgb_thermal"] = rgbt[..., 3:]
-        elif c.density_mode == "separate":
-            if thermal_done is not None:
-                main.wait_stream(side)
-                thermal_outputs, ray_samples_thermal = thermal_done
-                for v in list(thermal_outputs.values()) + [ray_samples_thermal._layout.ebins,
-                                                           ray_samples_thermal._layout.sbins]:
-                    if torch.is_tensor(v):
-                        v.record_stream(main)
-            else:
-                thermal_outputs, ray_samples_thermal = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
+        elif separate:
             field_rgb_thermal = thermal_outputs.pop("_field_rgb")
             for k, v in thermal_outputs.items():
                 outputs[f"{k}_thermal"] = v
-
-            if c.density_loss_mult > 0 or not self.training:
-                # cross-field densities for the density regulariser (:447-458).  The reference runs the full
-                # field forward here and throws the colour away; only the density is evaluated.
-                if thermal_done is not None and os.environ.get("TN_CROSS_STREAMS", "1") == "1":
-                    # the two cross-field evaluations are independent of each other as well
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
-                        outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
-                    outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
-                    main.wait_stream(side)
-                    outputs["density2_thermal"].record_stream(main)
-                else:
-                    outputs["density2"] = self.field.get_density_only(ray_samples_thermal)
-                    outputs["density2_thermal"] = self.field_thermal.get_density_only(ray_samples)
+            if cross is not None:
+                outputs["density2"], outputs["density2_thermal"] = cross
 
             if not self.training:
                 # "removal" renders (:460-487).  The reference recomputes both field forwards on the very same
@@ -509,17 +483,59 @@ class ThermalNerfactoModel(nn.Module):
                 outputs["removal_thermal"] = self.renderer_thermal(rgb=field_rgb_thermal, weights=w_rm_th)
         return outputs
 
-    def _thermal_branch(self, ray_bundle_thermal: RayBundle, jitters_thermal):
-        """The thermal half of get_outputs (:431-445): pose corrections, proposal sampling, field, renderers."""
+    def _thermal_samples(self, ray_bundle_thermal: RayBundle, jitters_thermal):
+        """Pose corrections and proposal sampling of the thermal branch (:431-440)."""
         self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
         if self.training:
             self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
         self._mark_thermal_branch(ray_bundle_thermal)
-        ray_samples_thermal, weights_list_thermal, ray_samples_list_thermal = self.proposal_sampler_thermal(
-            ray_bundle_thermal, density_fns=self.density_fns_thermal, jitters=jitters_thermal)
-        thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
-                                            ray_samples_thermal, weights_list_thermal, ray_samples_list_thermal)
-        return thermal_outputs, ray_samples_thermal
+        return self.proposal_sampler_thermal(ray_bundle_thermal, density_fns=self.density_fns_thermal,
+                                             jitters=jitters_thermal)
+
+    def _branches_on_streams(self, ray_bundle, ray_bundle_thermal, jitters, jitters_thermal, want_cross):
+        """Training, density_mode="separate", CUDA: the RGB and the thermal branch are independent until the
+        cross-field terms, which are independent of each other, and most of their kernels are latency- or
+        issue-bound.  The thermal branch and one cross term are therefore issued on a second stream: in the captured
+        train step they (and, through autograd's stream tracking, their backwards) become parallel arms of the
+        graph.  Measured: 2.93 -> 2.83 ms/step with the thermal branch on the second stream, -> 2.67 with the cross
+        terms overlapped as well; a four-stream version (cross terms started right after the samplers) was slower
+        (2.73).  The jitter draws are made first, in the reference's order, so the random stream is unchanged."""
+        dev = ray_bundle.origins.device
+        num_rays = ray_bundle.origins.shape[0]
+        if jitters is None:
+            jitters = self.proposal_sampler.draw_jitters(num_rays, dev)
+        if jitters_thermal is None:
+            jitters_thermal = self.proposal_sampler_thermal.draw_jitters(num_rays, dev)
+        main = torch.cuda.current_stream(dev)
+        if self._side_stream is None or self._side_stream.device != dev:
+            self._side_stream = torch.cuda.Stream(device=dev)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ray_samples_thermal, wl_t, rsl_t = self._thermal_samples(ray_bundle_thermal, jitters_thermal)
+            thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
+                                                ray_samples_thermal, wl_t, rsl_t)
+        self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
+        self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
+                                                                            jitters=jitters)
+        outputs = self._get_outputs(ray_bundle, self.field, self.renderer_rgb, ray_samples, weights_list,
+                                    ray_samples_list)
+        main.wait_stream(side)
+        cross = None
+        if want_cross:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                d2t = self.field_thermal.get_density_only(ray_samples)
+            d2 = self.field.get_density_only(ray_samples_thermal)
+            main.wait_stream(side)
+            cross = (d2, d2t)
+        crossing = list(thermal_outputs.values()) + [ray_samples_thermal._layout.ebins, ray_samples_thermal._layout.sbins]
+        crossing += [cross[1]] if cross is not None else []
+        for v in crossing:  # made on the side stream, consumed (and eventually freed) on the main one
+            if torch.is_tensor(v):
+                v.record_stream(main)
+        return outputs, thermal_outputs, ray_samples, ray_samples_thermal, cross
 
     def _mark_thermal_branch(self, bundle: RayBundle) -> None:
         """The gradients w.r.t. the thermal bundle's (pose-corrected) origins and directions are complete only after
