@@ -318,6 +318,22 @@ def run_render(args):
         dist.destroy_process_group()
 
 
+def shutdown_distributed():
+    """Leave the process group without waiting on NCCL work that captured CUDA graphs still reference: flush, meet
+    the other ranks once more, then tear down with a watchdog (a stalled destroy must never hang the launcher)."""
+    import threading
+
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    threading.Timer(20.0, lambda: os._exit(0)).start()
+    dist.destroy_process_group()
+    os._exit(0)
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch.distributed as dist
@@ -494,7 +510,8 @@ def run_b200(args):
             line["with_optimizer"] = {"value": world * R / (opt_ms * 1e-3), "unit": "rays/s", "ms_per_step": opt_ms,
                                       "what": "the same step plus one fused Adam + LR-schedule launch over all 7 "
                                               "parameter groups (dense, 38.8 M parameters), "
-                                              + ("inside the captured graph" if world == 1 else "after the all-reduce")}
+                                              + ("inside the captured graph" if world == 1 or opt_runner._comm_in_graph
+                                                 else "after the all-reduce")}
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -507,7 +524,7 @@ def run_b200(args):
                                               f"step ({t_small:.2f} s); total {time.perf_counter() - t0:.1f} s"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        shutdown_distributed()
 
 
 if __name__ == "__main__":

@@ -61,24 +61,29 @@ class GraphedTrainStep:
         self.group = group
         world = torch.distributed.get_world_size(group) if torch.distributed.is_initialized() else 1
         groups = model.get_param_groups()
-        # Data parallel, default: ONE all-reduce of the flat buffer after the graph replay.
-        # Opt-in (overlap_comm=True or TN_COMM=overlap): the thermal branch's backward finishes first (its forward
-        # ran last), so its groups sit at the FRONT of the flat buffer and their all-reduce is started from a
-        # backward hook while the RGB branch's backward is still running; the rest follows after the last backward
-        # kernel, and both collectives (and the optimiser) are captured in the graph.  Measured on 2 B200: correct
-        # (identical gradients on both ranks) but no faster (3.487 vs 3.493 ms/step), and tearing the process group
-        # down with captured NCCL kernels alive stalls -- hence opt-in.
-        early = [n for n in ("proposal_networks_thermal", "fields_thermal") if n in groups]
+        # Data parallel.  "after" (TN_COMM=after): ONE all-reduce of the flat buffer after the graph replay.
+        # "overlap" (default on NCCL): the main fields' groups (2 x 64 MB tables + their MLPs, 83 % of the buffer)
+        # sit at the FRONT of the flat buffer; their gradients are final as soon as both fields' encode backward
+        # kernels have run, well before the proposal networks' backward (issue-bound kernels that leave HBM and
+        # NVLink idle).  A backward hook per field records an event; when both have fired a communication stream
+        # waits for them and starts the all-reduce of that segment, the rest follows after the last backward kernel,
+        # and both collectives (and the optimiser) are captured inside the CUDA graph.
+        early = [n for n in ("fields", "fields_thermal") if n in groups]
         order = early + [n for n in groups if n not in early]
         self.grads = parallel.FlatGradBuffer.from_param_groups(groups, order=order, device=self.device)
         self.grads.attach_sinks(model)
         self._early_end = max((self.grads.group_ranges[n][1] for n in early), default=0)
         if overlap_comm is None:
-            overlap_comm = os.environ.get("TN_COMM", "after") == "overlap"
+            overlap_comm = os.environ.get("TN_COMM", "overlap") == "overlap"
         self._comm_in_graph = world > 1 and overlap_comm and torch.distributed.get_backend(group) == "nccl"
         self._early_work = None
+        self._ready_events: List[torch.cuda.Event] = []
+        self._fields = [f for f in (getattr(model, "field", None), getattr(model, "field_thermal", None))
+                        if f is not None and any(p.requires_grad for p in f.parameters())]
         if self._comm_in_graph and self._early_end > 0:
-            model.thermal_grads_ready_callback = self._reduce_early
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+            for f in self._fields:
+                f.grads_ready_callback = self._field_ready
         # parameters move into their flat buffer BEFORE anything is captured (the graph bakes in addresses)
         self.optimizer = FusedAdam(self.grads, optimizer) if optimizer is not None else None
         self._adam_in_graph = self.optimizer is not None and (world == 1 or self._comm_in_graph)
@@ -102,9 +107,19 @@ class GraphedTrainStep:
                 self._eager(apply_optimizer=True, captured=True)
             torch.cuda.synchronize(self.device)
 
-    def _reduce_early(self) -> None:
-        """Backward hook: all-reduce of the thermal groups, asynchronous w.r.t. the rest of the backward."""
-        self._early_work = self.grads.all_reduce_mean(self.group, async_op=True, begin=0, end=self._early_end)
+    def _field_ready(self) -> None:
+        """Backward hook of a main field (fires on the stream that ran its encode backward).  Once every field has
+        reported, the communication stream waits for those points of both streams and all-reduces the fields'
+        segment of the buffer, asynchronously w.r.t. the rest of the backward."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._ready_events.append(ev)
+        if len(self._ready_events) < len(self._fields):
+            return
+        for e in self._ready_events:
+            self._comm_stream.wait_event(e)
+        with torch.cuda.stream(self._comm_stream):
+            self._early_work = self.grads.all_reduce_mean(self.group, async_op=True, begin=0, end=self._early_end)
 
     def _load(self, batch: Dict[str, Tensor]) -> None:
         for k in BATCH_KEYS:
@@ -119,13 +134,14 @@ class GraphedTrainStep:
         _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
         total = getattr(self.losses, "total", None)
         self.total = total if total is not None else sum(self.losses.values())
-        self._early_work = None
+        self._early_work, self._ready_events = None, []
         self.total.backward()
         if self._comm_in_graph:
             begin = self._early_end if self._early_work is not None else 0
             self.grads.all_reduce_mean(self.group, begin=begin)
             if self._early_work is not None:
-                self._early_work.wait()
+                self._early_work.wait()  # the calling stream waits for the early collective
+                torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
         if apply_optimizer and self._adam_in_graph:
             self.optimizer.step(zero_grads=captured)
 

@@ -46,6 +46,7 @@ class Field(nn.Module):
     def __init__(self) -> None:
         super().__init__()
         self._sample_locations = None
+        self.grads_ready_callback = None  # see NerfactoField.forward
         self._density_before_activation = None
 
     def _grid_coordinates(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
@@ -178,6 +179,12 @@ class NerfactoField(Field):
             return super().forward(ray_samples, compute_normals=compute_normals)
         rays, samples = lay.num_rays, lay.num_samples
         x, selector = ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+        if self.grads_ready_callback is not None and torch.is_grad_enabled() and x.requires_grad:
+            # dL/dx of the main evaluation is produced by the encode backward, the LAST kernel that touches this
+            # field's parameters in a step (heads and density MLP run before it, the cross-field density term, created
+            # later in the forward, has run earlier): data-parallel runners start this field's all-reduce from here
+            cb = self.grads_ready_callback
+            x.register_hook(lambda _g: (cb(), None)[1])
         self._sample_locations = x.view(rays, samples, 3)
         h = self.mlp_base(x)
         self._density_before_activation = h.view(rays, samples, -1)[..., :1]

@@ -256,10 +256,6 @@ class ThermalNerfactoModel(nn.Module):
         self.kwargs = dict(metadata=metadata or {}, **kwargs)
         self.device_indicator_param = nn.Parameter(torch.empty(0))  # models/base_model.py:85
         self.fuse_losses = True  # pixel / density loss terms as single kernels (torch expressions otherwise)
-        # called during backward as soon as every gradient of the thermal branch (thermal field + thermal proposal
-        # networks) is final, i.e. before the RGB branch's backward starts: data-parallel runners start the
-        # all-reduce of that half of the gradient buffer there (engine.GraphedTrainStep)
-        self.thermal_grads_ready_callback = None
         self.branch_streams = os.environ.get("TN_BRANCH_STREAMS", "1") == "1"
         self._side_stream = None
         self._populate(aabb)
@@ -488,7 +484,6 @@ class ThermalNerfactoModel(nn.Module):
         self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
         if self.training:
             self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
-        self._mark_thermal_branch(ray_bundle_thermal)
         return self.proposal_sampler_thermal(ray_bundle_thermal, density_fns=self.density_fns_thermal,
                                              jitters=jitters_thermal)
 
@@ -536,25 +531,6 @@ class ThermalNerfactoModel(nn.Module):
             if torch.is_tensor(v):
                 v.record_stream(main)
         return outputs, thermal_outputs, ray_samples, ray_samples_thermal, cross
-
-    def _mark_thermal_branch(self, bundle: RayBundle) -> None:
-        """The gradients w.r.t. the thermal bundle's (pose-corrected) origins and directions are complete only after
-        every kernel of the thermal branch has run its backward; the cross-field density terms, created later in
-        the forward, have run before that.  Tensor hooks on both fire the callback once per backward."""
-        cb = self.thermal_grads_ready_callback
-        if cb is None or not (torch.is_grad_enabled() and bundle.origins.requires_grad
-                              and bundle.directions.requires_grad):
-            return
-        pending = [2]
-
-        def fire(_grad):
-            pending[0] -= 1
-            if pending[0] == 0:
-                cb()
-            return None
-
-        bundle.origins.register_hook(fire)
-        bundle.directions.register_hook(fire)
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:

@@ -38,4 +38,4 @@ for _ in range(20):
     runner.step(None)
 e1.record(); torch.cuda.synchronize()
 say("ms/step", e0.elapsed_time(e1) / 20)
-dist.destroy_process_group()
+sys.stdout.flush(); bench.shutdown_distributed()
