@@ -175,11 +175,20 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_fwd_kernel(
         med_out[r] = (__ldg(starts + r * TS + idx) + __ldg(ends + r * TS + idx)) / 2.f;
       }
       if (exp_out) exp_out[r] = num / (acc + 1e-10f);
-      if (minmax) {  // steps are >= 0 in practice; the int trick below is valid for any sign
-        atomicMin(reinterpret_cast<int*>(minmax), smin >= 0.f ? __float_as_int(smin) : (int)0x80000000);
-        if (smin < 0.f) atomicMax(reinterpret_cast<unsigned*>(minmax), __float_as_uint(smin));
-        if (smax >= 0.f) atomicMax(reinterpret_cast<int*>(minmax + 1), __float_as_int(smax));
-        else atomicMin(reinterpret_cast<unsigned*>(minmax + 1), __float_as_uint(smax));
+      if (minmax) {
+        // Launch-wide extrema: every ray would hit the same two words.  Read them first (they only ever move
+        // outwards, so a stale value just means one redundant atomic) and touch them only when this ray improves
+        // them -- a handful of rays per launch instead of all of them.
+        const float cur_min = *reinterpret_cast<volatile float*>(minmax);
+        const float cur_max = *reinterpret_cast<volatile float*>(minmax + 1);
+        if (smin < cur_min) {  // steps are >= 0 in practice; the int trick below is valid for any sign
+          atomicMin(reinterpret_cast<int*>(minmax), smin >= 0.f ? __float_as_int(smin) : (int)0x80000000);
+          if (smin < 0.f) atomicMax(reinterpret_cast<unsigned*>(minmax), __float_as_uint(smin));
+        }
+        if (smax > cur_max) {
+          if (smax >= 0.f) atomicMax(reinterpret_cast<int*>(minmax + 1), __float_as_int(smax));
+          else atomicMin(reinterpret_cast<unsigned*>(minmax + 1), __float_as_uint(smax));
+        }
       }
     }
   }
