@@ -35,9 +35,15 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) weights_fwd_kernel(const fl
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   double carry = 0.0;
+  // the next round's operands are requested before the current round's scan: the scan's shuffle chain would
+  // otherwise sit between two dependent trips to memory
+  float dl_n = lane < S ? __ldg(deltas + r * S + lane) : 0.f, sg_n = lane < S ? __ldg(sigma + r * S + lane) : 0.f;
   for (int base = 0; base < S; base += 32) {
     const int s = base + lane;
-    const float dd = s < S ? __ldg(deltas + r * S + s) * __ldg(sigma + r * S + s) : 0.f;
+    const float dd = dl_n * sg_n;
+    const int sn = s + 32;
+    dl_n = sn < S ? __ldg(deltas + r * S + sn) : 0.f;
+    sg_n = sn < S ? __ldg(sigma + r * S + sn) : 0.f;
     const double incl = warp_incl_scan((double)dd, lane) + carry;
     // exclusive cumsum (shifted inclusive scan: subtracting dd back would turn inf into nan), rounded to
     // float like torch.cumsum's output, then exp(-.)
@@ -117,21 +123,40 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) render_fwd_kernel(
   double carry = 0.0;
   int below_half = 0;  // number of cumulative weights < 0.5 == searchsorted(cum, 0.5, left)
   const bool need_steps = starts != nullptr;
+  // operands of the next round are requested before the current round's reductions and scan
+  float w_n = lane < S ? __ldg(w + r * S + lane) : 0.f;
+  float st_n = (need_steps && lane < S) ? __ldg(starts + r * TS + lane) : 0.f;
+  float en_n = (need_steps && lane < S) ? __ldg(ends + r * TS + lane) : 0.f;
+  float c_n[C > 0 ? C : 1];
+#pragma unroll
+  for (int c = 0; c < C; ++c) c_n[c] = lane < S ? __ldg(col + (r * S + lane) * C + c) : 0.f;
   for (int base = 0; base < S; base += 32) {
     const int s = base + lane;
     const bool ok = s < S;
-    const float wv = ok ? __ldg(w + r * S + s) : 0.f;
+    const float wv = w_n, st = st_n, en = en_n;
+    float cv[C > 0 ? C : 1];
+#pragma unroll
+    for (int c = 0; c < C; ++c) cv[c] = c_n[c];
+    const int sn = s + 32;
+    const bool okn = sn < S;
+    w_n = okn ? __ldg(w + r * S + sn) : 0.f;
+    if (need_steps) {
+      st_n = okn ? __ldg(starts + r * TS + sn) : 0.f;
+      en_n = okn ? __ldg(ends + r * TS + sn) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) c_n[c] = okn ? __ldg(col + (r * S + sn) * C + c) : 0.f;
     if (C > 0 && ok) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        float v = __ldg(col + (r * S + s) * C + c);
+        float v = cv[c];
         if (eval_mode) v = nan_to_num(v);
         comp[c] += wv * v;
       }
     }
     acc += wv;
     if (need_steps) {
-      const float step = ok ? (__ldg(starts + r * TS + s) + __ldg(ends + r * TS + s)) / 2.f : 0.f;
+      const float step = ok ? (st + en) / 2.f : 0.f;
       num += wv * step;
       if (ok) { smin = fminf(smin, step); smax = fmaxf(smax, step); }
       const double incl = warp_incl_scan((double)wv, lane) + carry;
