@@ -277,10 +277,12 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
   const int64_t tiles = (N + TP - 1) / TP;
   float xr[XP];  // this thread's half of its point's input row: fetched one tile ahead
   float xh0 = 0.f;  // head mode: h[p, 0] of that row
+  float xmul = 1.f;  // row multiplier of that row (column half 0 writes the output)
   auto fetch = [&](int64_t t) {
     const int64_t p = t * TP + row;
     if constexpr (HEAD) load_head_part(hf.in, p, p < N, half, xr, xh0);
     else load_row_part<XP>(x, p, prm.x_stride, prm.in_dim, p < N, half * XP, xr);
+    if (prm.row_mul && half == 0) xmul = p < N ? __ldg(prm.row_mul + p) : 0.f;
   };
   fetch(blockIdx.x);
 
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       issue_layer<W, IN, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
+    const float om = prm.out_scale * xmul;  // this tile's, before the prefetch overwrites it
     if (t + gridDim.x < tiles) fetch(t + gridDim.x);  // next tile's input rows: in flight while this tile computes
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -362,7 +365,6 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       tmem_ld_wait();
       if (row < rows) {
         float* dst = y + (row0 + row) * prm.out_dim;
-        const float om = prm.out_scale * (prm.row_mul ? __ldg(prm.row_mul + row0 + row) : 1.f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float z = v[j] + bias[2 * W + j];
@@ -592,12 +594,16 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   // operands fetched one tile ahead: this thread's half input row, and (column half 0) the point's dy row
   float xr[XP];
   float dyr[OUTP];
-  float xh0 = 0.f;  // head mode: h[p, 0] of the prefetched row
+  float xh0 = 0.f;   // head mode: h[p, 0] of the prefetched row
+  float xmul = 1.f;  // row multiplier of the prefetched row
   auto prefetch = [&](int64_t t) {
     const int64_t r = t * TP + row;
     if constexpr (HEAD) load_head_part(hd.in, r, r < N, half, xr, xh0);
     else load_row_part<XP>(x, r, prm.x_stride, prm.in_dim, r < N, half * XP, xr);
-    if (half == 0) load_row_part<OUTP>(dy, r, prm.out_dim, prm.out_dim, r < N, 0, dyr);
+    if (half == 0) {
+      load_row_part<OUTP>(dy, r, prm.out_dim, prm.out_dim, r < N, 0, dyr);
+      if (prm.row_mul) xmul = r < N ? __ldg(prm.row_mul + r) : 0.f;
+    }
   };
   prefetch(blockIdx.x);
 
@@ -702,7 +708,7 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
       tmem_ld16(tmem_row + L::c_acc, z);
       tmem_ld_wait();
       float u[16];
-      const float om = prm.out_scale * ((prm.row_mul && row < rows) ? __ldg(prm.row_mul + row0 + row) : 1.f);
+      const float om = prm.out_scale * xmul;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float gv = dyr[j] * om;  // zero beyond out_dim and for rows past N
