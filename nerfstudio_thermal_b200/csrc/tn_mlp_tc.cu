@@ -280,9 +280,13 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
   float xmul = 1.f;  // row multiplier of that row (column half 0 writes the output)
   auto fetch = [&](int64_t t) {
     const int64_t p = t * TP + row;
-    if constexpr (HEAD) load_head_part(hf.in, p, p < N, half, xr, xh0);
-    else load_row_part<XP>(x, p, prm.x_stride, prm.in_dim, p < N, half * XP, xr);
-    if (prm.row_mul && half == 0) xmul = p < N ? __ldg(prm.row_mul + p) : 0.f;
+    if constexpr (HEAD) {
+      load_head_part(hf.in, p, p < N, half, xr, xh0);
+      if (half == 0) xmul = p < N ? __ldg(hf.sel + p) : 0.f;  // head mode: the selector of the density epilogue
+    } else {
+      load_row_part<XP>(x, p, prm.x_stride, prm.in_dim, p < N, half * XP, xr);
+      if (prm.row_mul && half == 0) xmul = p < N ? __ldg(prm.row_mul + p) : 0.f;
+    }
   };
   fetch(blockIdx.x);
 
@@ -316,7 +320,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
     for (int c = 0; c < XP / 8; ++c) store_chunk_terms<FT>(act, L::act_term, half * (XP / 8) + c, row, xr + c * 8);
     if constexpr (HEAD) {
       if (half == 0 && row < rows)
-        hf.density_out[row0 + row] = hf.scale * expf(xh0) * __ldg(hf.sel + row0 + row);
+        hf.density_out[row0 + row] = hf.scale * expf(xh0) * xmul;
     }
     fence_async_smem();
     __syncthreads();  // A0 visible to the async proxy
@@ -326,7 +330,9 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       issue_layer<W, IN, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w1));
       mma_commit(bar);
     }
-    const float om = prm.out_scale * xmul;  // this tile's, before the prefetch overwrites it
+    // this tile's output multiplier, read before the prefetch overwrites it (head mode: xmul is the selector of
+    // the density epilogue above, the head's own output is not scaled)
+    const float om = HEAD ? prm.out_scale : prm.out_scale * xmul;
     if (t + gridDim.x < tiles) fetch(t + gridDim.x);  // next tile's input rows: in flight while this tile computes
     mbar_wait(bar, phase);
     phase ^= 1;
