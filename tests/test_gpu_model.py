@@ -226,3 +226,62 @@ def test_density_only_path_equals_get_density(golden):
         assert rel <= 2e-4, (k, rel)
     rel = ((o0 - o1).double().norm() / (o0.double().norm() + 1e-30)).item()
     assert rel <= 2e-4, rel
+
+
+@pytest.mark.parametrize("samples,props", [(16, (24, 12)), (40, (33, 17))])
+def test_odd_sample_counts_train_step_vs_oracle(samples, props):
+    """Non-default sample counts (not multiples of 32, one count = 32+1; 16 < 19 takes the unfused colour-head path,
+    40 the fused one): the train-mode loss dict and every gradient the oracle produces equal the oracle's.
+    (Reference-scale tables: with tables 300x larger the 3e-7 differences between the GPU's and the CPU's sample
+    positions alone move gradients by a few 1e-3 -- the hash grid's finest levels have slopes of ~60 per unit.)"""
+    torch.manual_seed(11)
+    pa = [{"hidden_dim": 16, "log2_hashmap_size": 10, "num_levels": 5, "max_res": 128, "use_linear": False},
+          {"hidden_dim": 16, "log2_hashmap_size": 10, "num_levels": 5, "max_res": 256, "use_linear": False}]
+    cfg = tn.ThermalNerfactoModelConfig(density_mode="separate", log2_hashmap_size=11, proposal_net_args_list=pa,
+                                        num_nerf_samples_per_ray=samples, num_proposal_samples_per_ray=props)
+    model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            if "pose_adjustment" in k:
+                p.normal_(0, 1e-3)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).train()
+    R = 32
+    gen = torch.Generator().manual_seed(3)
+    cams = (torch.arange(R // 4) % 8).repeat_interleave(4)[:, None]
+    o = torch.randn(R, 3, generator=gen) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(R, 3, generator=gen), dim=-1)
+    image = torch.rand(R, 3, generator=gen)
+    is_thermal = (cams[:, 0] >= 4).float()
+    jit = [torch.rand(R, 1, generator=gen) for _ in range(6)]
+    ocfg = oracle.OracleConfig(density_mode="separate", is_thermal_cameras=(0, 0, 0, 0, 1, 1, 1, 1), log2_hashmap_size=11,
+                               num_nerf_samples_per_ray=samples, num_proposal_samples_per_ray=props,
+                               proposal_net_args_list=[{k: v for k, v in a.items() if k != "use_linear"} for a in pa])
+    sd_ref = {k: v.clone().requires_grad_(v.is_floating_point() and v.numel() > 0) for k, v in sd.items()}
+    ref = oracle.thermal_nerfacto_forward(sd_ref, ocfg, o, d, cams, training=True, jitters=jit[:3],
+                                          jitters_thermal=jit[3:])
+    ref_losses = oracle.thermal_nerfacto_losses(sd_ref, ocfg, ref, image, is_thermal, training=True)
+    sum(ref_losses.values()).backward()
+    bundle_ = tn.RayBundle(origins=o.to(DEV), directions=d.to(DEV), pixel_area=torch.ones(R, 1, device=DEV),
+                           camera_indices=cams.to(DEV))
+    outs, losses, _ = model.get_train_loss_dict(bundle_, {"image": image.to(DEV), "is_thermal": is_thermal.to(DEV)},
+                                                jitters=[j.to(DEV) for j in jit[:3]],
+                                                jitters_thermal=[j.to(DEV) for j in jit[3:]])
+    for sfx in ("", "_thermal"):  # sample placement: exact counts, bins to float rounding
+        for i, n in enumerate((*props, samples)):
+            got = outs[f"ray_samples_list{sfx}"][i]._layout.sbins.cpu()
+            assert got.shape == (R, n + 1)
+            assert max_abs(got, ref[f"ray_samples_list{sfx}"][i].sdist().detach()) <= 1e-5
+    assert sorted(losses) == sorted(ref_losses)
+    for k in ref_losses:
+        torch.testing.assert_close(losses[k].detach().cpu().float(), ref_losses[k].detach().float(), rtol=1e-3, atol=1e-7)
+    losses.total.backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        want = sd_ref[k].grad if k in sd_ref else None
+        if p.grad is None or want is None or float(want.abs().max()) < 1e-9:
+            continue
+        rel = ((p.grad.cpu().double() - want.double()).norm() / want.double().norm()).item()
+        assert rel <= 1e-3, (k, rel)
+        checked += 1
+    assert checked >= 20
