@@ -77,6 +77,7 @@ class GraphedTrainStep:
             overlap_comm = os.environ.get("TN_COMM", "overlap") == "overlap"
         self._comm_in_graph = world > 1 and overlap_comm and torch.distributed.get_backend(group) == "nccl"
         self._early_work = None
+        self._zero_stream: Optional[torch.cuda.Stream] = None
         self._ready_events: List[torch.cuda.Event] = []
         self._fields = [f for f in (getattr(model, "field", None), getattr(model, "field_thermal", None))
                         if f is not None and any(p.requires_grad for p in f.parameters())]
@@ -127,14 +128,24 @@ class GraphedTrainStep:
 
     def _eager(self, apply_optimizer: bool = True, captured: bool = False) -> None:
         s = self.static if self.source is None else self.source.next()
+        cur = torch.cuda.current_stream(self.device)
+        zeroed = None
         if not (captured and self._adam_in_graph):  # the in-graph Adam pass leaves the gradients cleared
-            self.grads.zero_()
+            # the 155 MB clear is only needed by the backward: it runs beside the forward on its own stream
+            if self._zero_stream is None:
+                self._zero_stream = torch.cuda.Stream(device=self.device)
+            zeroed = self._zero_stream
+            zeroed.wait_stream(cur)
+            with torch.cuda.stream(zeroed):
+                self.grads.zero_()
         bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
                            camera_indices=s["camera_indices"])
         _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
         total = getattr(self.losses, "total", None)
         self.total = total if total is not None else sum(self.losses.values())
         self._early_work, self._ready_events = None, []
+        if zeroed is not None:
+            cur.wait_stream(zeroed)
         self.total.backward()
         if self._comm_in_graph:
             begin = self._early_end if self._early_work is not None else 0
