@@ -76,18 +76,23 @@ class GraphedTrainStep:
         if overlap_comm is None:
             overlap_comm = os.environ.get("TN_COMM", "overlap") == "overlap"
         self._comm_in_graph = world > 1 and overlap_comm and torch.distributed.get_backend(group) == "nccl"
-        self._early_work = None
+        self._early_done = False
+        self._adam_now = False
+        self._zero_in_adam = False
         self._zero_stream: Optional[torch.cuda.Stream] = None
         self._ready_events: List[torch.cuda.Event] = []
         self._fields = [f for f in (getattr(model, "field", None), getattr(model, "field_thermal", None))
                         if f is not None and any(p.requires_grad for p in f.parameters())]
-        if self._comm_in_graph and self._early_end > 0:
-            self._comm_stream = torch.cuda.Stream(device=self.device)
-            for f in self._fields:
-                f.grads_ready_callback = self._field_ready
         # parameters move into their flat buffer BEFORE anything is captured (the graph bakes in addresses)
         self.optimizer = FusedAdam(self.grads, optimizer) if optimizer is not None else None
         self._adam_in_graph = self.optimizer is not None and (world == 1 or self._comm_in_graph)
+        # the fields' segment is exchanged AND stepped early (HBM/NVLink-bound work beside the issue-bound proposal
+        # backward): both hang off the same backward hook and run on the auxiliary stream
+        self._early_active = self._early_end > 0 and (self._comm_in_graph or self._adam_in_graph)
+        if self._early_active:
+            self._comm_stream = torch.cuda.Stream(device=self.device)
+        for f in self._fields:  # (also detaches the hooks of an earlier runner of the same model)
+            f.grads_ready_callback = self._field_ready if self._early_active else None
         self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
         self._load(example_batch)
         self.losses: Dict[str, Tensor] = {}
@@ -120,7 +125,13 @@ class GraphedTrainStep:
         for e in self._ready_events:
             self._comm_stream.wait_event(e)
         with torch.cuda.stream(self._comm_stream):
-            self._early_work = self.grads.all_reduce_mean(self.group, async_op=True, begin=0, end=self._early_end)
+            if self._comm_in_graph:
+                work = self.grads.all_reduce_mean(self.group, async_op=True, begin=0, end=self._early_end)
+                if work is not None:
+                    work.wait()  # the auxiliary stream waits for the collective
+            if self._adam_now:
+                self.optimizer.step_range(0, self._early_end, zero_grads=self._zero_in_adam)
+        self._early_done = True
 
     def _load(self, batch: Dict[str, Tensor]) -> None:
         for k in BATCH_KEYS:
@@ -143,18 +154,21 @@ class GraphedTrainStep:
         _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
         total = getattr(self.losses, "total", None)
         self.total = total if total is not None else sum(self.losses.values())
-        self._early_work, self._ready_events = None, []
+        self._early_done, self._ready_events = False, []
+        self._adam_now = apply_optimizer and self._adam_in_graph
+        self._zero_in_adam = captured
+        if self._adam_now:
+            self.optimizer.tick()
         if zeroed is not None:
             cur.wait_stream(zeroed)
         self.total.backward()
+        begin = self._early_end if self._early_done else 0
         if self._comm_in_graph:
-            begin = self._early_end if self._early_work is not None else 0
             self.grads.all_reduce_mean(self.group, begin=begin)
-            if self._early_work is not None:
-                self._early_work.wait()  # the calling stream waits for the early collective
-                torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
-        if apply_optimizer and self._adam_in_graph:
-            self.optimizer.step(zero_grads=captured)
+        if self._adam_now:
+            self.optimizer.step_range(begin, self.grads.flat.numel(), zero_grads=captured)
+        if self._early_done:
+            cur.wait_stream(self._comm_stream)
 
     def step(self, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
         if batch is not None:

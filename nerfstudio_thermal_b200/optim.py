@@ -110,10 +110,30 @@ class FusedAdam:
              found_inf: Optional[Tensor] = None) -> None:
         """One optimiser + scheduler step of every group.  inv_scale / found_inf: the GradScaler's device scalars
         (optimizers.py:150-163); `zero_grads` clears the gradient buffer in the same pass (zero_grad_all)."""
+        self.tick()
+        self.step_range(0, self.params.numel(), zero_grads, inv_scale, found_inf)
+
+    def tick(self) -> None:
+        """Advance the device-side step counter (once per optimiser step, before any step_range of that step)."""
         call("tn_counter_add", ptr(self.step_dev), 1, stream())
-        call("tn_adam_step", ptr(self.params), ptr(self.grads.flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-             self.params.numel(), self._begin, self._end, self._hyper, len(self.names), float(self.betas[0]),
-             float(self.betas[1]), ptr(self.step_dev), 0, ptr(inv_scale), ptr(found_inf), int(zero_grads), stream())
+
+    def step_range(self, begin: int, end: int, zero_grads: bool = False, inv_scale: Optional[Tensor] = None,
+                   found_inf: Optional[Tensor] = None) -> None:
+        """The update of elements [begin, end) of the flat buffers only (begin a multiple of 4): lets a runner step
+        the parameters whose gradients are already final while the rest of the backward is still running."""
+        if begin % 4 != 0 or not 0 <= begin <= end <= self.params.numel():
+            raise ValueError(f"bad range [{begin}, {end})")
+        n = end - begin
+        if n == 0:
+            return
+        g = len(self.names)
+        clamp = lambda v: min(max(v - begin, 0), n)  # noqa: E731
+        b = (c_int64 * g)(*[clamp(self.grads.group_ranges[k][0]) for k in self.names])
+        e = (c_int64 * g)(*[clamp(self.grads.group_ranges[k][1]) for k in self.names])
+        off = begin * 4
+        call("tn_adam_step", ptr(self.params) + off, ptr(self.grads.flat) + off, ptr(self.exp_avg) + off,
+             ptr(self.exp_avg_sq) + off, n, b, e, self._hyper, g, float(self.betas[0]), float(self.betas[1]),
+             ptr(self.step_dev), 0, ptr(inv_scale), ptr(found_inf), int(zero_grads), stream())
 
     def unscale_and_check(self, inv_scale: Optional[Tensor], found_inf: Tensor) -> None:
         """GradScaler.unscale_'s inf/nan check over the whole gradient buffer (the scaling itself is applied inside
