@@ -207,8 +207,22 @@ def _ddp_worker(rank, world, port, results):
         for i, p in enumerate(buf.params):
             want = sum(torch.from_numpy(g[i]) for g in gathered) / world
             torch.testing.assert_close(p.grad, want, atol=1e-6, rtol=1e-6)
-        buf.zero_()
-        assert all(float(p.grad.abs().sum()) == 0 for p in buf.params) and buf.check_views()
+        # the two-segment exchange of the train step (fields first, the rest later): group order puts the early
+        # groups at the front of the buffer, each segment is averaged by its own collective
+        early = [n for n in ("fields", "fields_thermal") if n in groups]
+        order = early + [n for n in groups if n not in early]
+        buf2 = parallel.FlatGradBuffer.from_param_groups(groups, order=order)
+        cut = max(buf2.group_ranges[n][1] for n in early)
+        assert buf2.group_ranges[early[0]][0] == 0 and 0 < cut < buf2.numel() and cut % 4 == 0
+        buf2.flat.copy_(torch.arange(buf2.numel(), dtype=torch.float32) * (rank + 1))
+        buf2.all_reduce_mean(begin=0, end=cut)
+        want = torch.arange(buf2.numel(), dtype=torch.float32)
+        torch.testing.assert_close(buf2.flat[:cut], want[:cut] * 1.5)
+        torch.testing.assert_close(buf2.flat[cut:], want[cut:] * (rank + 1))  # untouched so far
+        buf2.all_reduce_mean(begin=cut)
+        torch.testing.assert_close(buf2.flat, want * 1.5)
+        buf2.zero_()
+        assert all(float(p.grad.abs().sum()) == 0 for p in buf2.params) and buf2.check_views()
         assert parallel.rank_seed(42, rank) == 42 + rank
         results[rank] = "ok"
     finally:
