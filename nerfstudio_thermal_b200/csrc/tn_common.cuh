@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "tn_b200.h"
 
@@ -35,6 +36,12 @@ inline int check_launch(const char* what) {
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 constexpr int kNumSMs = 148;  // B200
+
+// tuning knob (host): largest level scale whose table REDs are aggregated over runs of equal cells
+inline float agg_threshold(const char* env, float dflt) {
+  const char* v = getenv(env);
+  return v ? (float)atof(v) : dflt;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -349,7 +349,7 @@ extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_d
   for (int l = 0; l < TN_MAX_LEVELS; ++l) {
     sc.s[l] = l < L ? scales_host[l] : 0.f;
     // cells of coarse levels hold long runs of consecutive samples: aggregate there
-    if (l < L && l == n_coarse && scales_host[l] <= 96.f) ++n_coarse;
+    if (l < L && l == n_coarse && scales_host[l] <= agg_threshold("TN_AGG_ENC", 96.f)) ++n_coarse;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (F) {
