@@ -74,7 +74,11 @@ class GraphedTrainStep:
         self.grads.attach_sinks(model)
         self._early_end = max((self.grads.group_ranges[n][1] for n in early), default=0)
         if overlap_comm is None:
-            overlap_comm = os.environ.get("TN_COMM", "overlap") == "overlap"
+            # measured (profiles/r01_bench_train_n*.json): the overlapped exchange wins on 2 and 4 GPUs (2.90 vs
+            # 3.02 ms/step on 2); on 8 GPUs, with replays queued back to back, the early collective's spin-waits on
+            # late peers contend with the proposal backward (3.83 ms vs 3.20 with the trailing all-reduce)
+            default = "overlap" if world <= 4 else "after"
+            overlap_comm = os.environ.get("TN_COMM", default) == "overlap"
         self._comm_in_graph = world > 1 and overlap_comm and torch.distributed.get_backend(group) == "nccl"
         self._early_done = False
         self._adam_now = False
