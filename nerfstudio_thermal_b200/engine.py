@@ -1,16 +1,25 @@
 """Step runners for the hot path: a CUDA-graph-captured train step and a sharded full-frame renderer.
 
-The per-step work of thermal-nerfacto at 4096 rays is ~150 small launches (kernels of this library plus
-torch's elementwise glue and autograd bookkeeping); issued eagerly the GPU idles between them.  On B200 the
-idiomatic fix is a CUDA graph: the whole forward + loss + backward is captured once on static input buffers
-and replayed with one launch per step.  Everything on the path is capture-safe by construction -- the C ABI
-never allocates or synchronises, jitter comes from torch's graph-safe Philox generator, and the per-ray
-losses avoid boolean indexing.
+The per-step work of thermal-nerfacto at 4096 rays is ~200 small launches (82 kernels of this library plus torch's
+elementwise glue and autograd bookkeeping); issued eagerly the GPU idles between them.  On B200 the idiomatic fix is a
+CUDA graph: the whole iteration is captured once on static buffers and replayed with one launch per step.
+Everything on the path is capture-safe by construction -- the C ABI never allocates or synchronises, jitter comes
+from torch's graph-registered Philox generator, the loss assembly avoids boolean indexing, the optimiser reads its
+step counter from the device.
+
+What one replay contains (`GraphedTrainStep._eager` is the captured program):
+
+    [source: pixel sampling, collation, ray generation]            optional, `source=DeviceBatchSource(...)`
+    gradient-buffer clear                                          on its own stream, beside the forward
+    forward: RGB branch | thermal branch on a second stream        (model._branches_on_streams), cross terms, losses
+    backward: autograd replays every node on its forward stream
+      '- when both main fields' gradients are final (hook): all-reduce of their 134 MB segment [N>1] and Adam on
+         that segment [optimizer=], on an auxiliary stream beside the proposal networks' backward
+    remaining all-reduce [N>1], Adam on the remaining segment [optimizer=]
 
 Mirrors what `Trainer.train_iteration` + `VanillaPipeline.get_train_loss_dict` drive in the reference
-(engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304).  The optimiser + scheduler step is optional: with
-`optimizer=` the fused Adam launch (`optim.FusedAdam`) runs right after the backward -- inside the captured graph
-on one GPU, after the gradient all-reduce on several -- otherwise any optimiser can read the gradients from
+(engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304; DDP of base_pipeline.py:280-283; the optimiser and
+scheduler steps of engine/optimizers.py:150-192).  Without `optimizer=` any optimiser can read the gradients from
 `grads.flat` / `param.grad`.
 """
 import os
