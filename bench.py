@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optimizer-leg", action="store_true",
                     help="skip the extra timed pass with the fused Adam step inside the timed region")
+    ap.add_argument("--graph-render", action="store_true",
+                    help="--mode render: replay one captured CUDA graph per chunk instead of the eager chunk loop")
     ap.add_argument("--extra-legs", action="store_true",
                     help="run the with_optimizer / device_pipeline legs on several GPUs too (default: one GPU only)")
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
@@ -256,19 +258,26 @@ def run_render(args):
     host_frames = [{k: v.reshape(-1, v.shape[-1]).pin_memory() for k, v in fr.items()} for fr in frames]
     total_rays = sum(fr["origins"].shape[0] for fr in host_frames)
 
+    from nerfstudio_thermal_b200 import engine
+    # chunks of 32768 rays keep the GPU busy kernel by kernel: the eager chunk loop (6.79 M rays/s) is as fast as one
+    # captured graph per chunk with the thermal branch on a second stream (6.69 M), so the plain loop is the default
+    chunk_runner = engine.GraphedRenderChunk(model, chunk) if args.graph_render else None
+    dev_frames = [{k: v.to(dev) for k, v in fr.items()} for fr in host_frames]
+
     def render_all(from_host):
         outs = []
         with torch.no_grad():
-            for fr in host_frames:
+            for fr, dfr in zip(host_frames, dev_frames):
                 n = fr["origins"].shape[0]
                 for s, e in parallel.shard_chunks(n, chunk, rank, world):
-                    b = {k: v[s:e].to(dev, non_blocking=True) for k, v in fr.items()}
-                    res = model(tn.RayBundle(origins=b["origins"], directions=b["directions"],
-                                             pixel_area=b["pixel_area"], camera_indices=b["camera_indices"]))
-                    if from_host:  # end to end: rendered chunk back to the host, as base_model.py:200-203 does
+                    src = fr if from_host else dfr  # e2e: pinned host rays in, rendered chunk back to the host
+                    b = tn.RayBundle(**{k: src[k][s:e].to(dev, non_blocking=True) for k in
+                                        ("origins", "directions", "pixel_area", "camera_indices")})
+                    res = chunk_runner.render(b) if chunk_runner is not None else model(b)
+                    if from_host:  # as base_model.py:200-203 does
                         outs.append({k: res[k].to("cpu", non_blocking=True) for k in keys})
                     else:
-                        outs.append(res[keys[0]])
+                        outs.append(res[keys[0]].clone() if chunk_runner is not None else res[keys[0]])
         return outs
 
     def barrier():
@@ -311,7 +320,9 @@ def run_render(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"full-frame eval render 640x512 thermal + 1920x1080 RGB, density_mode={args.density_mode}, "
                                    f"chunks of {chunk} rays sharded over {world} rank(s)", "rays_per_step": total_rays,
-                       "init": args.init, "parallelism": f"dp{world}"},
+                       "init": args.init, "parallelism": f"dp{world}",
+                       "launch": "one CUDA graph replay per chunk (engine.GraphedRenderChunk)" if args.graph_render
+                                 else "eager chunk loop (models/base_model.py:177-206)"},
             "e2e": {"value": total_rays / (times["e2e"] * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 52 * total_rays,
                     "d2h_bytes_per_step": out_bytes, "ms_per_step": times["e2e"]},
         }

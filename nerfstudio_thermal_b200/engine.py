@@ -197,18 +197,82 @@ class GraphedTrainStep:
         return self.total
 
 
+class GraphedRenderChunk:
+    """The eval forward of one full chunk of rays (`eval_num_rays_per_chunk`, models/base_model.py:187-190) captured
+    as a CUDA graph: ~100 launches become one, and the thermal branch runs on a second stream beside the RGB one
+    (`model.eval_branch_streams`, as in training).  `render(bundle)` copies a chunk into the static input buffers,
+    replays, and returns the output dict (views of static buffers: consume or clone before the next call).  A
+    shorter last chunk is padded with copies of its first ray (duplicates leave the chunk-global extrema of
+    renderers.py:574 unchanged) and the outputs are sliced."""
+
+    def __init__(self, model: ThermalNerfactoModel, chunk: Optional[int] = None, warmup: int = 2):
+        self.model, self.device = model, model.device
+        assert self.device.type == "cuda", "the hot path runs on CUDA only (no CPU fallback)"
+        self.chunk = chunk or model.config.eval_num_rays_per_chunk
+        c = self.chunk
+        self.static = RayBundle(origins=torch.zeros((c, 3), device=self.device),
+                                directions=torch.zeros((c, 3), device=self.device),
+                                pixel_area=torch.ones((c, 1), device=self.device),
+                                camera_indices=torch.zeros((c, 1), dtype=torch.long, device=self.device))
+        self.static.directions[:, 2] = 1.0
+        model.eval()
+        streams, model.eval_branch_streams = model.eval_branch_streams, True
+        try:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(max(warmup, 1)):
+                    model(self._bundle())
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.no_grad():
+                self.outputs = {k: v for k, v in model(self._bundle()).items() if torch.is_tensor(v)}
+            torch.cuda.synchronize(self.device)
+        finally:
+            model.eval_branch_streams = streams
+
+    def _bundle(self) -> RayBundle:
+        s = self.static  # a fresh bundle object per call: the model rewrites origins/directions/nears/fars on it
+        return RayBundle(origins=s.origins, directions=s.directions, pixel_area=s.pixel_area,
+                         camera_indices=s.camera_indices)
+
+    @torch.no_grad()
+    def render(self, bundle: RayBundle) -> Dict[str, Tensor]:
+        n = bundle.origins.shape[0]
+        if n > self.chunk or n == 0:
+            raise ValueError(f"chunk of {n} rays (captured for up to {self.chunk})")
+        s = self.static
+        for dst, src in ((s.origins, bundle.origins), (s.directions, bundle.directions),
+                         (s.pixel_area, bundle.pixel_area), (s.camera_indices, bundle.camera_indices)):
+            dst[:n].copy_(src, non_blocking=True)
+            if n < self.chunk:
+                dst[n:].copy_(dst[:1].expand(self.chunk - n, -1))
+        self.graph.replay()
+        return self.outputs if n == self.chunk else {k: v[:n] for k, v in self.outputs.items()}
+
+
 @torch.no_grad()
 def render_rays_sharded(model: ThermalNerfactoModel, bundle: RayBundle, rank: int = 0, world: int = 1,
-                        keys: Optional[List[str]] = None) -> Dict[str, Tensor]:
+                        keys: Optional[List[str]] = None, use_graph: bool = False) -> Dict[str, Tensor]:
     """Zero-communication full-frame render: this rank evaluates its contiguous block of the reference's chunks
     (models/base_model.py:177-206) of a flattened ray bundle and returns the outputs for those rays only
-    (the caller concatenates rank outputs in rank order)."""
+    (the caller concatenates rank outputs in rank order).  use_graph: chunks replay one captured graph
+    (GraphedRenderChunk, cached on the model) -- pays off for small chunks; at the reference's 32768 rays per chunk the
+    kernels already fill the GPU and the eager loop is as fast."""
     model.eval()
     flat = bundle.flatten()
+    chunk = model.config.eval_num_rays_per_chunk
+    runner = None
+    if use_graph and model.device.type == "cuda":
+        runner = getattr(model, "_render_chunk_runner", None)
+        if runner is None or runner.chunk != chunk:
+            runner = model._render_chunk_runner = GraphedRenderChunk(model, chunk)
     outs: Dict[str, List[Tensor]] = {}
-    for start, end in parallel.shard_chunks(len(flat), model.config.eval_num_rays_per_chunk, rank, world):
-        res = model(flat[start:end].to(model.device))
+    for start, end in parallel.shard_chunks(len(flat), chunk, rank, world):
+        part = flat[start:end].to(model.device)
+        res = runner.render(part) if runner is not None else model(part)
         for k, v in res.items():
             if torch.is_tensor(v) and (keys is None or k in keys):
-                outs.setdefault(k, []).append(v)
+                outs.setdefault(k, []).append(v.clone() if runner is not None else v)
     return {k: torch.cat(v) for k, v in outs.items()}

@@ -285,3 +285,33 @@ def test_odd_sample_counts_train_step_vs_oracle(samples, props):
         assert rel <= 1e-3, (k, rel)
         checked += 1
     assert checked >= 20
+
+
+def test_graph_captured_render_chunk_equals_eager(golden):
+    """engine.GraphedRenderChunk (one graph replay per chunk, thermal branch on a second stream) returns exactly what the
+    eager eval forward returns, for a full chunk and for a padded shorter one; render_rays_sharded agrees with the
+    reference-style chunk loop."""
+    from nerfstudio_thermal_b200 import engine
+    g, model = build(golden, "separate", eval_num_rays_per_chunk=24)
+    model.eval()
+    b = bundle(g)
+    runner = engine.GraphedRenderChunk(model)
+    keys = ["rgb", "rgb_thermal", "depth", "depth_thermal", "accumulation", "expected_depth", "removal", "removal_thermal",
+            "density2", "prop_depth_0"]
+    for n in (24, 9):
+        part = b[:n]
+        with torch.no_grad():
+            want = model(tn.RayBundle(origins=part.origins.clone(), directions=part.directions.clone(),
+                                      pixel_area=part.pixel_area, camera_indices=part.camera_indices))
+        got = runner.render(part)
+        for k in keys:
+            assert got[k].shape == want[k].shape, k
+            assert torch.equal(got[k], want[k]), (n, k, max_abs(got[k], want[k].cpu()))
+    full = engine.render_rays_sharded(model, b, keys=keys, use_graph=True)
+    loop = model.get_outputs_for_camera_ray_bundle(tn.RayBundle(
+        origins=b.origins[:, None], directions=b.directions[:, None], pixel_area=b.pixel_area[:, None],
+        camera_indices=b.camera_indices[:, None]))
+    for k in keys:
+        assert torch.equal(full[k].reshape(-1), loop[k].reshape(-1)), k
+    halves = [engine.render_rays_sharded(model, b, rank=r, world=2, keys=["rgb"])["rgb"] for r in (0, 1)]  # eager loop
+    assert torch.equal(torch.cat(halves), full["rgb"])
