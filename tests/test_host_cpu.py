@@ -264,3 +264,39 @@ def test_reference_checkpoint_round_trip(golden):
     checkpoint.load_checkpoint(out, model2)
     for k, v in model2.state_dict().items():
         assert torch.equal(v, sd[k]), k
+
+
+def test_ctypes_table_matches_header_prototypes():
+    """Every prototype of include/tn_b200.h and its ctypes binding agree on the number and the KIND of the arguments
+    (pointer / int64 / int / float / double), so a changed C signature cannot silently shift the Python call."""
+    import ctypes as C
+    text = open(os.path.join(ROOT, "include", "tn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(?:int|const char\*)\s+(tn_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib._SIGNATURES)
+
+    def kind_c(arg):
+        arg = " ".join(arg.split())
+        if "*" in arg:
+            return "ptr"
+        for t, k in (("int64_t", "i64"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+            if re.search(rf"\b{t}\b", arg):
+                return k
+        raise AssertionError(f"unparsed argument {arg!r}")
+
+    def kind_py(t):
+        if t in (C.c_int64,):
+            return "i64"
+        if t in (C.c_int, C.c_int32):
+            return "i32"
+        if t is C.c_float:
+            return "f32"
+        if t is C.c_double:
+            return "f64"
+        return "ptr"  # c_void_p and POINTER(...) tables
+
+    for name, args in protos.items():
+        cargs = [a for a in (s.strip() for s in args.split(",")) if a and a != "void"]
+        want = [kind_c(a) for a in cargs]
+        got = [kind_py(t) for t in _lib._SIGNATURES[name]]
+        assert got == want, (name, got, want)
