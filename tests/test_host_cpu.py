@@ -300,3 +300,24 @@ def test_ctypes_table_matches_header_prototypes():
         want = [kind_c(a) for a in cargs]
         got = [kind_py(t) for t in _lib._SIGNATURES[name]]
         assert got == want, (name, got, want)
+
+
+def test_draw_jitters_reproduces_the_samplers_random_stream():
+    """ProposalNetworkSampler.draw_jitters makes exactly the torch.rand calls the sampler would make level by level
+    (one [R,1] draw per level with use_single_jitter, ray_samplers.py:96-106, 311-320), and none in eval."""
+    cfg = tn.ThermalNerfactoModelConfig(density_mode="separate", log2_hashmap_size=4,
+                                        proposal_net_args_list=[{"hidden_dim": 16, "log2_hashmap_size": 4,
+                                                                 "num_levels": 2, "max_res": 32, "use_linear": False}] * 2)
+    model = cfg.setup(num_train_data=4, metadata={"is_thermal": [0, 0, 1, 1]})
+    model.train()
+    torch.manual_seed(9)
+    got = model.proposal_sampler.draw_jitters(10, "cpu") + model.proposal_sampler_thermal.draw_jitters(10, "cpu")
+    torch.manual_seed(9)
+    want = [torch.rand((10, 1)) for _ in range(6)]
+    assert len(got) == 6 and all(torch.equal(a, b) for a, b in zip(got, want))
+    model.eval()
+    assert model.proposal_sampler.draw_jitters(10, "cpu") is None
+    model.train()
+    model.proposal_sampler.initial_sampler.single_jitter = False
+    j = model.proposal_sampler.draw_jitters(10, "cpu")
+    assert j[0].shape == (10, 257) and j[1].shape == (10, 1)
