@@ -132,15 +132,17 @@ int tn_sh4(const float* d, int64_t N, float* out, void* stream);
 int tn_piecewise_bins(const float* unit_bins, const float* nears, const float* fars, const float* jitter,
                       int jitter_per_sample, int64_t R, int S, float* sbins_out, float* ebins_out, void* stream);
 /* replaces: model_components/ray_samplers.py:301-372 (PDFSampler, include_original=False).
- * weights[R,S_old] (already annealed), sbins_old[R,S_old+1].
+ * weights[R,S_old], sbins_old[R,S_old+1].  anneal_dev: NULL (weights are used as given) or a device float a: the
+ * histogram is weights ** a, ProposalNetworkSampler's annealing (:602), read at run time so that a captured CUDA
+ * graph follows the BEFORE_TRAIN_ITERATION schedule (models/nerfacto.py:271-281).
  * u_base[S_new+1]: eval (jitter == NULL): linspace(0, 1-1/nb, nb) + 1/(2 nb), nb = S_new+1 (:328-329);
  *                  train (jitter given: [R], or [R,nb] with jitter_per_sample = 1): linspace(0, 1-1/nb, nb),
  *                  the kernel adds jitter/nb (:319-325).
  * Outputs sbins_new/ebins_new [R,S_new+1].  S_old <= 1024. */
 int tn_pdf_sample(const float* weights, const float* sbins_old, const float* nears, const float* fars,
-                  const float* u_base, const float* jitter, int jitter_per_sample, int64_t R, int S_old,
-                  int S_new, float histogram_padding, float eps, float* sbins_new, float* ebins_new,
-                  void* stream);
+                  const float* u_base, const float* jitter, int jitter_per_sample, const float* anneal_dev,
+                  int64_t R, int S_old, int S_new, float histogram_padding, float eps, float* sbins_new,
+                  float* ebins_new, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Volume rendering.
@@ -319,16 +321,25 @@ int tn_generate_rays(const int64_t* ray_indices, const float* camera_to_worlds, 
  * params/grads/exp_avg/exp_avg_sq: flat fp32 device buffers of n elements (16-byte aligned).  Group i covers
  * elements [group_begin_host[i], group_end_host[i]) (ordered, disjoint; elements of no group are left alone) and
  * group_hyper_host[i*8 ..] = {lr_init, lr_final (<=0: lr_init), lr_pre_warmup, eps, weight_decay, warmup_steps,
- * max_steps (0: constant lr), ramp (0 linear, 1 cosine)}.  The step number t (1-based, as torch's state['step']
- * after the increment) is read from step_dev when non-NULL (so the call can live in a CUDA graph), else step_host;
- * the learning rate used is lr_init * lr_lambda(t-1), evaluated on the device in double.  Dense update exactly as
- * torch.optim.Adam (amsgrad off): m = lerp(m,g,1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m /
+ * max_steps (0: constant lr), ramp (0 linear, 1 cosine)}.  Step numbers are read from the device when step_dev
+ * is non-NULL (so the call can live in a CUDA graph), else step_host serves for both: step_dev[0] = i, the 1-based
+ * number of this training iteration -- the learning rate used is lr_init * lr_lambda(i-1) (the schedulers step
+ * once per iteration for every group, optimizers.py:182-192), evaluated on the device in double; with
+ * per_group_steps != 0, step_dev[1+k] = t_k, the 1-based number of group k's own Adam step (torch's state['step']
+ * after the increment: it lags i for groups that sat out iterations without a gradient).  active_mask bit k = 0:
+ * group k is left untouched this call (its gradients are None in the reference, :165-170).  Dense update exactly
+ * as torch.optim.Adam (amsgrad off): m = lerp(m,g,1-b1); v = b2 v + (1-b2) g^2; p -= lr/(1-b1^t) * m /
  * (sqrt(v)/sqrt(1-b2^t) + eps).  inv_scale_dev: NULL or device float multiplying the gradients (GradScaler);
- * found_inf_dev: NULL or device float, non-zero = skip the update; zero_grads: clear grads after reading them. */
+ * found_inf_dev: NULL or device float, non-zero = skip the update; zero_grads: clear grads after reading them
+ * (inactive groups' and padding elements included). */
 int tn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                  const int64_t* group_begin_host, const int64_t* group_end_host, const float* group_hyper_host,
                  int n_groups, double beta1, double beta2, const int32_t* step_dev, int step_host,
-                 const float* inv_scale_dev, const float* found_inf_dev, int zero_grads, void* stream);
+                 int per_group_steps, uint32_t active_mask, const float* inv_scale_dev,
+                 const float* found_inf_dev, int zero_grads, void* stream);
+/* counters_dev[0] += 1 (iteration) and counters_dev[1+k] += 1 for every group k with active_mask bit k set:
+ * the device-side counters tn_adam_step reads (per_group_steps layout), advanced once per iteration. */
+int tn_step_counters_tick(int32_t* counters_dev, int n_groups, uint32_t active_mask, void* stream);
 /* replaces: torch.cuda.amp.GradScaler.unscale_'s inf check (used by engine/optimizers.py:150-163):
  * found_inf_dev[0] = 1 if any grads[i] * inv_scale is not finite, else 0. */
 int tn_grad_unscale_check(const float* grads, int64_t n, const float* inv_scale_dev, float* found_inf_dev,

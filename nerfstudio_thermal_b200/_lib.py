@@ -6,7 +6,7 @@ entry point raises `TnLibraryError`.  Build it with `python -c "import __graft_e
 """
 import ctypes
 import os
-from ctypes import c_double, POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_double, POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint, c_void_p
 
 import torch
 
@@ -43,7 +43,7 @@ _SIGNATURES = {
                       _FPP, _P],
     "tn_sh4": [_P, c_int64, _P, _P],
     "tn_piecewise_bins": [_P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, _P],
-    "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],
+    "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],
     "tn_weights_fwd": [_P, _P, c_int64, c_int, _P, _P],
     "tn_weights_bwd": [_P, _P, _P, c_int64, c_int, _P, _P],
     "tn_render_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), c_int, _P, _P, _P, _P, _P, _P],
@@ -72,7 +72,8 @@ _SIGNATURES = {
     "tn_gather_pixels": [_P, c_int, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P, _P, _P],
     "tn_generate_rays": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P],
     "tn_adam_step": [_P, _P, _P, _P, c_int64, POINTER(c_int64), POINTER(c_int64), POINTER(c_float), c_int, c_double,
-                     c_double, _P, c_int, _P, _P, c_int, _P],
+                     c_double, _P, c_int, c_int, c_uint, _P, _P, c_int, _P],
+    "tn_step_counters_tick": [_P, c_int, c_uint, _P],
     "tn_grad_unscale_check": [_P, c_int64, _P, _P, _P],
     "tn_counter_add": [_P, c_int, _P],
 }

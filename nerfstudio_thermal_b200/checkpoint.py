@@ -28,20 +28,40 @@ def model_state_from_pipeline(pipeline_state: Dict[str, Any]) -> Dict[str, Any]:
     return model_state
 
 
+# Sub-modules of the reference model that hold weights but are reporting code, not the hot path: the torchmetrics
+# objects built in NerfactoModel.populate_modules (models/nerfacto.py:251-253).  A real `step-*.ckpt` carries the
+# LPIPS network's weights under `_model.lpips.net.*`; this package has no such modules, so those keys are dropped
+# before the strict load instead of being reported as unexpected.
+METRIC_MODULE_PREFIXES = ("lpips.", "psnr.", "ssim.")
+
+
 def load_checkpoint(ckpt: Dict[str, Any], model: ThermalNerfactoModel, optimizer: Optional[FusedAdam] = None,
-                    strict: bool = True) -> int:
+                    strict: Optional[bool] = True) -> int:
     """Load a reference `step-*.ckpt` dict (torch.load(..., map_location="cpu")) into the model (and the fused
-    optimiser).  Returns the step to resume from (`loaded_state["step"] + 1`, trainer.py:402)."""
+    optimiser).  Returns the step to resume from (`loaded_state["step"] + 1`, trainer.py:402).
+
+    Keys of the reference's metric modules (`METRIC_MODULE_PREFIXES`) are ignored.  Everything else is loaded with
+    strict=True; `strict=None`/False retries non-strictly like Pipeline.load_state_dict (base_pipeline.py:116-122)."""
     step = int(ckpt["step"])
     model.set_anneal_step(step)  # Model.update_to_step
-    model.load_state_dict(model_state_from_pipeline(ckpt["pipeline"]), strict=strict)
+    state = {k: v for k, v in model_state_from_pipeline(ckpt["pipeline"]).items()
+             if not k.startswith(METRIC_MODULE_PREFIXES)}
+    try:
+        model.load_state_dict(state, strict=True)
+    except RuntimeError:
+        if strict:
+            raise
+        model.load_state_dict(state, strict=False)
     if optimizer is not None and "optimizers" in ckpt:
-        optimizer.load_state_dict({k: v for k, v in ckpt["optimizers"].items() if k in optimizer.config})
+        optimizer.load_state_dict({k: v for k, v in ckpt["optimizers"].items() if k in optimizer.config},
+                                  schedulers=ckpt.get("schedulers"))
     return step + 1
 
 
 def save_checkpoint(step: int, model: ThermalNerfactoModel, optimizer: Optional[FusedAdam] = None) -> Dict[str, Any]:
-    """The dict `Trainer.save_checkpoint` writes (pass it to torch.save): loadable by the reference's trainer."""
+    """The dict `Trainer.save_checkpoint` writes (pass it to torch.save).  The reference's metric modules
+    (`_model.lpips.net.*`) are not part of this package, so their keys are absent: the reference's trainer loads the
+    result through its strict-then-non-strict fallback (Pipeline.load_state_dict with strict=None/False)."""
     out: Dict[str, Any] = {"step": step,
                            "pipeline": {f"_model.{k}": v.detach().cpu().clone() for k, v in model.state_dict().items()},
                            "optimizers": {}, "schedulers": {}, "scalers": {}}

@@ -70,19 +70,27 @@ __global__ void __launch_bounds__(kAdamThreads) adam_kernel(float* __restrict__ 
                                                             float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                             AdamGroups groups, double beta1, double beta2,
                                                             const int32_t* __restrict__ step_dev, int step_host,
+                                                            int per_group_steps, uint32_t active_mask,
                                                             const float* __restrict__ inv_scale_dev,
                                                             const float* __restrict__ found_inf_dev, int zero_grads) {
   __shared__ AdamCoef coef[TN_ADAM_MAX_GROUPS];
   __shared__ int64_t gbegin[TN_ADAM_MAX_GROUPS], gend[TN_ADAM_MAX_GROUPS];
-  const int step = step_dev ? *step_dev : step_host;  // 1-based count of this Adam step
+  // step_dev[0]: 1-based number of this ITERATION (the schedulers have stepped iteration-1 times);
+  // step_dev[1+k] (per_group_steps): 1-based number of group k's Adam step -- torch's state['step'], which lags the
+  // iteration count for groups that sat out steps without a gradient
+  const int iteration = step_dev ? step_dev[0] : step_host;
   if (threadIdx.x < groups.n) {
     const AdamGroup& gr = groups.g[threadIdx.x];
-    const double lr = scheduled_lr(gr, step - 1);
+    const int step = (step_dev && per_group_steps) ? step_dev[1 + threadIdx.x] : iteration;
+    const double lr = scheduled_lr(gr, iteration - 1);
     const double bc1 = 1.0 - pow(beta1, (double)step);
     const double bc2 = 1.0 - pow(beta2, (double)step);
     coef[threadIdx.x] = {(float)(lr / bc1), (float)sqrt(bc2), gr.eps, gr.weight_decay};
+    // a group that is not active this step (no gradient: torch.optim.Adam skips parameters whose grad is None,
+    // engine/optimizers.py:165-170) covers no elements
+    const bool on = (active_mask >> threadIdx.x) & 1u;
     gbegin[threadIdx.x] = gr.begin;
-    gend[threadIdx.x] = gr.end;
+    gend[threadIdx.x] = on ? gr.end : gr.begin;
   }
   __syncthreads();
   const bool skip = found_inf_dev && *found_inf_dev != 0.f;  // GradScaler.step: no update on inf/nan gradients
@@ -153,6 +161,13 @@ __global__ void __launch_bounds__(256) grad_check_kernel(const float* __restrict
 
 __global__ void counter_add_kernel(int32_t* c, int v) { *c += v; }
 
+// counters[0] += 1 (iteration), counters[1+k] += 1 for every active group k
+__global__ void step_counters_tick_kernel(int32_t* c, int n_groups, uint32_t active_mask) {
+  const int t = threadIdx.x;
+  if (t == 0) c[0] += 1;
+  else if (t <= n_groups && ((active_mask >> (t - 1)) & 1u)) c[t] += 1;
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -160,8 +175,8 @@ using namespace tn;
 extern "C" int tn_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                             const int64_t* group_begin_host, const int64_t* group_end_host,
                             const float* group_hyper_host, int n_groups, double beta1, double beta2,
-                            const int32_t* step_dev, int step_host, const float* inv_scale_dev,
-                            const float* found_inf_dev, int zero_grads, void* stream) {
+                            const int32_t* step_dev, int step_host, int per_group_steps, uint32_t active_mask,
+                            const float* inv_scale_dev, const float* found_inf_dev, int zero_grads, void* stream) {
   TN_REQUIRE(n >= 0 && n_groups >= 0 && n_groups <= TN_ADAM_MAX_GROUPS, TN_EINVAL, "adam_step: n=%lld groups=%d",
              (long long)n, n_groups);
   if (n == 0 || n_groups == 0) return TN_OK;
@@ -190,8 +205,8 @@ extern "C" int tn_adam_step(float* params, float* grads, float* exp_avg, float* 
   const int64_t n4 = (n + 3) / 4;
   const unsigned grid = (unsigned)min((n4 + kAdamThreads - 1) / kAdamThreads, (int64_t)kNumSMs * 8);
   adam_kernel<<<grid, kAdamThreads, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, gs, beta1, beta2,
-                                                               step_dev, step_host, inv_scale_dev, found_inf_dev,
-                                                               zero_grads);
+                                                               step_dev, step_host, per_group_steps, active_mask,
+                                                               inv_scale_dev, found_inf_dev, zero_grads);
   return check_launch("adam_kernel");
 }
 
@@ -209,6 +224,13 @@ extern "C" int tn_grad_unscale_check(const float* grads, int64_t n, const float*
   const unsigned grid = (unsigned)min((n4 + 255) / 256, (int64_t)kNumSMs * 8);
   grad_check_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(grads, n, inv_scale_dev, found_inf_dev);
   return check_launch("grad_check_kernel");
+}
+
+extern "C" int tn_step_counters_tick(int32_t* counters_dev, int n_groups, uint32_t active_mask, void* stream) {
+  TN_REQUIRE(counters_dev && n_groups >= 0 && n_groups <= TN_ADAM_MAX_GROUPS, TN_EINVAL,
+             "step_counters_tick: bad arguments");
+  step_counters_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters_dev, n_groups, active_mask);
+  return check_launch("step_counters_tick_kernel");
 }
 
 extern "C" int tn_counter_add(int32_t* counter_dev, int value, void* stream) {

@@ -272,8 +272,8 @@ __device__ __forceinline__ float spacing_inv(float y) { return y < 0.5f ? 2.f * 
 __global__ void __launch_bounds__(32 * kWarpsPerCta) pdf_sample_kernel(
     const float* __restrict__ weights, const float* __restrict__ sbins_old, const float* __restrict__ nears,
     const float* __restrict__ fars, const float* __restrict__ u_base, const float* __restrict__ jitter,
-    int jitter_per_sample, int64_t R, int S_old, int S_new, float pad, float eps, float* __restrict__ sbins_new,
-    float* __restrict__ ebins_new) {
+    int jitter_per_sample, const float* __restrict__ anneal_dev, int64_t R, int S_old, int S_new, float pad, float eps,
+    float* __restrict__ sbins_new, float* __restrict__ ebins_new) {
   extern __shared__ float smem[];
   float* cdf = smem + (size_t)(threadIdx.x >> 5) * 2 * (S_old + 1);
   float* bins = cdf + (S_old + 1);
@@ -281,9 +281,14 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) pdf_sample_kernel(
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
   // weights + histogram_padding, their sum, the zero-weight guard (:305-311)
+  // proposal-weight annealing (ray_samplers.py:602: weights ** anneal) with the exponent read from the device, so
+  // a captured graph follows the schedule; pow(w, 1) == w is taken literally
+  const float anneal = anneal_dev ? __ldg(anneal_dev) : 1.f;
   double sum_d = 0.0;
   for (int s = lane; s < S_old; s += 32) {
-    const float wv = __ldg(weights + r * S_old + s) + pad;
+    float w0 = __ldg(weights + r * S_old + s);
+    if (anneal != 1.f) w0 = powf(w0, anneal);
+    const float wv = w0 + pad;
     cdf[s + 1] = wv;  // stash
     sum_d += (double)wv;
   }
@@ -422,9 +427,9 @@ extern "C" int tn_render_bwd(const float* weights, const float* colour, const fl
 }
 
 extern "C" int tn_pdf_sample(const float* weights, const float* sbins_old, const float* nears, const float* fars,
-                             const float* u_base, const float* jitter, int jitter_per_sample, int64_t R, int S_old,
-                             int S_new, float histogram_padding, float eps, float* sbins_new, float* ebins_new,
-                             void* stream) {
+                             const float* u_base, const float* jitter, int jitter_per_sample,
+                             const float* anneal_dev, int64_t R, int S_old, int S_new, float histogram_padding,
+                             float eps, float* sbins_new, float* ebins_new, void* stream) {
   TN_REQUIRE(weights && sbins_old && nears && fars && u_base && sbins_new && ebins_new, TN_EINVAL,
              "pdf_sample: null pointer");
   TN_REQUIRE(R >= 0 && S_old >= 1 && S_old <= 1024 && S_new >= 1, TN_EINVAL, "pdf_sample: bad R=%lld S_old=%d S_new=%d",
@@ -432,7 +437,7 @@ extern "C" int tn_pdf_sample(const float* weights, const float* sbins_old, const
   if (R == 0) return TN_OK;
   const size_t smem = (size_t)kWarpsPerCta * 2 * (S_old + 1) * sizeof(float);
   pdf_sample_kernel<<<ray_blocks(R), 32 * kWarpsPerCta, smem, (cudaStream_t)stream>>>(
-      weights, sbins_old, nears, fars, u_base, jitter, jitter_per_sample, R, S_old, S_new, histogram_padding, eps,
+      weights, sbins_old, nears, fars, u_base, jitter, jitter_per_sample, anneal_dev, R, S_old, S_new, histogram_padding, eps,
       sbins_new, ebins_new);
   return check_launch("pdf_sample_kernel");
 }

@@ -23,7 +23,7 @@ scheduler steps of engine/optimizers.py:150-192).  Without `optimizer=` any opti
 `grads.flat` / `param.grad`.
 """
 import os
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -110,21 +110,82 @@ class GraphedTrainStep:
         self._load(example_batch)
         self.losses: Dict[str, Tensor] = {}
         self.total: Optional[Tensor] = None
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = use_graph
+        # Host-side schedule state that a captured graph would otherwise freeze (ray_samplers.py:591, 604-613): whether
+        # each proposal sampler's networks are "updated" (trained) this iteration.  One graph VARIANT is captured per
+        # decision tuple, lazily; step() picks the variant on the host and applies the samplers' bookkeeping after the
+        # replay.  (The annealing exponent is not frozen either: the PDF kernel reads it from a device scalar that
+        # ProposalNetworkSampler.set_anneal rewrites.)
+        self._samplers = [model.proposal_sampler]
+        self._sampler_groups = ["proposal_networks"]
+        if model.config.density_mode == "separate":
+            self._samplers.append(model.proposal_sampler_thermal)
+            self._sampler_groups.append("proposal_networks_thermal")
+        self._variants: Dict[Tuple[bool, ...], Tuple[torch.cuda.CUDAGraph, Tensor, Dict[str, Tensor]]] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None  # the variant replayed last
+        if self.optimizer is not None or use_graph:
+            from .field_components import HashEncoding
+            if any(isinstance(m, HashEncoding) and m.use_half_table for m in model.modules()):
+                # the fp16 gather mirrors are refreshed from Python when the parameter's version changes; neither the
+                # fused optimiser (raw pointers) nor a graph replay would ever trigger that
+                raise NotImplementedError("fp16 gather tables (use_half_table) are an inference option: not supported "
+                                          "together with the fused optimiser or a captured train step")
+        if world > 1:
+            self.sync_replicas()
         model.train()
         if use_graph:
+            key = self._variant_key()
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
-                for _ in range(max(warmup, 2)):  # allocator / cudaFuncSetAttribute / host-constant caches warm
-                    self._eager(apply_optimizer=False)  # warm-up must not move the parameters
+                for _ in range(max(warmup, 2) - 1):  # allocator / cudaFuncSetAttribute / host-constant caches warm
+                    self._eager(apply_optimizer=False, key=key)  # warm-up must not move the parameters
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
-            self.grads.zero_()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._eager(apply_optimizer=True, captured=True)
-            torch.cuda.synchronize(self.device)
+            self._capture(key)
+
+    def sync_replicas(self) -> None:
+        """Data-parallel replicas must start identical: DistributedDataParallel broadcasts rank 0's parameters and
+        buffers when it wraps the model (pipelines/base_pipeline.py:280-283); this is the same step for the flat
+        buffers (call it again after loading a checkpoint on one rank)."""
+        if not torch.distributed.is_initialized() or torch.distributed.get_world_size(self.group) == 1:
+            return
+        bc = lambda t: torch.distributed.broadcast(t, src=torch.distributed.get_global_rank(self.group, 0)  # noqa: E731
+                                                   if self.group is not None else 0, group=self.group)
+        with torch.no_grad():
+            if self.grads.flat_params is not None:
+                bc(self.grads.flat_params)
+            else:
+                for p in self.grads.params:
+                    bc(p.data)
+            for b in self.model.buffers():
+                if b.numel() > 0:
+                    bc(b)
+            if self.optimizer is not None:
+                for t in (self.optimizer.exp_avg, self.optimizer.exp_avg_sq, self.optimizer.step_dev):
+                    bc(t)
+
+    def _variant_key(self) -> Tuple[bool, ...]:
+        return tuple(s.will_update() for s in self._samplers)
+
+    def _capture(self, key: Tuple[bool, ...]):
+        """Capture the train step for one tuple of "updated" decisions (one extra eager pass first: a variant met for
+        the first time mid-training may run kernels that have not been launched yet)."""
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self._eager(apply_optimizer=False, key=key)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.grads.zero_()
+        graph = torch.cuda.CUDAGraph()
+        pool = next(iter(self._variants.values()))[0].pool() if self._variants else None  # variants replay serially
+        with torch.cuda.graph(graph, pool=pool):
+            self._eager(apply_optimizer=True, captured=True, key=key)
+        torch.cuda.synchronize(self.device)
+        self.graph = graph
+        self._variants[key] = (graph, self.total, self.losses)
+        return self._variants[key]
 
     def _field_ready(self) -> None:
         """Backward hook of a main field (fires on the stream that ran its encode backward).  Once every field has
@@ -150,7 +211,10 @@ class GraphedTrainStep:
         for k in BATCH_KEYS:
             self.static[k].copy_(batch[k], non_blocking=True)
 
-    def _eager(self, apply_optimizer: bool = True, captured: bool = False) -> None:
+    def _eager(self, apply_optimizer: bool = True, captured: bool = False,
+               key: Optional[Tuple[bool, ...]] = None) -> None:
+        if key is None:
+            key = self._variant_key()
         s = self.static if self.source is None else self.source.next()
         cur = torch.cuda.current_stream(self.device)
         zeroed = None
@@ -164,14 +228,23 @@ class GraphedTrainStep:
                 self.grads.zero_()
         bundle = RayBundle(origins=s["origins"], directions=s["directions"], pixel_area=s["pixel_area"],
                            camera_indices=s["camera_indices"])
-        _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"], "is_thermal": s["is_thermal"]})
+        for smp, upd in zip(self._samplers, key):
+            smp._forced_updated = upd
+        try:
+            _, self.losses, _ = self.model.get_train_loss_dict(bundle, {"image": s["image"],
+                                                                        "is_thermal": s["is_thermal"]})
+        finally:
+            for smp in self._samplers:
+                smp._forced_updated = None
         total = getattr(self.losses, "total", None)
         self.total = total if total is not None else sum(self.losses.values())
         self._early_done, self._ready_events = False, []
         self._adam_now = apply_optimizer and self._adam_in_graph
         self._zero_in_adam = captured
         if self._adam_now:
-            self.optimizer.tick()
+            # proposal networks that are not updated this iteration have no gradient in the reference: their
+            # optimiser is skipped (engine/optimizers.py:165-170)
+            self.optimizer.tick(inactive=[g for g, upd in zip(self._sampler_groups, key) if not upd])
         if zeroed is not None:
             cur.wait_stream(zeroed)
         self.total.backward()
@@ -186,15 +259,31 @@ class GraphedTrainStep:
     def step(self, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
         if batch is not None:
             self._load(batch)
-        if self.graph is not None:
+        key = self._variant_key()
+        if self.use_graph:
+            variant = self._variants.get(key)
+            if variant is None:
+                variant = self._capture(key)
+            self.graph, self.total, self.losses = variant
             self.graph.replay()
         else:
-            self._eager()
+            self._eager(key=key)
+        for smp, upd in zip(self._samplers, key):  # what generate_ray_samples does at its end
+            smp.mark_sampled(upd)
         if not self._comm_in_graph:
             self.grads.all_reduce_mean(self.group)
         if self.optimizer is not None and not self._adam_in_graph:
-            self.optimizer.step()
+            self.optimizer.step(inactive=[g for g, upd in zip(self._sampler_groups, key) if not upd])
         return self.total
+
+    def train_iteration(self, step: int, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
+        """Trainer.train_iteration with its callbacks (engine/trainer.py:262-275, 456-500): the
+        BEFORE_TRAIN_ITERATION hooks (proposal-weight annealing), the step, the AFTER_TRAIN_ITERATION hooks (the
+        samplers' update counters)."""
+        self.model.set_anneal_step(step)
+        total = self.step(batch)
+        self.model.step_cb(step)
+        return total
 
 
 class GraphedRenderChunk:

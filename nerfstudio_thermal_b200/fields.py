@@ -52,7 +52,7 @@ class Field(nn.Module):
     def _grid_coordinates(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
         """(x [N,3] in [0,1] zeroed outside the box, selector [N]) for the samples; the steps of
         fields/nerfacto_field.py:207-215 == fields/density_fields.py:96-103."""
-        lay = ray_samples._layout
+        lay = getattr(ray_samples, "_layout", None)  # None for reference-built RaySamples
         if _is_linf_contraction(self.spatial_distortion):
             if lay is not None:
                 return ops.sample_positions(lay.origins, lay.directions, lay.ebins)
@@ -173,7 +173,7 @@ class NerfactoField(Field):
         """Field.forward (fields/base_field.py:114-133).  For samples that carry a per-ray layout the density
         activation, the geo/SH/appearance concatenation (:335-344) and its backward run as one kernel each
         (`fused_ops.field_split`); the values are those of get_density + get_outputs."""
-        lay = ray_samples._layout
+        lay = getattr(ray_samples, "_layout", None)  # None for reference-built RaySamples
         if compute_normals or lay is None or not _is_linf_contraction(self.spatial_distortion) \
                 or ray_samples.camera_indices is None:
             return super().forward(ray_samples, compute_normals=compute_normals)
@@ -218,7 +218,7 @@ class NerfactoField(Field):
         if ray_samples.camera_indices is None:
             raise AttributeError("Camera indices are not provided.")
         shape = ray_samples.frustums.directions.shape[:-1]
-        lay = ray_samples._layout
+        lay = getattr(ray_samples, "_layout", None)  # None for reference-built RaySamples
         if lay is not None:  # SH once per ray, broadcast over the samples
             d = self.direction_encoding(get_normalized_directions(lay.directions))
             d = d[:, None, :].expand(*shape, d.shape[-1])
@@ -279,7 +279,7 @@ class HashMLPDensityField(Field):
 
     def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
         """fields/density_fields.py:95-118."""
-        lay = ray_samples._layout
+        lay = getattr(ray_samples, "_layout", None)  # None for reference-built RaySamples
         enc = self.encoding
         if (self.fuse and lay is not None and _is_linf_contraction(self.spatial_distortion) and not self.use_linear
                 and enc.features_per_level == 2 and enc.num_levels <= 8 and not enc.use_half_table

@@ -1,48 +1,29 @@
 """Per-ray losses of thermal-nerfacto (the row after the hot path).
 
-Mirrors `nerfstudio/model_components/losses.py:57-158` (interlevel / distortion) and `:593-651`
-(tv_pixel / cross_channel).  Round 1: torch expressions over the kernel outputs (same formulas as the
-reference, so loss values and gradients agree); fusing them into the compositing kernel is the next step.
+Entry points with the reference's names: `interlevel_loss` / `distortion_loss`
+(`nerfstudio/model_components/losses.py:114-158`) run as warp-per-ray kernels (csrc/tn_fused.cu: value and
+gradient from one launch, no [R,S,S] temporaries); `tv_pixel_loss` / `cross_channel_loss` (`:593-651`) are the
+torch fallbacks of the fused pixel-loss kernel (`fused_ops.pixel_losses`), used when the batch is not
+patch-ordered.
 """
 import torch
 from torch import Tensor
-
-EPS = 1.0e-7  # losses.py:39
 
 L1Loss = torch.nn.L1Loss
 MSELoss = torch.nn.MSELoss
 
 
-def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
-    """losses.py:57-84."""
-    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
-    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
-    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
-    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
-    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
-    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
-    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
-    return cy1_hi - cy1_lo
-
-
-def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
-    """losses.py:87-103."""
-    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
-    return torch.clip(w - w_outer, min=0) ** 2 / (w + EPS)
-
-
 def ray_samples_to_sdist(ray_samples) -> Tensor:
     """losses.py:106-111."""
     if getattr(ray_samples, "_layout", None) is not None:
-        return ray_samples._layout.sbins
+        return getattr(ray_samples, "_layout").sbins
     starts, ends = ray_samples.spacing_starts, ray_samples.spacing_ends
     return torch.cat([starts[..., 0], ends[..., -1:, 0]], dim=-1)
 
 
 def interlevel_loss(weights_list, ray_samples_list) -> Tensor:
     """losses.py:114-135: the final histogram (detached) must be bounded by every proposal histogram.  One
-    warp-per-ray kernel per proposal level computes the value and the gradient w.r.t. the proposal weights
-    (`outer`/`lossfun_outer` above are the same math as torch expressions, kept for callers and tests)."""
+    warp-per-ray kernel per proposal level computes the value and the gradient w.r.t. the proposal weights."""
     from . import fused_ops
 
     c = ray_samples_to_sdist(ray_samples_list[-1]).detach()
@@ -57,18 +38,9 @@ def interlevel_loss(weights_list, ray_samples_list) -> Tensor:
     return loss_interlevel
 
 
-def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
-    """losses.py:139-150."""
-    ut = (t[..., 1:] + t[..., :-1]) / 2
-    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
-    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
-    loss_intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
-    return loss_inter + loss_intra
-
-
 def distortion_loss(weights_list, ray_samples_list) -> Tensor:
     """losses.py:153-158: mean over rays of lossfun_distortion on the final level.  The O(S^2) pairwise term runs
-    in one warp-per-ray kernel (no [R,S,S] temporaries); `lossfun_distortion` above is the torch expression."""
+    in one warp-per-ray kernel (no [R,S,S] temporaries)."""
     from . import fused_ops
 
     c = ray_samples_to_sdist(ray_samples_list[-1])

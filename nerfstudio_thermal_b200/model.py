@@ -376,6 +376,17 @@ class ThermalNerfactoModel(nn.Module):
             if c.use_proposal_thermal_weight_anneal:
                 self.proposal_sampler_thermal.set_anneal(anneal)
 
+    def step_cb(self, step: int) -> None:
+        """The AFTER_TRAIN_ITERATION callbacks (models/nerfacto.py:289-295, models/thermal_nerfacto.py:244-250): the
+        proposal samplers count the iterations since their networks were last updated.  As in the reference, the
+        thermal sampler is only driven when `use_proposal_thermal_weight_anneal` is on (otherwise its `_step`
+        stays 0 and its proposal networks are updated on every iteration)."""
+        c = self.config
+        if c.use_proposal_weight_anneal:
+            self.proposal_sampler.step_cb(step)
+            if c.use_proposal_thermal_weight_anneal:
+                self.proposal_sampler_thermal.step_cb(step)
+
     # -------------------------------------------------------------------------------------- forward
     def forward(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
                 jitters_thermal: Optional[List[Tensor]] = None) -> Dict[str, Tensor]:
@@ -395,7 +406,7 @@ class ThermalNerfactoModel(nn.Module):
         if bg_per_ray is None and weights.dim() == 3:
             # the four renderer calls below (models/nerfacto.py:316-320) read the same weights: one launch
             r_, s_ = weights.shape[0], weights.shape[1]
-            lay = ray_samples._layout
+            lay = getattr(ray_samples, "_layout", None)
             in_place = lay is not None and lay.ebins.shape == (r_, s_ + 1)
             rgb, accumulation, depth, exp_raw, minmax = ops.render(
                 weights.reshape(r_, s_), colour, None if in_place else ray_samples.frustums.starts,

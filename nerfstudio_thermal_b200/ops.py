@@ -311,8 +311,10 @@ def piecewise_bins(nears: Tensor, fars: Tensor, num_samples: int, jitter: Option
 
 
 def pdf_sample(weights: Tensor, sbins_old: Tensor, nears: Tensor, fars: Tensor, num_samples: int,
-               jitter: Optional[Tensor], histogram_padding: float = 0.01, eps: float = 1e-5) -> Tuple[Tensor, Tensor]:
-    """PDFSampler (include_original=False): new (spacing bins, euclidean bins) [R, S_new+1]."""
+               jitter: Optional[Tensor], histogram_padding: float = 0.01, eps: float = 1e-5,
+               anneal: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """PDFSampler (include_original=False): new (spacing bins, euclidean bins) [R, S_new+1].
+    anneal: optional device scalar; the histogram is then weights ** anneal (evaluated in the kernel)."""
     w = _f32c(weights.detach())
     r, s_old = w.shape
     nb = num_samples + 1
@@ -325,7 +327,7 @@ def pdf_sample(weights: Tensor, sbins_old: Tensor, nears: Tensor, fars: Tensor, 
     eb = torch.empty_like(sb)
     jit, per_sample = _jitter_arg(jitter, r, nb)
     call("tn_pdf_sample", ptr(w), ptr(_f32c(sbins_old)), ptr(_f32c(nears).view(-1)), ptr(_f32c(fars).view(-1)), ptr(u),
-         ptr(jit), per_sample, r, s_old, num_samples, histogram_padding, eps, ptr(sb), ptr(eb), stream())
+         ptr(jit), per_sample, ptr(anneal), r, s_old, num_samples, histogram_padding, eps, ptr(sb), ptr(eb), stream())
     return sb, eb
 
 

@@ -91,8 +91,12 @@ class FusedAdam:
         self.params = grads.flatten_params()
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.params.device)
         g = len(self.names)
+        # device-side counters read by the kernel (capturable): [0] iterations = scheduler steps, [1+k] Adam steps of
+        # group k (torch's state['step']; lags the iteration count for groups that sat out steps without a gradient)
+        self.step_dev = torch.zeros(1 + g, dtype=torch.int32, device=self.params.device)
+        self._all_active = (1 << g) - 1
+        self._active = self._all_active
         self._begin = (c_int64 * g)(*[grads.group_ranges[n][0] for n in self.names])
         self._end = (c_int64 * g)(*[grads.group_ranges[n][1] for n in self.names])
         hyper: List[float] = []
@@ -104,18 +108,38 @@ class FusedAdam:
 
     @property
     def step_count(self) -> int:
-        return int(self.step_dev.item())
+        """Iterations taken (= scheduler steps)."""
+        return int(self.step_dev[0].item())
+
+    def group_step_counts(self) -> Dict[str, int]:
+        """Adam steps taken per group (torch's state['step'])."""
+        v = self.step_dev.tolist()
+        return {n: int(v[1 + i]) for i, n in enumerate(self.names)}
+
+    def active_mask(self, inactive: Optional[List[str]] = None) -> int:
+        """Bit mask of the groups that take part in a step; `inactive` names the groups without a gradient this
+        iteration (the reference skips them: torch.optim.Adam ignores parameters whose grad is None and
+        Optimizers.optimizer_scaler_step_all skips optimisers with no gradient at all, optimizers.py:150-170)."""
+        mask = self._all_active
+        for n in inactive or ():
+            if n in self.names:
+                mask &= ~(1 << self.names.index(n))
+        return mask
 
     def step(self, zero_grads: bool = False, inv_scale: Optional[Tensor] = None,
-             found_inf: Optional[Tensor] = None) -> None:
+             found_inf: Optional[Tensor] = None, inactive: Optional[List[str]] = None) -> None:
         """One optimiser + scheduler step of every group.  inv_scale / found_inf: the GradScaler's device scalars
-        (optimizers.py:150-163); `zero_grads` clears the gradient buffer in the same pass (zero_grad_all)."""
-        self.tick()
+        (optimizers.py:150-163); `zero_grads` clears the gradient buffer in the same pass (zero_grad_all);
+        `inactive`: groups without a gradient this iteration (left untouched, their step count does not advance;
+        their scheduler still steps, as in Trainer.train_iteration)."""
+        self.tick(inactive)
         self.step_range(0, self.params.numel(), zero_grads, inv_scale, found_inf)
 
-    def tick(self) -> None:
-        """Advance the device-side step counter (once per optimiser step, before any step_range of that step)."""
-        call("tn_counter_add", ptr(self.step_dev), 1, stream())
+    def tick(self, inactive: Optional[List[str]] = None) -> None:
+        """Advance the device-side counters (once per iteration, before any step_range of that iteration) and fix
+        which groups the step_range calls of this iteration update."""
+        self._active = self.active_mask(inactive)
+        call("tn_step_counters_tick", ptr(self.step_dev), len(self.names), self._active, stream())
 
     def step_range(self, begin: int, end: int, zero_grads: bool = False, inv_scale: Optional[Tensor] = None,
                    found_inf: Optional[Tensor] = None) -> None:
@@ -133,7 +157,7 @@ class FusedAdam:
         off = begin * 4
         call("tn_adam_step", ptr(self.params) + off, ptr(self.grads.flat) + off, ptr(self.exp_avg) + off,
              ptr(self.exp_avg_sq) + off, n, b, e, self._hyper, g, float(self.betas[0]), float(self.betas[1]),
-             ptr(self.step_dev), 0, ptr(inv_scale), ptr(found_inf), int(zero_grads), stream())
+             ptr(self.step_dev), 0, 1, self._active, ptr(inv_scale), ptr(found_inf), int(zero_grads), stream())
 
     def unscale_and_check(self, inv_scale: Optional[Tensor], found_inf: Tensor) -> None:
         """GradScaler.unscale_'s inf/nan check over the whole gradient buffer (the scaling itself is applied inside
@@ -149,27 +173,33 @@ class FusedAdam:
     # ---- checkpoint compatibility with the reference's per-group torch.optim.Adam state (trainer.py:389-453)
     def state_dict(self) -> Dict[str, dict]:
         k = self.step_count
+        steps = self.group_step_counts()
         out = {}
         for n in self.names:
             state, idx = {}, []
             for i, (p, off) in enumerate(self.grads.group_params(n)):
                 sl = slice(off, off + p.numel())
-                state[i] = {"step": torch.tensor(float(k)), "exp_avg": self.exp_avg[sl].view_as(p).clone(),
+                state[i] = {"step": torch.tensor(float(steps[n])), "exp_avg": self.exp_avg[sl].view_as(p).clone(),
                             "exp_avg_sq": self.exp_avg_sq[sl].view_as(p).clone()}
                 idx.append(i)
             c = self.config[n]
-            out[n] = {"state": state if k > 0 else {},
+            out[n] = {"state": state if steps[n] > 0 else {},
                       "param_groups": [{"lr": scheduled_lr(c, k), "betas": self.betas, "eps": c.eps,
                                         "weight_decay": c.weight_decay, "amsgrad": False, "maximize": False,
                                         "initial_lr": c.lr, "params": idx}]}
         return out
 
-    def load_state_dict(self, loaded: Dict[str, dict]) -> None:
-        """Optimizers.load_optimizers (optimizers.py:194-201): adopt the moments and the step count."""
-        steps = set()
+    def load_state_dict(self, loaded: Dict[str, dict], schedulers: Optional[Dict[str, dict]] = None) -> None:
+        """Optimizers.load_optimizers / load_schedulers (optimizers.py:194-210): adopt the moments, every group's own
+        step count (real reference checkpoints disagree across groups: the proposal networks sit out the iterations
+        on which they are not updated) and the schedulers' iteration count (`last_epoch`; without `schedulers` the
+        largest group step stands in for it)."""
+        counts = self.step_dev.tolist()
         for n, sd in loaded.items():
             if n not in self.config:
                 raise KeyError(f"unknown parameter group {n}")
+            gi = self.names.index(n)
+            group_steps = set()
             for i, (p, off) in enumerate(self.grads.group_params(n)):
                 st = sd["state"].get(i)
                 if st is None:
@@ -177,8 +207,11 @@ class FusedAdam:
                 sl = slice(off, off + p.numel())
                 self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1))
                 self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
-                steps.add(int(float(st["step"])))
-        if len(steps) > 1:
-            raise ValueError(f"groups disagree on the step count: {sorted(steps)} (one counter drives all groups)")
-        if steps:
-            self.step_dev.fill_(steps.pop())
+                group_steps.add(int(float(st["step"])))
+            if len(group_steps) > 1:
+                # one counter per group: parameters of a group that disagree cannot be represented
+                raise ValueError(f"group {n}: parameters disagree on the step count: {sorted(group_steps)}")
+            counts[1 + gi] = group_steps.pop() if group_steps else 0
+        epochs = [int(v["last_epoch"]) for k, v in (schedulers or {}).items() if k in self.config and "last_epoch" in v]
+        counts[0] = max(epochs) if epochs else max(counts[1:], default=0)
+        self.step_dev.copy_(torch.tensor(counts, dtype=torch.int32))

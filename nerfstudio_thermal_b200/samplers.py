@@ -148,7 +148,9 @@ class PDFSampler(Sampler):
 
     def generate_ray_samples(self, ray_bundle: Optional[RayBundle] = None, ray_samples: Optional[RaySamples] = None,
                              weights: Optional[Tensor] = None, num_samples: Optional[int] = None, eps: float = 1e-5,
-                             jitter: Optional[Tensor] = None) -> RaySamples:
+                             jitter: Optional[Tensor] = None, anneal: Optional[Tensor] = None) -> RaySamples:
+        """`anneal` (extension): device scalar a; the histogram is then weights ** a, formed inside the kernel
+        (ProposalNetworkSampler's annealing with an exponent a captured CUDA graph can follow)."""
         if ray_samples is None or ray_bundle is None:
             raise ValueError("ray_samples and ray_bundle must be provided")
         assert weights is not None, "weights must be provided"
@@ -157,7 +159,7 @@ class PDFSampler(Sampler):
         assert ray_samples.spacing_starts is not None and ray_samples.spacing_ends is not None, \
             "ray_sample spacing_starts and spacing_ends must be provided"
         assert ray_samples.spacing_to_euclidean_fn is not None, "ray_samples.spacing_to_euclidean_fn must be provided"
-        lay = ray_samples._layout
+        lay = getattr(ray_samples, "_layout", None)  # reference-built RaySamples carry no layout
         if lay is not None:
             existing_bins = lay.sbins
         else:
@@ -172,7 +174,7 @@ class PDFSampler(Sampler):
         nears = fn.nears if piecewise else torch.zeros(num_rays, device=existing_bins.device)
         fars = fn.fars if piecewise else torch.ones(num_rays, device=existing_bins.device)
         sbins, ebins = ops.pdf_sample(weights[..., 0], existing_bins, nears, fars, num_samples, jitter,
-                                      self.histogram_padding, eps)
+                                      self.histogram_padding, eps, anneal=anneal)
         if self.include_original:
             sbins, _ = torch.sort(torch.cat([existing_bins, sbins], -1), -1)
             ebins = fn(sbins)
@@ -204,13 +206,36 @@ class ProposalNetworkSampler(Sampler):
         self._anneal = 1.0
         self._steps_since_update = 0
         self._step = 0
+        # device copy of the anneal exponent: the PDF kernel reads it at run time, so a CUDA graph captured at one
+        # step follows the schedule on later replays (set_anneal rewrites it before the replay)
+        self._anneal_dev: Optional[Tensor] = None
+        # engine.GraphedTrainStep pins the "updated" decision while it captures a graph variant and applies the
+        # bookkeeping itself after each replay
+        self._forced_updated: Optional[bool] = None
 
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
+        if self._anneal_dev is not None:
+            self._anneal_dev.fill_(float(anneal))
+
+    def _anneal_tensor(self, device) -> Tensor:
+        if self._anneal_dev is None or self._anneal_dev.device != device:
+            self._anneal_dev = torch.full((1,), float(self._anneal), dtype=torch.float32, device=device)
+        return self._anneal_dev
 
     def step_cb(self, step):
         self._step = step
         self._steps_since_update += 1
+
+    def will_update(self) -> bool:
+        """The `updated` decision the next generate_ray_samples call takes (ray_samplers.py:591)."""
+        return bool(self._steps_since_update > self.update_sched(self._step) or self._step < 10)
+
+    def mark_sampled(self, updated: bool) -> None:
+        """The bookkeeping generate_ray_samples does at its end (ray_samplers.py:612-613), for runners that replay
+        a captured forward instead of calling it."""
+        if updated:
+            self._steps_since_update = 0
 
     @staticmethod
     def _density(density_fn: Callable, ray_samples: RaySamples) -> Tensor:
@@ -246,7 +271,8 @@ class ProposalNetworkSampler(Sampler):
         n = self.num_proposal_network_iterations
         weights = None
         ray_samples = None
-        updated = self._steps_since_update > self.update_sched(self._step) or self._step < 10
+        updated = self.will_update() if self._forced_updated is None else self._forced_updated
+        on_device = ray_bundle.origins.is_cuda
         for i_level in range(n + 1):
             is_prop = i_level < n
             num_samples = self.num_proposal_samples_per_ray[i_level] if is_prop else self.num_nerf_samples_per_ray
@@ -255,9 +281,14 @@ class ProposalNetworkSampler(Sampler):
                 ray_samples = self.initial_sampler(ray_bundle, num_samples=num_samples, jitter=jit)
             else:
                 assert weights is not None
-                annealed_weights = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
-                ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed_weights, num_samples=num_samples,
-                                               jitter=jit)
+                if on_device and isinstance(self.pdf_sampler, PDFSampler):
+                    # weights ** anneal (:602) inside the PDF kernel, exponent read from the device
+                    ray_samples = self.pdf_sampler(ray_bundle, ray_samples, weights, num_samples=num_samples,
+                                                   jitter=jit, anneal=self._anneal_tensor(ray_bundle.origins.device))
+                else:
+                    annealed_weights = weights if self._anneal == 1.0 else torch.pow(weights, self._anneal)
+                    ray_samples = self.pdf_sampler(ray_bundle, ray_samples, annealed_weights,
+                                                   num_samples=num_samples, jitter=jit)
             if is_prop:
                 if updated:
                     density = self._density(density_fns[i_level], ray_samples)
@@ -267,7 +298,7 @@ class ProposalNetworkSampler(Sampler):
                 weights = ray_samples.get_weights(density)
                 weights_list.append(weights)
                 ray_samples_list.append(ray_samples)
-        if updated:
-            self._steps_since_update = 0
+        if self._forced_updated is None:
+            self.mark_sampled(updated)
         assert ray_samples is not None
         return ray_samples, weights_list, ray_samples_list

@@ -12,6 +12,10 @@ results, same op order) against golden vectors produced by importing the UNMODIF
 `tests/golden/*.npz`, test `tests/test_oracle_golden.py`).  The reference's own tests pin no numeric
 values on this path, so those generated vectors are the pin.
 
+Device: every function builds its constants on the device of its inputs, so the same code runs on `cuda`
+unchanged -- that is the north star's literal parity target (the reference's `implementation="torch"` ops on the
+B200) and what the full-size `-m gpu` parity tests compare the kernels with (tests/test_gpu_fullsize.py).
+
 All file:line citations are relative to /root/reference/nerfstudio/.
 """
 

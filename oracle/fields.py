@@ -101,7 +101,7 @@ def density_field(sd: Dict[str, torch.Tensor], prefix: str, positions: torch.Ten
     positions [*bs,3] world space -> (density [*bs,1], geo features [*bs,15]).
     """
     x, selector = normalize_positions(positions)
-    scal = hash_scalings(num_levels, base_res, max_res)
+    scal = hash_scalings(num_levels, base_res, max_res).to(x.device)
     enc = hash_encode(x.view(-1, 3), sd[f"{prefix}.mlp_base.model.0.hash_table"], scal, log2_hashmap_size)
     ws, bs = _linear_stack(sd, f"{prefix}.mlp_base.model.1")
     h = mlp_forward(enc, ws, bs).view(*positions.shape[:-1], -1)
@@ -116,7 +116,7 @@ def proposal_density(sd: Dict[str, torch.Tensor], prefix: str, positions: torch.
     """HashMLPDensityField.get_density via Field.density_fn, fields/density_fields.py:95-118,
     fields/base_field.py:48-69."""
     x, selector = normalize_positions(positions)
-    scal = hash_scalings(num_levels, base_res, max_res)
+    scal = hash_scalings(num_levels, base_res, max_res).to(x.device)
     enc = hash_encode(x.view(-1, 3), sd[f"{prefix}.mlp_base.0.hash_table"], scal, log2_hashmap_size)
     ws, bs = _linear_stack(sd, f"{prefix}.mlp_base.1")
     raw = mlp_forward(enc, ws, bs).view(*positions.shape[:-1], -1).to(x)
@@ -137,9 +137,9 @@ def colour_head(sd: Dict[str, torch.Tensor], prefix: str, directions: torch.Tens
     if training:
         emb = emb_w[camera_indices.squeeze()]
     elif use_average_appearance_embedding:
-        emb = torch.ones((*directions.shape[:-1], emb_w.shape[1])) * emb_w.mean(0)
+        emb = torch.ones((*directions.shape[:-1], emb_w.shape[1]), device=emb_w.device) * emb_w.mean(0)
     else:
-        emb = torch.zeros((*directions.shape[:-1], emb_w.shape[1]))
+        emb = torch.zeros((*directions.shape[:-1], emb_w.shape[1]), device=emb_w.device)
     h = torch.cat([d, geo.reshape(-1, geo.shape[-1]), emb.reshape(-1, emb_w.shape[1])], dim=-1)
     ws, bs = _linear_stack(sd, f"{prefix}.mlp_head")
     out = mlp_forward(h, ws, bs, out_activation="sigmoid")

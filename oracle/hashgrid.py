@@ -33,7 +33,7 @@ def hash_scalings(num_levels: int, min_res: int, max_res: int) -> torch.Tensor:
 
 def _hash(coords: torch.Tensor, table_size: int, level_offset: torch.Tensor) -> torch.Tensor:
     """encodings.py:401-418: int32 coords * int64 primes, xor, mod T, + l*T."""
-    prod = coords * torch.tensor(_PRIMES)
+    prod = coords * torch.tensor(_PRIMES, device=coords.device)
     h = torch.bitwise_xor(torch.bitwise_xor(prod[..., 0], prod[..., 1]), prod[..., 2])
     h = h % table_size
     return h + level_offset
@@ -50,7 +50,7 @@ def hash_corner_indices(x: torch.Tensor, scalings: torch.Tensor, log2_table_size
     hi = torch.ceil(scaled).type(torch.int32)
     lo = torch.floor(scaled).type(torch.int32)
     offset = scaled - lo
-    level_offset = torch.arange(num_levels) * table_size
+    level_offset = torch.arange(num_levels, device=x.device) * table_size
     idx = []
     for use_ceil in CORNER_USES_CEIL:
         coords = torch.stack([hi[..., a] if use_ceil[a] else lo[..., a] for a in range(3)], dim=-1)

@@ -75,7 +75,7 @@ def exp_map_so3xr3(tangent: torch.Tensor) -> torch.Tensor:
     inv = 1.0 / ang
     fac1 = inv * ang.sin()
     fac2 = inv * inv * (1.0 - ang.cos())
-    sk = torch.zeros((log_rot.shape[0], 3, 3), dtype=log_rot.dtype)
+    sk = torch.zeros((log_rot.shape[0], 3, 3), dtype=log_rot.dtype, device=log_rot.device)
     sk[:, 0, 1] = -log_rot[:, 2]
     sk[:, 0, 2] = log_rot[:, 1]
     sk[:, 1, 0] = log_rot[:, 2]
@@ -83,8 +83,8 @@ def exp_map_so3xr3(tangent: torch.Tensor) -> torch.Tensor:
     sk[:, 2, 0] = -log_rot[:, 1]
     sk[:, 2, 1] = log_rot[:, 0]
     sk2 = torch.bmm(sk, sk)
-    ret = torch.zeros(tangent.shape[0], 3, 4, dtype=tangent.dtype)
-    ret[:, :3, :3] = fac1[:, None, None] * sk + fac2[:, None, None] * sk2 + torch.eye(3)[None]
+    ret = torch.zeros(tangent.shape[0], 3, 4, dtype=tangent.dtype, device=tangent.device)
+    ret[:, :3, :3] = fac1[:, None, None] * sk + fac2[:, None, None] * sk2 + torch.eye(3, device=tangent.device)[None]
     ret[:, :3, 3] = tangent[:, :3]
     return ret
 
@@ -95,7 +95,7 @@ def apply_camera_optimizer(pose_adjustment: torch.Tensor, frozen: torch.Tensor, 
     frozen[num_cams] bool marks non-trainable cameras (identity correction)."""
     idx = camera_indices.squeeze()
     corr = exp_map_so3xr3(pose_adjustment[idx, :])
-    corr[frozen[idx]] = torch.eye(4)[:3, :4]
+    corr[frozen[idx]] = torch.eye(4, device=corr.device)[:3, :4]
     origins = origins + corr[:, :3, 3]
     directions = torch.bmm(corr[:, :3, :3], directions[..., None]).squeeze()
     return origins, directions
@@ -157,6 +157,9 @@ def _get_outputs(sd, cfg, prefix, samples, weights_list, samples_list, training)
     for i in range(len(cfg.num_proposal_samples_per_ray)):
         out[f"prop_depth_{i}"] = R_.render_depth_median(weights_list[i], samples_list[i].starts, samples_list[i].ends)
     out["_field_rgb"] = col
+    # checker-only extras (not reference outputs): what the median-depth searchsorted saw
+    out["_weights"] = [x.detach() for x in weights_list]
+    out["_steps"] = [((x.starts + x.ends) / 2).detach() for x in samples_list]
     return out
 
 
@@ -176,7 +179,7 @@ def thermal_nerfacto_forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, ori
     nears = torch.ones_like(origins[..., 0:1]) * near
     fars = torch.ones_like(origins[..., 0:1]) * cfg.far_plane
     n_lvls = len(cfg.num_proposal_samples_per_ray) + 1
-    frozen_rgb = torch.tensor([bool(t) for t in cfg.is_thermal_cameras])
+    frozen_rgb = torch.tensor([bool(t) for t in cfg.is_thermal_cameras], device=origins.device)
     frozen_thermal = ~frozen_rgb
 
     def _draw(given):
@@ -189,7 +192,7 @@ def thermal_nerfacto_forward(sd: Dict[str, torch.Tensor], cfg: OracleConfig, ori
 
         def __getitem__(self, i):
             while len(self) <= i:
-                self.append(torch.rand((R, 1)))
+                self.append(torch.rand((R, 1)).to(origins.device))
             return list.__getitem__(self, i)
 
     jit = _draw(jitters)
@@ -273,7 +276,7 @@ def distortion_loss(weights_list, samples_list) -> torch.Tensor:
 
 def _rgb_to_rgbt(image, is_thermal):
     """utils/rgbt_utils.py:6-33."""
-    rgbt = torch.zeros(image.shape[:-1] + (4,))
+    rgbt = torch.zeros(image.shape[:-1] + (4,), device=image.device)
     rgbt[..., :3] = torch.einsum("ij,i->ij", image, 1 - is_thermal)
     rgbt[..., 3] = image[..., 0] * is_thermal
     return rgbt
@@ -314,7 +317,7 @@ def thermal_nerfacto_losses(sd, cfg: OracleConfig, outputs: Dict, image: torch.T
     if cfg.density_mode != "rgb_only":
         pred = torch.cat((outputs["rgb"], outputs["rgb_thermal"]), dim=1)
     else:
-        pred = torch.cat((outputs["rgb"], torch.zeros(outputs["rgb"].shape[0], 1)), dim=1)
+        pred = torch.cat((outputs["rgb"], torch.zeros(outputs["rgb"].shape[0], 1, device=outputs["rgb"].device)), dim=1)
     if cfg.background_color == "random":
         raise NotImplementedError("oracle covers last_sample/black/white backgrounds")
     gt = _rgb_to_rgbt(image, is_thermal)

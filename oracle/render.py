@@ -43,7 +43,7 @@ def render_depth_median(weights: torch.Tensor, starts: torch.Tensor, ends: torch
     """DepthRenderer(method="median"), renderers.py:547-557."""
     steps = (starts + ends) / 2
     cum = torch.cumsum(weights[..., 0], dim=-1)
-    split = torch.ones((*weights.shape[:-2], 1)) * 0.5
+    split = torch.ones((*weights.shape[:-2], 1), device=weights.device) * 0.5
     idx = torch.searchsorted(cum, split, side="left")
     idx = torch.clamp(idx, 0, steps.shape[-2] - 1)
     return torch.gather(steps[..., 0], dim=-1, index=idx)

@@ -53,12 +53,12 @@ def _make_samples(origins, directions, camera_indices, bins, s_near, s_far) -> O
     )
 
 
-def initial_bins(num_rays: int, num_samples: int, jitter: Optional[torch.Tensor]) -> torch.Tensor:
+def initial_bins(num_rays: int, num_samples: int, jitter: Optional[torch.Tensor], device=None) -> torch.Tensor:
     """SpacedSampler.generate_ray_samples, ray_samplers.py:100-111.
 
     jitter: None (eval) or the [R,1] tensor the reference draws with torch.rand (single_jitter=True).
     """
-    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    bins = torch.linspace(0.0, 1.0, num_samples + 1).to(device)[None, ...]  # made on the CPU, then moved (:100)
     if jitter is not None:
         centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
         upper = torch.cat([centers, bins[..., -1:]], -1)
@@ -68,7 +68,7 @@ def initial_bins(num_rays: int, num_samples: int, jitter: Optional[torch.Tensor]
 
 
 def initial_samples(origins, directions, camera_indices, nears, fars, num_samples, jitter) -> OracleSamples:
-    bins = initial_bins(origins.shape[0], num_samples, jitter)
+    bins = initial_bins(origins.shape[0], num_samples, jitter, origins.device)
     return _make_samples(origins, directions, camera_indices, bins, piecewise_spacing(nears), piecewise_spacing(fars))
 
 
@@ -88,7 +88,7 @@ def pdf_resample(prev: OracleSamples, weights: torch.Tensor, num_samples: int, j
     cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
 
-    u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
+    u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins).to(cdf.device)
     if jitter is not None:
         u = u.expand(size=(*cdf.shape[:-1], num_bins))
         u = u + jitter / num_bins
@@ -110,9 +110,20 @@ def pdf_resample(prev: OracleSamples, weights: torch.Tensor, num_samples: int, j
     return _make_samples(prev.origins, prev.directions, prev.camera_indices, bins, prev.s_near, prev.s_far)
 
 
+# Checker-only switch (conditioning experiments of the parity tests): move every sample position this many float32
+# ulps towards +inf before it is used.  0 = the reference's arithmetic.
+POSITION_ULP_SHIFT = 0
+
+
 def sample_positions(s: OracleSamples) -> torch.Tensor:
     """Frustums.get_positions, cameras/rays.py:49-58 -> [R,S,3]."""
-    return s.origins[:, None, :] + s.directions[:, None, :] * (s.starts + s.ends) / 2
+    pos = s.origins[:, None, :] + s.directions[:, None, :] * (s.starts + s.ends) / 2
+    if POSITION_ULP_SHIFT:
+        shifted = pos.detach()
+        for _ in range(POSITION_ULP_SHIFT):
+            shifted = torch.nextafter(shifted, torch.full_like(shifted, float("inf")))
+        pos = pos + (shifted - pos.detach())  # same gradient path, values moved by whole ulps
+    return pos
 
 
 def sample_weights(deltas: torch.Tensor, densities: torch.Tensor) -> torch.Tensor:
@@ -120,6 +131,6 @@ def sample_weights(deltas: torch.Tensor, densities: torch.Tensor) -> torch.Tenso
     dd = deltas * densities
     alphas = 1 - torch.exp(-dd)
     trans = torch.cumsum(dd[..., :-1, :], dim=-2)
-    trans = torch.cat([torch.zeros((*trans.shape[:1], 1, 1)), trans], dim=-2)
+    trans = torch.cat([torch.zeros((*trans.shape[:1], 1, 1), device=densities.device), trans], dim=-2)
     trans = torch.exp(-trans)
     return torch.nan_to_num(alphas * trans)

@@ -147,10 +147,10 @@ def test_adam_step_argument_errors():
     hyper = float_array([1e-2, -1, 1e-8, 1e-15, 0, 0, 0, 1])
     with pytest.raises(TnKernelError, match="range"):
         call("tn_adam_step", ptr(x), ptr(x), ptr(x), ptr(x), 16, (c_int64 * 1)(0), (c_int64 * 1)(17), hyper, 1, 0.9,
-             0.999, None, 1, None, None, 0, stream())
+             0.999, None, 1, 0, 1, None, None, 0, stream())
     with pytest.raises(TnKernelError, match="step"):
         call("tn_adam_step", ptr(x), ptr(x), ptr(x), ptr(x), 16, (c_int64 * 1)(0), (c_int64 * 1)(16), hyper, 1, 0.9,
-             0.999, None, 0, None, None, 0, stream())
+             0.999, None, 0, 0, 1, None, None, 0, stream())
 
 
 def _small_model_and_batch(golden):
@@ -225,3 +225,57 @@ def test_two_stream_branches_give_the_same_gradients_in_a_captured_step(golden):
         assert l1[k] == pytest.approx(l0[k], rel=1e-5, abs=1e-9), k
     rel = ((g0 - g1).double().norm() / g0.double().norm()).item()
     assert rel <= 1e-5, rel
+
+
+def test_inactive_groups_follow_torch_adam_with_grad_none():
+    """A group without a gradient is skipped exactly like torch.optim.Adam skips parameters whose grad is None
+    (engine/optimizers.py:150-170): its parameters and moments stay, its step count does not advance, its
+    scheduler still steps; per-group step counts drive the bias corrections; state_dict / load_state_dict keep
+    groups' differing step counts (a real reference checkpoint has them: ADVICE r1)."""
+    shapes = {"a": [(33, 2), (7,)], "b": [(5, 3)], "c": [(9,)]}
+    groups = _random_groups(5, shapes)
+    cfg = {"a": poptim.AdamGroupConfig(lr=1e-2, lr_final=1e-4, max_steps=100),
+           "b": poptim.AdamGroupConfig(lr=3e-3, lr_final=1e-4, max_steps=50),
+           "c": poptim.AdamGroupConfig(lr=1e-3)}
+    buf = FlatGradBuffer.from_param_groups(groups)
+    opt = poptim.FusedAdam(buf, cfg)
+    tgroups = {n: [torch.nn.Parameter(p.detach().clone()) for p in ps] for n, ps in groups.items()}
+    topt = {n: torch.optim.Adam(ps, lr=cfg[n].lr, eps=cfg[n].eps) for n, ps in tgroups.items()}
+    sched = {n: torch.optim.lr_scheduler.LambdaLR(
+        topt[n], lambda k, c=cfg[n]: poptim.scheduled_lr(c, k) / c.lr) for n in topt}
+    gen = torch.Generator().manual_seed(6)
+    pattern = [[], ["b"], ["b"], [], ["b", "c"], []]  # groups without a gradient per iteration
+    for inactive in pattern:
+        for n, ps in groups.items():
+            for p, tp in zip(ps, tgroups[n]):
+                gr = torch.randn(p.shape, generator=gen).to(DEV)
+                p.grad.copy_(gr)
+                tp.grad = None if n in inactive else gr.clone()
+        opt.step(inactive=inactive)
+        for n in topt:
+            if n not in inactive:
+                topt[n].step()
+            sched[n].step()
+    assert opt.step_count == len(pattern)
+    assert opt.group_step_counts() == {"a": 6, "b": 3, "c": 5}
+    for n, ps in groups.items():
+        for p, tp in zip(ps, tgroups[n]):
+            torch.testing.assert_close(p.detach(), tp.detach(), rtol=2e-5, atol=1e-7)
+    sd = opt.state_dict()
+    assert float(sd["b"]["state"][0]["step"]) == 3.0 and float(sd["a"]["state"][0]["step"]) == 6.0
+    for n in topt:  # the reference's own optimisers accept it, and the moments agree
+        tsd = topt[n].state_dict()
+        for i in tsd["state"]:
+            torch.testing.assert_close(sd[n]["state"][i]["exp_avg"], tsd["state"][i]["exp_avg"], rtol=2e-5, atol=1e-9)
+            assert float(tsd["state"][i]["step"]) == float(sd[n]["state"][i]["step"])
+    # a fresh optimiser adopts differing step counts and continues identically
+    groups2 = {n: [torch.nn.Parameter(p.detach().clone()) for p in ps] for n, ps in groups.items()}
+    buf2 = FlatGradBuffer.from_param_groups(groups2)
+    opt2 = poptim.FusedAdam(buf2, cfg)
+    opt2.load_state_dict({n: topt[n].state_dict() for n in topt},
+                         schedulers={n: sched[n].state_dict() for n in sched})
+    assert opt2.step_count == len(pattern) and opt2.group_step_counts() == opt.group_step_counts()
+    buf.flat.normal_(generator=None)
+    buf2.flat.copy_(buf.flat)
+    opt.step(); opt2.step()
+    torch.testing.assert_close(opt2.params, opt.params, rtol=0, atol=0)

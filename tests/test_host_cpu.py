@@ -253,6 +253,9 @@ def test_reference_checkpoint_round_trip(golden):
         model = cfg.setup(num_train_data=8, metadata={"is_thermal": [0] * 4 + [1] * 4})
         ckpt = {"step": 1234, "pipeline": {prefix + k: v for k, v in sd.items()}, "optimizers": {}, "scalers": {}}
         ckpt["pipeline"]["datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(8, 6)  # non-model key
+        # a real step-*.ckpt carries the LPIPS network of NerfactoModel (models/nerfacto.py:253): ignored, not an error
+        ckpt["pipeline"][prefix + "lpips.net.lin0.model.1.weight"] = torch.zeros(1, 64, 1, 1)
+        ckpt["pipeline"][prefix + "lpips.net.scaling_layer.shift"] = torch.zeros(1, 3, 1, 1)
         assert checkpoint.load_checkpoint(ckpt, model) == 1235
         assert model.step == 1234
         for k, v in model.state_dict().items():
@@ -279,7 +282,7 @@ def test_ctypes_table_matches_header_prototypes():
         arg = " ".join(arg.split())
         if "*" in arg:
             return "ptr"
-        for t, k in (("int64_t", "i64"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
+        for t, k in (("int64_t", "i64"), ("uint32_t", "u32"), ("double", "f64"), ("float", "f32"), ("int", "i32")):
             if re.search(rf"\b{t}\b", arg):
                 return k
         raise AssertionError(f"unparsed argument {arg!r}")
@@ -289,6 +292,8 @@ def test_ctypes_table_matches_header_prototypes():
             return "i64"
         if t in (C.c_int, C.c_int32):
             return "i32"
+        if t in (C.c_uint, C.c_uint32):
+            return "u32"
         if t is C.c_float:
             return "f32"
         if t is C.c_double:
