@@ -37,11 +37,12 @@ inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_
 
 constexpr int kNumSMs = 148;  // B200
 
-// tuning knob (host): largest level scale whose table REDs are aggregated over runs of equal cells
-inline float agg_threshold(const char* env, float dflt) {
-  const char* v = getenv(env);
-  return v ? (float)atof(v) : dflt;
-}
+// Tuning knobs (host): the largest level scale whose table REDs are aggregated over equal cells of a warp.  The
+// environment is consulted ONCE, when the library first needs the value (no per-launch getenv, no state that changes
+// after that): TN_AGG_ENC / TN_AGG_ENC_PATCH (encode backward, plain / patch tiles), TN_AGG_PROP (proposal backward).
+float agg_threshold_enc();
+float agg_threshold_enc_patch();
+float agg_threshold_prop();
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

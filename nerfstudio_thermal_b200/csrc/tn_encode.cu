@@ -6,15 +6,23 @@
 // like the reference's chain of separate torch ops, which makes corner indices AND interpolated features
 // bit-identical to the reference for identical inputs.
 //
-// Mapping: one thread per point, 128 points per CTA, levels looped inside the thread (unrolled by two so
-// sixteen independent 8-byte gathers are in flight per thread).  The [128 x L*F] output tile is staged in
-// shared memory (rows rotated to dodge bank conflicts) and leaves the SM as one contiguous, fully
-// coalesced 128*L*F*4-byte run.  Tables live in L2 (64 MB fp32 / 32 MB fp16 at T=2^19 vs 126 MB of L2).
+// Mapping: one thread per point, a tile of consecutive points per CTA, levels looped inside the thread (unrolled by
+// two so sixteen independent 8-byte gathers are in flight per thread).  The [tile x L*F] output tile is staged in
+// shared memory (rows rotated to dodge bank conflicts) and leaves the SM as one contiguous, fully coalesced run.
+// Tables live in L2 (64 MB fp32 / 32 MB fp16 at T=2^19 vs 126 MB of L2).
 //
-// Backward: the same index math, then one vectorised RED (red.global.add.v2.f32) per corner.  On coarse
-// levels, where the consecutive samples of a ray sit in the same cell, lanes holding the same cell form
-// contiguous runs; a segmented shuffle reduction folds each run into its head lane so that one RED per
-// corner per run is issued instead of one per lane (warp-aggregated atomics).
+// Which point a LANE owns is a permutation inside the tile.  When the caller says the points are ray samples
+// (samples_per_ray = S, S % 8 == 0), a tile is 4 rays x S samples (one 2x2 pixel patch of the reference's patch
+// sampler, data/pixel_samplers.py:389-438, or four neighbouring pixels of a render chunk) and a warp owns 8
+// consecutive samples of each of the 4 rays: those 32 points share far more grid cells than 32 consecutive samples
+// of one ray (measured on the bench batch: 0.57 distinct cells per point and level instead of 0.82), so the
+// gathers of a warp coalesce into fewer L1 wavefronts and the backward issues fewer REDs.
+//
+// Backward: the same index math, then one vectorised RED (red.global.add.v2.f32) per corner.  The kernel is bound
+// by RED lanes (L2 atomic units), not bytes: lanes of a warp that hold the SAME cell are found with
+// match.any on the cell key -- anywhere in the warp, not only neighbouring lanes -- their 8 corner gradients are
+// folded into the lowest such lane by a peer-tree of shuffles, and only that lane issues the 8 REDs
+// (warp-aggregated atomics).  Levels finer than the aggregation threshold have no duplicates worth the shuffles.
 #include "tn_encode_core.cuh"
 
 namespace tn {
@@ -30,25 +38,32 @@ constexpr int kLevelBatch = 2;  // levels whose 8-corner gathers are issued back
 
 // JAC: also store d(feature)/d(x) (times the level scale) as jac[L][N][F][3].  The backward then needs no second
 // gather of the corner rows for dL/dx: 12*F bytes/level of streaming instead of 8 L2 gathers/level.
+// tile row owned by a thread: identity, or (patch mode) warp w / lane -> ray lane>>3, sample 8w + (lane&7)
+__device__ __forceinline__ int tile_row(int tid, int patch_S) {
+  return patch_S ? ((tid & 31) >> 3) * patch_S + ((tid >> 5) << 3) + (tid & 7) : tid;
+}
+
 template <int F, bool HALF, bool WRITE_IDX, bool JAC = false>
-__global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
-                                                           LevelScales sc, int64_t N, int L, int log2T,
-                                                           float* __restrict__ out, int32_t* __restrict__ idx_out,
-                                                           float* __restrict__ jac) {
+__global__ void __launch_bounds__(kMaxTile, 3) hash_fwd_kernel(const float* __restrict__ x,
+                                                               const void* __restrict__ table, LevelScales sc,
+                                                               int64_t N, int L, int log2T, int patch_S,
+                                                               float* __restrict__ out, int32_t* __restrict__ idx_out,
+                                                               float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   __shared__ float s_scale[TN_MAX_LEVELS];
   float* tile = reinterpret_cast<float*>(smem4);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, kTile = blockDim.x;
   if (tid < TN_MAX_LEVELS) s_scale[tid] = sc.s[tid];
-  const int64_t base_pt = (int64_t)blockIdx.x * kPts;
-  const int64_t p = base_pt + tid;
+  const int64_t base_pt = (int64_t)blockIdx.x * kTile;
+  const int row_t = tile_row(tid, patch_S);
+  const int64_t p = base_pt + row_t;
   const bool valid = p < N;
   const uint32_t T = 1u << log2T, mask = T - 1u;
   float x0 = 0.f, x1 = 0.f, x2 = 0.f;
   if (valid) {
     x0 = __ldg(x + 3 * p); x1 = __ldg(x + 3 * p + 1); x2 = __ldg(x + 3 * p + 2);
   }
-  const int rowmod = tid % L;
+  const int rowmod = row_t % L;
   __syncthreads();
 #pragma unroll 1
   for (int l0 = 0; l0 < L; l0 += kLevelBatch) {
@@ -79,7 +94,7 @@ __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restri
         const float mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
         int r = l + rowmod;
         if (r >= L) r -= L;
-        float* dst = tile + (tid * L + r) * F;
+        float* dst = tile + (row_t * L + r) * F;
 #pragma unroll
         for (int j = 0; j < F; ++j) {
           // encodings.py:449-459, same association
@@ -107,9 +122,9 @@ __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restri
   }
   __syncthreads();
   // contiguous, coalesced write-out of the tile (rows base_pt .. base_pt+rows-1 are adjacent in `out`)
-  const int rows = (int)min((int64_t)kPts, N - base_pt);
+  const int rows = (int)min((int64_t)kTile, N - base_pt);
   float* gout = out + base_pt * (int64_t)(L * F);
-  for (int i = tid; i < rows * L; i += kPts) {
+  for (int i = tid; i < rows * L; i += kTile) {
     const int row = i / L, l = i - row * L;
     const float* src = tile + tile_pos(row, l, L, F);
     if constexpr (F == 2) {
@@ -124,22 +139,51 @@ __global__ void __launch_bounds__(kPts, 6) hash_fwd_kernel(const float* __restri
   }
 }
 
+// Fold the corner gradients of all lanes that hold the same cell into the lowest such lane (peer tree: log2 of the
+// largest group rounds, each a shuffle per value).  Returns true on the lane that must issue the REDs.
+template <int F>
+__device__ __forceinline__ bool aggregate_equal_cells(uint64_t key, int lane, float (&gc)[8][F]) {
+  const unsigned all = 0xffffffffu;
+  const unsigned peers_all = __match_any_sync(all, key);
+  int rel = __popc(peers_all & ((1u << lane) - 1u));  // peers in lower lanes
+  const bool leader = rel == 0;
+  unsigned peers = peers_all & (0xfffffffeu << lane);  // peers in higher lanes
+  while (__any_sync(all, peers != 0u)) {
+    const int next = __ffs(peers);  // 1-based lane of the nearest remaining higher peer, 0: none
+    const int src = next ? next - 1 : lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        const float o = __shfl_sync(all, gc[k][j], src);
+        if (next) gc[k][j] += o;
+      }
+    // lanes at odd positions among their remaining peers have just been absorbed by their predecessor
+    peers &= ~__ballot_sync(all, rel & 1);
+    rel >>= 1;
+  }
+  return leader;
+}
+
 template <int F, bool HALF, bool NEED_DX, bool JAC = false>
-__global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restrict__ x, const void* __restrict__ table,
-                                                        LevelScales sc, const float* __restrict__ dy, int64_t N, int L,
-                                                        int log2T, int n_coarse, float* __restrict__ dtable,
-                                                        float* __restrict__ dx, const float* __restrict__ jac) {
+__global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __restrict__ x,
+                                                               const void* __restrict__ table, LevelScales sc,
+                                                               const float* __restrict__ dy, int64_t N, int L,
+                                                               int log2T, int n_agg, int patch_S,
+                                                               float* __restrict__ dtable, float* __restrict__ dx,
+                                                               const float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   float* tile = reinterpret_cast<float*>(smem4);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t base_pt = (int64_t)blockIdx.x * kPts;
-  const int64_t p = base_pt + tid;
+  const int tid = threadIdx.x, lane = tid & 31, kTile = blockDim.x;
+  const int64_t base_pt = (int64_t)blockIdx.x * kTile;
+  const int row_t = tile_row(tid, patch_S);
+  const int64_t p = base_pt + row_t;
   const bool valid = p < N;
   const uint32_t T = 1u << log2T, mask = T - 1u;
   // coalesced load of the dy tile into the rotated layout
-  const int rows = (int)min((int64_t)kPts, N - base_pt);
+  const int rows = (int)min((int64_t)kTile, N - base_pt);
   const float* gdy = dy + base_pt * (int64_t)(L * F);
-  for (int i = tid; i < rows * L; i += kPts) {
+  for (int i = tid; i < rows * L; i += kTile) {
     const int row = i / L, l = i - row * L;
     float* dst = tile + tile_pos(row, l, L, F);
     if constexpr (F == 2) {
@@ -157,11 +201,11 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
     x0 = __ldg(x + 3 * p); x1 = __ldg(x + 3 * p + 1); x2 = __ldg(x + 3 * p + 2);
   }
   __syncthreads();
-  const int rowmod = tid % L;
+  const int rowmod = row_t % L;
   float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
   // One level per iteration on purpose. Prefetching the next level's corner rows one iteration ahead (16 gathers
   // in flight) and merging x-neighbour rows into 16-byte accesses were both measured and both lost: the kernel
-  // is bound by L2 atomic throughput, not by gather latency ("experiments that lost").
+  // is bound by RED lanes, not by gather latency ("experiments that lost").
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const float scale = sc.s[l];
@@ -170,7 +214,7 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
     if (r >= L) r -= L;
     float g[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) g[j] = valid ? tile[(tid * L + r) * F + j] : 0.f;
+    for (int j = 0; j < F; ++j) g[j] = valid ? tile[(row_t * L + r) * F + j] : 0.f;
     const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
     float gc[8][F];
     float f[8][F];
@@ -214,27 +258,9 @@ __global__ void __launch_bounds__(kPts, 4) hash_bwd_kernel(const float* __restri
       dx0 += dox * scale; dx1 += doy * scale; dx2 += doz * scale;
     }
     bool issue = valid;
-    if (l < n_coarse) {  // warp-uniform branch: segmented reduction over runs of equal cells
-      const uint64_t key = valid ? c.key : ~0ull;
-      // run id = number of run heads at or below this lane: monotone, so equal ids at distance d mean the
-      // whole span is one run (equal KEYS would not: a ray can leave and re-enter a cell, and callers may
-      // pass unordered points)
-      const uint64_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
-      const bool head = (lane == 0) || (pkey != key);
-      const int run = __popc(__ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int orun = __shfl_down_sync(0xffffffffu, run, d);
-        const bool take = (lane + d < 32) && (orun == run);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-          for (int j = 0; j < F; ++j) {
-            const float o = __shfl_down_sync(0xffffffffu, gc[k][j], d);
-            if (take) gc[k][j] += o;
-          }
-      }
-      issue = valid && head;
+    if (l < n_agg) {  // warp-uniform branch; lanes without a point get a key no other lane has
+      const uint64_t key = valid ? c.key : ((1ull << 63) | (uint64_t)lane);
+      issue = aggregate_equal_cells<F>(key, lane, gc) && valid;
     }
     if (issue) {
 #pragma unroll
@@ -261,21 +287,33 @@ static int check_common(const float* x, const void* table, const float* scales_h
   return TN_OK;
 }
 
+// Tile geometry: patch mode (4 rays x S samples per CTA, see the file header) when the points are whole 4-ray
+// groups of S samples and the tile fits a CTA; otherwise 128 consecutive points, lane = point.
+struct TileShape {
+  int threads, patch_S;
+};
+static TileShape tile_shape(int64_t N, int samples_per_ray) {
+  const int S = samples_per_ray;
+  if (S >= 8 && S % 8 == 0 && 4 * S <= kMaxTile && N % (4 * (int64_t)S) == 0) return {4 * S, S};
+  return {kPts, 0};
+}
+
 template <int F>
 static int launch_fwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, int64_t N, int L,
-                      int log2_T, float* out, int32_t* idx_out, float* jac, cudaStream_t st) {
-  const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
-  const size_t smem = (size_t)kPts * L * F * sizeof(float);
+                      int log2_T, int samples_per_ray, float* out, int32_t* idx_out, float* jac, cudaStream_t st) {
+  const TileShape ts = tile_shape(N, samples_per_ray);
+  const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
+  const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_FWD(H, W)                                                                                         \
   do {                                                                                                       \
     auto k = hash_fwd_kernel<F, H, W>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, idx_out, jac);                               \
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, out, idx_out, jac);             \
   } while (0)
   if (jac) {  // (no index dump on this path: checked by the caller)
     auto k = table_dtype == 0 ? hash_fwd_kernel<F, false, false, true> : hash_fwd_kernel<F, true, false, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, kPts, smem, st>>>(x, table, sc, N, L, log2_T, out, nullptr, jac);
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, out, nullptr, jac);
   } else if (table_dtype == 0) {
     if (idx_out) TN_FWD(false, true); else TN_FWD(false, false);
   } else {
@@ -287,20 +325,21 @@ static int launch_fwd(const float* x, const void* table, int table_dtype, const 
 
 template <int F>
 static int launch_bwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, const float* dy,
-                      int64_t N, int L, int log2_T, int n_coarse, float* dtable, float* dx, const float* jac,
-                      cudaStream_t st) {
-  const unsigned grid = (unsigned)((N + kPts - 1) / kPts);
-  const size_t smem = (size_t)kPts * L * F * sizeof(float);
+                      int64_t N, int L, int log2_T, int n_agg, int samples_per_ray, float* dtable, float* dx,
+                      const float* jac, cudaStream_t st) {
+  const TileShape ts = tile_shape(N, samples_per_ray);
+  const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
+  const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_BWD(H, D)                                                                                         \
   do {                                                                                                       \
     auto k = hash_bwd_kernel<F, H, D>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac);                   \
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, dtable, dx, jac);    \
   } while (0)
   if (jac && dx) {
     auto k = table_dtype == 0 ? hash_bwd_kernel<F, false, true, true> : hash_bwd_kernel<F, true, true, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, kPts, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac);
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, dtable, dx, jac);
   } else if (table_dtype == 0) {
     if (dx) TN_BWD(false, true); else TN_BWD(false, false);
   } else {
@@ -315,47 +354,53 @@ static int launch_bwd(const float* x, const void* table, int table_dtype, const 
 using namespace tn;
 
 extern "C" int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                                  int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, float* jac_out,
-                                  void* stream) {
+                                  int64_t N, int L, int F, int log2_T, int samples_per_ray, float* out,
+                                  int32_t* idx_out, float* jac_out, void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
   TN_REQUIRE(out || N == 0, TN_EINVAL, "hash_encode_fwd: out is null");
   TN_REQUIRE(aligned(out, 16), TN_EALIGN, "hash_encode_fwd: out must be 16-byte aligned");
-  TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_fwd: L*F=%d too large", L * F);
+  TN_REQUIRE((size_t)kMaxTile * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_fwd: L*F=%d too large", L * F);
+  TN_REQUIRE(samples_per_ray >= 0, TN_EINVAL, "hash_encode_fwd: samples_per_ray=%d", samples_per_ray);
   TN_REQUIRE(!(jac_out && idx_out), TN_EINVAL, "hash_encode_fwd: idx_out and jac_out are exclusive");
   if (N == 0) return TN_OK;
   LevelScales sc;
   for (int l = 0; l < TN_MAX_LEVELS; ++l) sc.s[l] = l < L ? scales_host[l] : 0.f;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (F) {
-    case 1: return launch_fwd<1>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
-    case 2: return launch_fwd<2>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
-    case 4: return launch_fwd<4>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
-    default: return launch_fwd<8>(x, table, table_dtype, sc, N, L, log2_T, out, idx_out, jac_out, st);
+    case 1: return launch_fwd<1>(x, table, table_dtype, sc, N, L, log2_T, samples_per_ray, out, idx_out, jac_out, st);
+    case 2: return launch_fwd<2>(x, table, table_dtype, sc, N, L, log2_T, samples_per_ray, out, idx_out, jac_out, st);
+    case 4: return launch_fwd<4>(x, table, table_dtype, sc, N, L, log2_T, samples_per_ray, out, idx_out, jac_out, st);
+    default: return launch_fwd<8>(x, table, table_dtype, sc, N, L, log2_T, samples_per_ray, out, idx_out, jac_out, st);
   }
 }
 
 extern "C" int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                                  const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
-                                  const float* jac, void* stream) {
+                                  const float* dy, int64_t N, int L, int F, int log2_T, int samples_per_ray,
+                                  float* dtable, float* dx, const float* jac, void* stream) {
   int rc = check_common(x, table, scales_host, N, L, F, log2_T, table_dtype);
   if (rc) return rc;
   TN_REQUIRE((dy || N == 0) && dtable, TN_EINVAL, "hash_encode_bwd: null pointer");
   TN_REQUIRE(aligned(dy, 16) && aligned(dtable, 16), TN_EALIGN, "hash_encode_bwd: dy/dtable must be 16-byte aligned");
-  TN_REQUIRE((size_t)kPts * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_bwd: L*F=%d too large", L * F);
+  TN_REQUIRE((size_t)kMaxTile * L * F * 4 <= 200 * 1024, TN_EINVAL, "hash_encode_bwd: L*F=%d too large", L * F);
+  TN_REQUIRE(samples_per_ray >= 0, TN_EINVAL, "hash_encode_bwd: samples_per_ray=%d", samples_per_ray);
   if (N == 0) return TN_OK;
   LevelScales sc;
-  int n_coarse = 0;
+  int n_agg = 0;
+  // levels coarse enough for the lanes of a warp to share cells: aggregate there.  Measured on the bench batch
+  // (distinct cells per point in a warp): 0.10 at scale 16 ... 0.63 at 212, 0.74 at 294, 0.91 at 561 (patch tiles);
+  // lane = consecutive sample of one ray: 0.29 at 16 ... 0.82 at 80, 1.0 from 212 on.
+  const TileShape ts = tile_shape(N, samples_per_ray);
+  const float thr = ts.patch_S ? agg_threshold_enc_patch() : agg_threshold_enc();
   for (int l = 0; l < TN_MAX_LEVELS; ++l) {
     sc.s[l] = l < L ? scales_host[l] : 0.f;
-    // cells of coarse levels hold long runs of consecutive samples: aggregate there
-    if (l < L && l == n_coarse && scales_host[l] <= agg_threshold("TN_AGG_ENC", 96.f)) ++n_coarse;
+    if (l < L && l == n_agg && scales_host[l] <= thr) ++n_agg;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (F) {
-    case 1: return launch_bwd<1>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
-    case 2: return launch_bwd<2>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
-    case 4: return launch_bwd<4>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
-    default: return launch_bwd<8>(x, table, table_dtype, sc, dy, N, L, log2_T, n_coarse, dtable, dx, jac, st);
+    case 1: return launch_bwd<1>(x, table, table_dtype, sc, dy, N, L, log2_T, n_agg, samples_per_ray, dtable, dx, jac, st);
+    case 2: return launch_bwd<2>(x, table, table_dtype, sc, dy, N, L, log2_T, n_agg, samples_per_ray, dtable, dx, jac, st);
+    case 4: return launch_bwd<4>(x, table, table_dtype, sc, dy, N, L, log2_T, n_agg, samples_per_ray, dtable, dx, jac, st);
+    default: return launch_bwd<8>(x, table, table_dtype, sc, dy, N, L, log2_T, n_agg, samples_per_ray, dtable, dx, jac, st);
   }
 }

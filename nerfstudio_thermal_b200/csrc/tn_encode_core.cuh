@@ -11,7 +11,8 @@ struct LevelScales {
 
 constexpr uint32_t kPrimeY = 2654435761u;  // encodings.py:413
 constexpr uint32_t kPrimeZ = 805459861u;
-constexpr int kPts = 128;                  // points per CTA
+constexpr int kPts = 128;                  // points per CTA (lane = consecutive point)
+constexpr int kMaxTile = 256;              // largest encode tile (patch mode: 4 rays x S samples, S <= 64)
 // Measured on B200 (profiles/): fetching / reducing adjacent x-pairs of corners as one 16-byte access lowers the L2
 // sector count by 25 % but is SLOWER (bwd main grid 0.633 -> 0.654 ms/step, fused proposal bwd 0.475 -> 0.557): the
 // atomic path is bound by REDs per lane-address, and unmerged lanes pay a padded 16-byte RED plus the 8-byte one.

@@ -67,15 +67,17 @@ def test_captured_step_follows_anneal_and_update_schedules(use_graph):
     ssu, expected_updates, seen_not_updated = 0, 0, 0
     prop_params = [p for p in model.proposal_networks.parameters()]
     none_jit = [None] * 6
-    for step in range(16):
+    for step in range(18):
         sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
         before = [p.detach().clone() for p in prop_params]
         # the reference's schedule, restated on the host
         frac = np.clip(step / c.proposal_weights_anneal_max_num_iters, 0, 1)
         b = c.proposal_weights_anneal_slope
         anneal = b * frac / ((b - 1) * frac + 1)
-        sched = np.clip(np.interp(step, [0, c.proposal_warmup], [0, c.proposal_update_every]), 1, c.proposal_update_every)
-        updated = ssu > sched or step < 10
+        # (step_cb runs AFTER the iteration: during iteration `step` the sampler still holds the previous step)
+        seen = max(step - 1, 0)
+        sched = np.clip(np.interp(seen, [0, c.proposal_warmup], [0, c.proposal_update_every]), 1, c.proposal_update_every)
+        updated = ssu > sched or seen < 10
         total = runner.train_iteration(step, batch)
         with torch.no_grad():
             # thermal sampler: never driven by callbacks in the default config -> anneal 1, always updated
@@ -104,8 +106,8 @@ def test_captured_step_follows_anneal_and_update_schedules(use_graph):
     assert seen_not_updated >= 2
     counts = runner.optimizer.group_step_counts()
     assert counts["proposal_networks"] == expected_updates
-    assert counts["proposal_networks_thermal"] == 16 and counts["fields"] == 16
-    assert runner.optimizer.step_count == 16
+    assert counts["proposal_networks_thermal"] == 18 and counts["fields"] == 18
+    assert runner.optimizer.step_count == 18
     if use_graph:
         assert len(runner._variants) == 2
 
