@@ -47,17 +47,21 @@ const char* tn_build_arch(void);          /* "sm_100a" */
  *   corner order hashed_0..hashed_7 (encodings.py:431-438) -- the bit-exactness test hook.
  * jac_out: NULL, or float32[L, N, F, 3] receiving d out[n, l*F+f] / d x[n, :] (exclusive with idx_out): handed
  *   back to tn_hash_encode_bwd it saves the backward its second gather of the corner rows.
+ * samples_per_ray: 0, or S when the points are the [R,S] samples of R rays in ray-major order (a HINT: results
+ *   do not depend on it).  With S % 8 == 0, S <= 64 and N % 4S == 0 a CTA then owns 4 consecutive rays (one 2x2
+ *   pixel patch of data/pixel_samplers.py:389-438) and a warp 8 consecutive samples of each, whose points share
+ *   grid cells: fewer L1 wavefronts per gather and fewer table REDs in the backward.
  * ------------------------------------------------------------------------------------------------ */
 int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                       int64_t N, int L, int F, int log2_T, float* out, int32_t* idx_out, float* jac_out,
-                       void* stream);
+                       int64_t N, int L, int F, int log2_T, int samples_per_ray, float* out, int32_t* idx_out,
+                       float* jac_out, void* stream);
 
 /* dy[N, L*F].  dtable[L*T, F] float32 is ACCUMULATED into (caller zero-fills for a fresh gradient).
  * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; computed from `jac` (the
  * forward's jac_out) when given, else by gathering the corner rows of `table` again. */
 int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
-                       const float* dy, int64_t N, int L, int F, int log2_T, float* dtable, float* dx,
-                       const float* jac, void* stream);
+                       const float* dy, int64_t N, int L, int F, int log2_T, int samples_per_ray, float* dtable,
+                       float* dx, const float* jac, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sample positions -> normalised grid coordinates.

@@ -30,8 +30,8 @@ _SIGNATURES = {
     "tn_version": [],
     "tn_last_error_string": [],
     "tn_build_arch": [],
-    "tn_hash_encode_fwd": [_P, _P, c_int, POINTER(c_float), c_int64, c_int, c_int, c_int, _P, _P, _P, _P],
-    "tn_hash_encode_bwd": [_P, _P, c_int, POINTER(c_float), _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P],
+    "tn_hash_encode_fwd": [_P, _P, c_int, POINTER(c_float), c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "tn_hash_encode_bwd": [_P, _P, c_int, POINTER(c_float), _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tn_sample_positions_fwd": [_P, _P, _P, c_int64, c_int, _P, _P, _P],
     "tn_sample_positions_bwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
     "tn_contract_points_fwd": [_P, c_int64, _P, _P, _P],

@@ -12,6 +12,24 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Tuning knobs: the environment is read once, on first use (C++11 magic statics: thread-safe, immutable afterwards).
+static float env_float(const char* name, float dflt) {
+  const char* e = getenv(name);
+  return e ? (float)atof(e) : dflt;
+}
+float agg_threshold_enc() {
+  static const float v = env_float("TN_AGG_ENC", 96.f);
+  return v;
+}
+float agg_threshold_enc_patch() {
+  static const float v = env_float("TN_AGG_ENC_PATCH", 300.f);
+  return v;
+}
+float agg_threshold_prop() {
+  static const float v = env_float("TN_AGG_PROP", 96.f);
+  return v;
+}
 }  // namespace tn
 
 extern "C" int tn_version(void) { return 100; }

@@ -389,7 +389,7 @@ extern "C" int tn_prop_density_bwd(const float* origins, const float* directions
   int n_coarse = 0;
   for (int l = 0; l < TN_MAX_LEVELS; ++l) {
     sc.s[l] = l < L ? scales_host[l] : 0.f;
-    if (l < L && l == n_coarse && scales_host[l] <= agg_threshold("TN_AGG_PROP", 96.f)) ++n_coarse;
+    if (l < L && l == n_coarse && scales_host[l] <= agg_threshold_prop()) ++n_coarse;
   }
   const int64_t N = R * S;
   const unsigned grid = (unsigned)min((N + kPts - 1) / kPts, (int64_t)kNumSMs * 4);

@@ -95,7 +95,9 @@ class HashEncoding(Encoding):
     def forward(self, in_tensor: Tensor) -> Tensor:
         assert in_tensor.shape[-1] == 3
         flat = in_tensor.reshape(-1, 3)
-        out = ops.hash_encode(flat, self.hash_table, self.spec, self._half(), self.grad_sink)
+        # [R, S, 3] inputs are ray samples in ray-major order: tell the kernels (tiling hint, see tn_b200.h)
+        spr = in_tensor.shape[-2] if in_tensor.dim() == 3 else 0
+        out = ops.hash_encode(flat, self.hash_table, self.spec, self._half(), self.grad_sink, samples_per_ray=spr)
         return out.view(*in_tensor.shape[:-1], self.get_out_dim())
 
 

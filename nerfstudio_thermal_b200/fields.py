@@ -142,8 +142,8 @@ class NerfactoField(Field):
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape
         self._sample_locations = x.view(*shape, 3)
-        h_flat = self.mlp_base(x)
-        h = h_flat.view(*shape, -1)
+        h = self.mlp_base(self._sample_locations)  # [R,S,3] tells the encode kernels the ray structure
+        h_flat = h.view(-1, h.shape[-1])
         density_before_activation, base_mlp_out = torch.split(h, [1, self.geo_feat_dim], dim=-1)
         self._density_before_activation = density_before_activation
         # average_init_density * trunc_exp(h0) * selector in one kernel (:227-228)
@@ -158,7 +158,7 @@ class NerfactoField(Field):
         if mlp._out_act != ops.ACT_NONE or len(mlp.layers) < 2:
             return self.get_density(ray_samples)[0]
         x, selector = self._grid_coordinates(ray_samples)
-        feats = self.mlp_base.model[0](x)
+        feats = self.mlp_base.model[0](x.view(*ray_samples.frustums.shape, 3)).view(x.shape[0], -1)
         ws = [l.weight for l in mlp.layers[:-1]] + [mlp.layers[-1].weight[:1]]
         bs = [l.bias for l in mlp.layers[:-1]] + [mlp.layers[-1].bias[:1]]
         sinks = None
@@ -186,7 +186,7 @@ class NerfactoField(Field):
             cb = self.grads_ready_callback
             x.register_hook(lambda _g: (cb(), None)[1])
         self._sample_locations = x.view(rays, samples, 3)
-        h = self.mlp_base(x)
+        h = self.mlp_base(self._sample_locations).view(rays * samples, -1)
         self._density_before_activation = h.view(rays, samples, -1)[..., :1]
         sh = self.direction_encoding(get_normalized_directions(lay.directions))
         emb_ray = None
@@ -292,10 +292,11 @@ class HashMLPDensityField(Field):
             return density.view(lay.num_rays, lay.num_samples, 1), None
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape
+        xs = x.view(*shape, 3)
         if not self.use_linear:
-            raw = self.mlp_base(x)
+            raw = self.mlp_base(xs).view(x.shape[0], -1)
         else:
-            raw = self.linear(self.encoding(x))
+            raw = self.linear(self.encoding(xs)).view(x.shape[0], -1)
         # average_init_density * trunc_exp(raw) * selector in one kernel (:116-117)
         density = fused_ops.density_act(raw, selector, self.average_init_density).view(*shape, 1)
         return density, None

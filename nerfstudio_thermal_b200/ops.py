@@ -50,7 +50,7 @@ def hash_encode_indices(x: Tensor, spec: HashGridSpec) -> Tensor:
     out = torch.empty((n, spec.out_dim), device=x.device)
     idx = torch.empty((n, spec.num_levels, 8), device=x.device, dtype=torch.int32)
     call("tn_hash_encode_fwd", ptr(x), ptr(dummy), 0, spec._c_scales, n, spec.num_levels, spec.features, spec.log2_T,
-         ptr(out), ptr(idx), None, stream())
+         0, ptr(out), ptr(idx), None, stream())
     return idx
 
 
@@ -61,7 +61,7 @@ SAVE_JACOBIAN = os.environ.get("TN_SAVE_JAC", "0") == "1"
 
 class _HashEncodeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, table, spec: HashGridSpec, table_f16, grad_sink):
+    def forward(ctx, x, table, spec: HashGridSpec, table_f16, grad_sink, samples_per_ray):
         x = _f32c(x)
         n = x.shape[0]
         out = torch.empty((n, spec.out_dim), device=x.device, dtype=torch.float32)
@@ -72,9 +72,10 @@ class _HashEncodeFn(torch.autograd.Function):
         if SAVE_JACOBIAN and ctx.needs_input_grad[0]:
             jac = torch.empty((spec.num_levels, n, spec.features, 3), device=x.device)
         call("tn_hash_encode_fwd", ptr(x), ptr(src), dtype, spec._c_scales, n, spec.num_levels, spec.features,
-             spec.log2_T, ptr(out), None, ptr(jac), stream(),
+             spec.log2_T, samples_per_ray, ptr(out), None, ptr(jac), stream(),
              tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',jac' if jac is not None else ''}]")
         ctx.spec = spec
+        ctx.samples_per_ray = samples_per_ray
         ctx.grad_sink = grad_sink
         ctx.save_for_backward(x, table, table_f16, jac)
         return out
@@ -89,25 +90,26 @@ class _HashEncodeFn(torch.autograd.Function):
         want_table = ctx.needs_input_grad[1]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         if not want_table and dx is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         if want_table and sink is not None:
             dtable = sink  # scatter straight into the (flat) gradient buffer: no 64 MB temporary, no add pass
         else:  # fresh gradient (or scratch target when only dx is wanted: the kernel always scatters)
             dtable = torch.zeros_like(table, dtype=torch.float32)
         src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
         call("tn_hash_encode_bwd", ptr(x), ptr(src), dtype, spec._c_scales, ptr(dy), n, spec.num_levels, spec.features,
-             spec.log2_T, ptr(dtable), ptr(dx), ptr(jac if dx is not None else None), stream(),
+             spec.log2_T, ctx.samples_per_ray, ptr(dtable), ptr(dx), ptr(jac if dx is not None else None), stream(),
              tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',dx' if dx is not None else ''}]")
-        return dx, (dtable if (want_table and sink is None) else None), None, None, None
+        return dx, (dtable if (want_table and sink is None) else None), None, None, None, None
 
 
 def hash_encode(x: Tensor, table: Tensor, spec: HashGridSpec, table_f16: Optional[Tensor] = None,
-                grad_sink: Optional[Tensor] = None) -> Tensor:
+                grad_sink: Optional[Tensor] = None, samples_per_ray: int = 0) -> Tensor:
     """x[N,3] in [0,1], table[L*T,F] -> [N, L*F].  field_components/encodings.py:420-461.
 
     grad_sink: optional float32 tensor shaped like `table` that the backward kernel accumulates the table
-    gradient INTO (e.g. the parameter's slice of a FlatGradBuffer); autograd then receives no table gradient."""
-    return _HashEncodeFn.apply(x, table, spec, table_f16, grad_sink)
+    gradient INTO (e.g. the parameter's slice of a FlatGradBuffer); autograd then receives no table gradient.
+    samples_per_ray: S when x holds the [R,S] samples of R rays in ray-major order (a tiling hint, same results)."""
+    return _HashEncodeFn.apply(x, table, spec, table_f16, grad_sink, int(samples_per_ray))
 
 
 # ----------------------------------------------------------------------------------- positions
