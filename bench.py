@@ -10,6 +10,11 @@ as 2x2 patches from 64 cameras (32 RGB + 32 thermal), seed 42 + rank.  One step 
 dict, backward (and, for N > 1, ONE flat NCCL all-reduce of all gradients).  `value` is measured with the batch
 already in HBM; `e2e` copies the batch from pinned host memory every step and reads the loss back.
 
+Besides the headline (configs[1]) the same command measures the rest of BASELINE.json's metric and adds it to the
+line as `legs`: `render` (configs[2], full-frame eval render sharded over the ranks), `shared8192` (configs[3]),
+`sweep` (configs[4]: 2^16..2^22 rays x T in {2^19, 2^21}) and `l2_probe` (the measured L2 gather / RED peaks the
+encode rooflines are also reported against).  `--train-only` skips them.
+
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -52,6 +57,8 @@ def parse():
     ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--mode", choices=["train", "render"], default="train",
                     help="train: BASELINE configs[1] (the headline metric); render: configs[2] full-frame eval render")
+    ap.add_argument("--train-only", action="store_true",
+                    help="only the headline train leg (no render / shared8192 / sweep / L2-probe legs): profiling runs")
     ap.add_argument("--profile-kernels", action="store_true", help="print the per-kernel time table to stderr")
     return ap.parse_args()
 
@@ -130,10 +137,74 @@ def algorithmic_bytes_per_point(L, F=2, table_bytes=4, bwd=False, dx=False):
 
 
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source) -- the driver-written MEASURED_PEAKS.json, else the recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
-        return json.load(open(path)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        d = json.load(open(path))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1650.0, "fallback (B200_PROFILING.md)"
+
+
+def _tag_int(tag, key, default=0):
+    """integer that follows `key` in a launch tag, e.g. _tag_int('tn_hash_encode_fwd[L16,T2^19]', 'L') == 16"""
+    import re
+
+    m = re.search(re.escape(key) + r"(\d+)", tag)
+    return int(m.group(1)) if m else default
+
+
+def kernel_roofline(tag, launches, ms, units, peaks, l2=None, half_tables=False):
+    """Roofline entry of one launch tag from its CUDA-event time: algorithmic bytes (or flops) per unit (DESIGN.md
+    section 4) x the units its launches processed / their total duration, against the measured peak.  Returns None
+    for kernels without a per-unit model (small latency-bound launches)."""
+    hbm, tflops, src = peaks
+    if not units or ms <= 0:
+        return None
+    sec = ms * 1e-3
+    base = {"kernel": tag, "launches": launches, "avg_launch_ms": ms / launches, "units_per_launch": units / launches}
+    if tag.startswith("tn_hash_encode"):
+        L, bwd, dx = _tag_int(tag, "[L", 16), "bwd" in tag, ",dx" in tag
+        per = algorithmic_bytes_per_point(L, 2, 2 if (half_tables and not bwd) else 4, bwd, dx)
+        ach = per * units / sec / 1e9
+        r = dict(base, bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, bytes_per_unit=per,
+                 algorithmic_bytes_per_launch=per * units / launches, peak_source=src)
+        if l2:  # the same launch against the MEASURED L2 request rates (8 gathers [+ 8 REDs] per point and level)
+            gathers = 8 * L * units if (not bwd or dx) else 0
+            reds = 8 * L * units if bwd else 0
+            floor = gathers / (l2["gather8"] * 1e9) + reds / (l2["red_v2"] * 1e9)
+            r["l2"] = {"floor_ms_per_launch": floor * 1e3 / launches, "frac": floor / sec,
+                       "what": "row gathers / vector REDs per point and level at the rates tn_l2_probe measured for "
+                               "one row per lane; > 1 means duplicate and neighbouring rows were merged"}
+        return r
+    if tag.startswith("tn_prop_density"):
+        L, bwd = _tag_int(tag, "[L", 5), "bwd" in tag
+        # SURVEY 8(d)'s encode formulas with the fused field's I/O: the position (12) is formed on chip from the ray
+        # and a bin edge, one density leaves (4) instead of L*F features; backward = the density gradient in (4),
+        # 8 corner rows of 8 bytes per level reduced into, dL/dx out (12)
+        per = (12 + 4 + L * 64 + (12 if ",dx" in tag else 0)) if bwd else (12 + L * 64 + 4)
+        ach = per * units / sec / 1e9
+        return dict(base, bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, bytes_per_unit=per,
+                    peak_source=src)
+    if tag.startswith("tn_mlp_tc") or tag.startswith("tn_field_head"):
+        import re
+
+        m = re.search(r"\[(\d+)-(\d+)x(\d+)-(\d+)\]", tag)
+        if not m:
+            return None
+        i, w, nh, o = (int(g) for g in m.groups())
+        macs = i * w + (nh - 1) * w * w + w * o
+        flops = 2 * macs * (3 if "bwd" in tag else 1)  # backward: recomputed forward + dX + dW products
+        ach = flops * units / sec / 1e12
+        return dict(base, bound="tensor", achieved=ach, peak=tflops, unit="TFLOP/s", frac=ach / tflops,
+                    flops_per_unit=flops, peak_source=src,
+                    note="fp32-equivalent flops; every product is 6 (fwd) / 3 (bwd) bf16 MMAs")
+    return None
+
+
+def load_traffic():
+    """DRAM bytes per launch of each kernel tag from the newest committed ncu capture (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
@@ -186,32 +257,78 @@ def time_oracle(args, rays, steps, warmup):
 
 
 def run_reference(args):
+    """The reference algorithm on the host cores (oracle port, all threads), same workload as the B200 arm: the full
+    4096-ray batch every step.  When K+W full steps would not fit the time budget the STEP COUNT is cut (never the
+    batch), and the line says how many steps were timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count()
-    # bounded sample: a first full-size step decides how many rays fit the time budget of the whole run
-    t_probe = time_oracle(args, args.rays, 1, 0)
-    budget = 150.0
-    total_steps = args.steps + args.warmup
-    rays = args.rays
-    if t_probe * total_steps > budget:
-        rays = max(256, int(args.rays * budget / (t_probe * total_steps)) // 64 * 64)
-    sec = time_oracle(args, rays, args.steps, args.warmup)
-    value = rays / sec
+    t_probe = time_oracle(args, args.rays, 1, 0)  # also pages everything in
+    budget = 170.0
+    warmup = min(args.warmup, 1) if t_probe * (args.steps + args.warmup) > budget else args.warmup
+    steps = min(args.steps, max(3, int((budget - t_probe * (1 + warmup)) / t_probe)))
+    sec = time_oracle(args, args.rays, steps, warmup)
+    value = args.rays / sec
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"thermal-nerfacto train step fwd+loss+bwd, density_mode={args.density_mode}, "
-                               f"T=2^{args.log2_hashmap_size}, CPU torch ops (oracle port of implementation='torch')",
-                   "rays_per_step": rays, "init": args.init},
+        "config": {"workload": train_workload(args), "rays_per_gpu": args.rays, "init": args.init,
+                   "implementation": "CPU torch ops (oracle port of implementation='torch'), "
+                                     f"{cores} host threads, ONE host process whatever --gpus says"
+                                     + (" (single-host figure: not comparable with an N-GPU line)" if world > 1 else ""),
+                   "steps_requested": args.steps, "warmup_requested": args.warmup},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of {rays} rays (full batch is {args.rays}); probe step of "
-                                   f"{args.rays} rays took {t_probe:.2f} s"},
+                         "sample": f"{steps} timed steps (+{warmup} warm-up) of the full {args.rays}-ray batch, "
+                                   f"{sec:.2f} s each; the step count, not the batch, is cut to fit ~{budget:.0f} s"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def train_workload(args):
+    return (f"thermal-nerfacto train step (fwd + loss + bwd), density_mode={args.density_mode}, {args.rays} rays/GPU, "
+            f"main grids 16x2^{args.log2_hashmap_size}x2, proposal grids 5x2^17x2, samples 256/96+48")
+
+
+# ------------------------------------------------------------------------------------------------ distributed glue
+class Dist:
+    """rank / world / device of this process and the two collectives the bench itself needs."""
+
+    def __init__(self, gpus):
+        import torch.distributed as dist
+
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (there is no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        assert self.world == gpus, f"--gpus {gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run"
+        self.dist = dist
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """device time of `steps` calls of fn, bracketed by barrier + synchronize, MAX over ranks (ms, total)."""
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return ms.item()
 
 
 # ------------------------------------------------------------------------------------------------ render (config 3)
@@ -232,33 +349,31 @@ def pinhole_rays(width, height, cam_index, seed):
                 camera_indices=torch.full((height, width, 1), cam_index, dtype=torch.long))
 
 
-def run_render(args):
-    """BASELINE.json configs[2]: full-frame eval render, 640x512 thermal + 1920x1080 RGB camera, rays sharded over
-    the ranks on the reference's chunk boundaries (eval_num_rays_per_chunk = 1<<15), zero communication."""
-    import torch.distributed as dist
-
-    import nerfstudio_thermal_b200 as tn
-    from nerfstudio_thermal_b200 import parallel
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    model = build_model(args).to(dev).eval()
-    frames = [pinhole_rays(640, 512, NUM_CAMERAS - 1, 7), pinhole_rays(1920, 1080, 0, 8)]
+def render_keys(density_mode):
+    if density_mode == "rgb_only":
+        return ["rgb", "depth", "accumulation"]
     keys = ["rgb", "rgb_thermal", "depth", "depth_thermal", "accumulation", "accumulation_thermal"]
-    if args.density_mode != "separate":
+    if density_mode != "separate":
         keys = [k for k in keys if not k.endswith("_thermal") or k == "rgb_thermal"]
-    if args.density_mode == "rgb_only":
-        keys = ["rgb", "depth", "accumulation"]
+    return keys
+
+
+def render_leg(args, model, D, steps, warmup, peaks, l2=None, profile=False):
+    """BASELINE.json configs[2]: full-frame eval render, 640x512 thermal + 1920x1080 RGB camera, rays sharded over
+    the ranks on the reference's chunk boundaries (eval_num_rays_per_chunk = 1<<15), zero communication.  value:
+    rays resident in HBM; e2e: pinned host rays in, every rendered chunk copied back to the host (as
+    models/base_model.py:200-203 does)."""
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import _lib, engine, parallel
+
+    dev, rank, world = D.dev, D.rank, D.world
+    was_training = model.training
+    model.eval()
+    frames = [pinhole_rays(640, 512, NUM_CAMERAS - 1, 7), pinhole_rays(1920, 1080, 0, 8)]
+    keys = render_keys(args.density_mode)
     chunk = model.config.eval_num_rays_per_chunk
     host_frames = [{k: v.reshape(-1, v.shape[-1]).pin_memory() for k, v in fr.items()} for fr in frames]
     total_rays = sum(fr["origins"].shape[0] for fr in host_frames)
-
-    from nerfstudio_thermal_b200 import engine
     # chunks of 32768 rays keep the GPU busy kernel by kernel: the eager chunk loop (6.79 M rays/s) is as fast as one
     # captured graph per chunk with the thermal branch on a second stream (6.69 M), so the plain loop is the default
     chunk_runner = engine.GraphedRenderChunk(model, chunk) if args.graph_render else None
@@ -270,65 +385,232 @@ def run_render(args):
             for fr, dfr in zip(host_frames, dev_frames):
                 n = fr["origins"].shape[0]
                 for s, e in parallel.shard_chunks(n, chunk, rank, world):
-                    src = fr if from_host else dfr  # e2e: pinned host rays in, rendered chunk back to the host
+                    src = fr if from_host else dfr
                     b = tn.RayBundle(**{k: src[k][s:e].to(dev, non_blocking=True) for k in
                                         ("origins", "directions", "pixel_area", "camera_indices")})
                     res = chunk_runner.render(b) if chunk_runner is not None else model(b)
-                    if from_host:  # as base_model.py:200-203 does
+                    if from_host:
                         outs.append({k: res[k].to("cpu", non_blocking=True) for k in keys})
                     else:
                         outs.append(res[keys[0]].clone() if chunk_runner is not None else res[keys[0]])
         return outs
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    for _ in range(max(1, warmup)):
+        render_all(False)
+    ms_value = D.timed(lambda: render_all(False), steps) / steps
+    ms_e2e = D.timed(lambda: render_all(True), steps) / steps
+    # instrumented pass: per-kernel CUDA-event times at chunk size (the encode forward's roofline while streaming)
+    _lib.STATS.reset(timing=True)
+    render_all(False)
+    torch.cuda.synchronize()
+    table = _lib.STATS.summary()
+    launches = _lib.STATS.count
+    _lib.STATS.reset()
+    if profile and rank == 0:
+        print_kernel_table(table, 1, ms_value, "render")
+    out_bytes = sum({"rgb": 12}.get(k, 4) for k in keys) * total_rays
+    roofs = top_rooflines(table, peaks, l2, args.half_tables, prefix="tn_hash_encode_fwd")
+    res = {"metric": "render rays/s, thermal-nerfacto", "value": total_rays / (ms_value * 1e-3), "unit": "rays/s",
+           "ms_per_step": ms_value, "steps": steps, "warmup": max(1, warmup), "scaling": "strong",
+           "config": {"workload": f"full-frame eval render 640x512 thermal + 1920x1080 RGB, density_mode={args.density_mode}, "
+                                  f"chunks of {chunk} rays sharded over {world} rank(s), zero communication",
+                      "rays_per_step": total_rays, "parallelism": f"dp{world}",
+                      "launch": "one CUDA graph replay per chunk (engine.GraphedRenderChunk)" if args.graph_render
+                                else "eager chunk loop (models/base_model.py:177-206)"},
+           "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 52 * total_rays,
+                   "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
+           "gpu_launches_per_step": launches,
+           "roofline": roofs[0] if roofs else None}
+    model.train(was_training)
+    return res
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        render_all(False)
-    steps = max(1, min(args.steps, 5))
-    times = {}
-    for name, from_host in (("value", False), ("e2e", True)):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            render_all(from_host)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        times[name] = ms.item() / steps
-    if args.profile_kernels and rank == 0:
-        from nerfstudio_thermal_b200 import _lib
-        _lib.STATS.reset(timing=True)
-        render_all(False)
-        torch.cuda.synchronize()
-        table = _lib.STATS.summary()
-        _lib.STATS.reset()
-        for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
-            print(f"{k:58s} {n:6d} launches/step {ms:8.3f} ms/step", file=sys.stderr)
-        print(f"sum of libtn_b200 kernels {sum(ms for _, ms in table.values()):.3f} ms/step; step {times['value']:.3f} ms",
-              file=sys.stderr)
-    if rank == 0:
-        out_bytes = sum({"rgb": 12, "rgb_thermal": 4}.get(k, 4) for k in keys) * total_rays
-        line = {
-            "metric": "render rays/s, thermal-nerfacto", "value": total_rays / (times["value"] * 1e-3), "unit": "rays/s",
-            "n_gpus": world, "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": times["value"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"full-frame eval render 640x512 thermal + 1920x1080 RGB, density_mode={args.density_mode}, "
-                                   f"chunks of {chunk} rays sharded over {world} rank(s)", "rays_per_step": total_rays,
-                       "init": args.init, "parallelism": f"dp{world}",
-                       "launch": "one CUDA graph replay per chunk (engine.GraphedRenderChunk)" if args.graph_render
-                                 else "eager chunk loop (models/base_model.py:177-206)"},
-            "e2e": {"value": total_rays / (times["e2e"] * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 52 * total_rays,
-                    "d2h_bytes_per_step": out_bytes, "ms_per_step": times["e2e"]},
-        }
+
+def run_render(args):
+    D = Dist(args.gpus)
+    model = build_model(args).to(D.dev).eval()
+    peaks = measured_peaks()
+    l2 = l2_probe_leg(D) if not args.train_only else None
+    res = render_leg(args, model, D, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), peaks, l2,
+                     profile=args.profile_kernels)
+    if D.rank == 0:
+        line = dict(res, n_gpus=D.world, higher_is_better=True, vs_baseline=None, dtype="f32", data="synthetic")
+        line["config"]["init"] = args.init
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if D.world > 1:
+        D.dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ shared helpers
+def print_kernel_table(table, steps, ms_step, title):
+    print(f"--- {title}", file=sys.stderr)
+    for k, (n, ms, _u) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:58s} {n / steps:6.1f} launches/step {ms / steps:8.3f} ms/step", file=sys.stderr)
+    kern = sum(ms for _, ms, _u in table.values()) / steps
+    print(f"sum of libtn_b200 kernels {kern:.3f} ms/step; step {ms_step:.3f} ms", file=sys.stderr)
+
+
+def top_rooflines(table, peaks, l2, half_tables, prefix=None, limit=6):
+    """Roofline entries of the launch tags with a per-unit model, longest total time first."""
+    total = sum(ms for _, ms, _u in table.values()) or 1.0
+    out = []
+    for tag, (n, ms, units) in sorted(table.items(), key=lambda kv: -kv[1][1]):
+        if prefix and not tag.startswith(prefix):
+            continue
+        r = kernel_roofline(tag, n, ms, units, peaks, l2, half_tables)
+        if r is not None:
+            r["share_of_kernel_time"] = ms / total
+            out.append(r)
+        if len(out) >= limit:
+            break
+    return out
+
+
+def l2_probe_leg(D):
+    """the L2 peak must be measured.  Row gathers / vector REDs per second (giga per-lane operations) at
+    pseudo-random rows of a 64 MB table (what one main grid is), one row per lane -- the access pattern of the encode
+    kernels and nothing else (csrc/tn_probe.cu)."""
+    from nerfstudio_thermal_b200._lib import call, ptr, stream
+
+    log2_rows, iters, ctas = 23, 64, 148 * 8
+    table = torch.zeros((1 << log2_rows, 2), device=D.dev)
+    sink = torch.zeros(1, device=D.dev)
+    out = {"table_MB": (8 << log2_rows) / 1e6, "unit": "G lane-operations/s"}
+    for mode, name in ((0, "gather8"), (1, "gather8_pair"), (2, "red_v2"), (3, "red_v2_pair")):
+        best = float("inf")
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call("tn_l2_probe", mode, ptr(table), log2_rows, iters, ctas, ptr(sink), stream())
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        out[name] = ctas * 256 * iters / (best * 1e-3) / 1e9
+    out["gather8_GBps"] = out["gather8"] * 8
+    out["red_v2_GBps"] = out["red_v2"] * 8
+    return out
+
+
+def shared8192_leg(args, D, steps, peaks, l2):
+    """BASELINE.json configs[3]: density_mode=shared (one RGBT field, density_loss and cross_channel_loss enabled as in
+    the reference's defaults), 8192 rays/GPU, proposal sampler 256/96 + 48 samples; same step definition as the
+    headline (fwd + loss + bwd, gradient all-reduce for N > 1), captured as one CUDA graph."""
+    import copy
+
+    from nerfstudio_thermal_b200 import engine, parallel
+
+    a = copy.copy(args)
+    a.density_mode, a.rays = "shared", 8192
+    model = build_model(a).to(D.dev).train()
+    host = {k: v.pin_memory() for k, v in make_batch(a.rays, parallel.rank_seed(42, D.rank)).items()}
+    resident = {k: v.to(D.dev) for k, v in host.items()}
+    runner = engine.GraphedTrainStep(model, resident, use_graph=not args.eager, warmup=3)
+    for _ in range(3):
+        runner.step(None)
+    ms = D.timed(lambda: runner.step(None), steps) / steps
+    for _ in range(2):
+        runner.step(host).item()
+    ms_e2e = D.timed(lambda: runner.step(host).item(), steps) / steps
+    c = model.config
+    res = {"metric": METRIC, "value": D.world * a.rays / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms, "steps": steps,
+           "scaling": "weak",
+           "config": {"workload": train_workload(a), "rays_per_gpu": a.rays, "parallelism": f"dp{D.world}",
+                      "density_loss_mult": c.density_loss_mult, "cross_channel_loss_mult": c.cross_channel_loss_mult},
+           "e2e": {"value": D.world * a.rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                   "d2h_bytes_per_step": 4}}
+    del runner, model
+    torch.cuda.empty_cache()
+    return res
+
+
+def device_rays(n, seed, dev, num_cams=NUM_CAMERAS):
+    """make_batch's patch-structured rays, drawn on the device (the sweep's batches reach 4 M rays)."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    patches = n // 4
+    centre = torch.randn(patches, 3, generator=g, device=dev) * 0.3
+    origins = centre.repeat_interleave(4, 0) + torch.randn(n, 3, generator=g, device=dev) * 0.002
+    dirs = torch.nn.functional.normalize(torch.randn(patches, 3, generator=g, device=dev), dim=-1).repeat_interleave(4, 0)
+    directions = torch.nn.functional.normalize(dirs + torch.randn(n, 3, generator=g, device=dev) * 0.002, dim=-1)
+    cams = ((torch.arange(patches, device=dev) * num_cams) // patches).repeat_interleave(4)[:, None]
+    return dict(origins=origins, directions=directions, pixel_area=torch.full((n, 1), 1e-6, device=dev),
+                camera_indices=cams, image=torch.rand(n, 3, generator=g, device=dev),
+                is_thermal=(cams[:, 0] >= num_cams // 2).float())
+
+
+def sweep_leg(args, model19, D, peaks, l2, deadline):
+    """BASELINE.json configs[4]: rays per batch 2^16..2^22 x hash table 2^19 / 2^21 per level.  Per point of the grid:
+    render rays/s (the eval forward in chunks of 32768 rays, the batch sharded over the ranks = strong scaling) with
+    the encode forward's roofline fraction at that size; train rays/s (eager fwd + loss + bwd + all-reduce, rays PER
+    GPU) for the batch sizes whose activations are kept to tens of GB (2^16, 2^18).  Stops adding points when the
+    leg's time budget is used up (the line says which points ran)."""
+    import copy
+
+    import nerfstudio_thermal_b200 as tn
+    from nerfstudio_thermal_b200 import _lib, engine, parallel
+
+    dev = D.dev
+    out = []
+    for log2_T in (19, 21):
+        if log2_T == args.log2_hashmap_size:
+            model = model19
+        else:
+            a = copy.copy(args)
+            a.log2_hashmap_size = log2_T
+            model = build_model(a).to(dev)
+        chunk = model.config.eval_num_rays_per_chunk
+        for log2_R in range(16, 23):
+            if time.perf_counter() > deadline:
+                break
+            n = 1 << log2_R
+            model.eval()
+            rays = device_rays(n, 1000 + log2_R, dev)
+            spans = list(parallel.shard_chunks(n, chunk, D.rank, D.world))
+
+            def render_batch():
+                with torch.no_grad():
+                    for s, e in spans:
+                        model(tn.RayBundle(origins=rays["origins"][s:e], directions=rays["directions"][s:e],
+                                           pixel_area=rays["pixel_area"][s:e], camera_indices=rays["camera_indices"][s:e]))
+
+            if log2_R == 16:
+                render_batch()  # warm (allocator, host-side caches)
+            _lib.STATS.reset(timing=True)
+            ms = D.timed(render_batch, 1)
+            table = _lib.STATS.summary()
+            _lib.STATS.reset()
+            roofs = top_rooflines(table, peaks, l2, args.half_tables, prefix="tn_hash_encode_fwd", limit=1)
+            point = {"log2_rays": log2_R, "log2_T": log2_T, "render_rays_per_s": n / (ms * 1e-3), "render_ms": ms}
+            if roofs:
+                point["encode_fwd"] = {k: roofs[0][k] for k in ("achieved", "frac", "avg_launch_ms") if k in roofs[0]}
+                if "l2" in roofs[0]:
+                    point["encode_fwd"]["l2_frac"] = roofs[0]["l2"]["frac"]
+            if log2_R in (16, 18) and time.perf_counter() < deadline:
+                model.train()
+                batch = device_rays(n, parallel.rank_seed(2000 + log2_R, D.rank), dev)
+                runner = engine.GraphedTrainStep(model, batch, use_graph=False)
+                for _ in range(2):
+                    runner.step(None)
+                _lib.STATS.reset(timing=True)
+                tms = D.timed(lambda: runner.step(None), 2) / 2
+                table = _lib.STATS.summary()
+                _lib.STATS.reset()
+                point["train_rays_per_s"] = D.world * n / (tms * 1e-3)
+                point["train_ms"] = tms
+                for r in top_rooflines(table, peaks, l2, args.half_tables, prefix="tn_hash_encode_bwd", limit=1):
+                    point["encode_bwd"] = {k: r[k] for k in ("achieved", "frac", "avg_launch_ms") if k in r}
+                    if "l2" in r:
+                        point["encode_bwd"]["l2_frac"] = r["l2"]["frac"]
+                del runner, batch
+            out.append(point)
+            del rays
+            torch.cuda.empty_cache()
+        if model is not model19:
+            del model
+            torch.cuda.empty_cache()
+    model19.train()
+    return {"what": "rays per batch 2^16..2^22 x T in {2^19, 2^21}; render = eval forward sharded over the ranks, "
+                    "train = fwd+loss+bwd(+all-reduce) with that many rays PER GPU (eager launches)",
+            "unit": "rays/s", "n_gpus": D.world, "points": out}
 
 
 def shutdown_distributed():
@@ -349,21 +631,12 @@ def shutdown_distributed():
 
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
-    import torch.distributed as dist
-
     import nerfstudio_thermal_b200 as tn
     from nerfstudio_thermal_b200 import _lib, engine, parallel
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py --impl b200 needs a GPU (there is no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run"
-
+    t_start = time.perf_counter()
+    D = Dist(args.gpus)
+    world, rank, dev, dist = D.world, D.rank, D.dev, D.dist
     model = build_model(args).to(dev).train()
     if args.half_tables:
         for m in model.modules():
@@ -380,37 +653,19 @@ def run_b200(args):
     def step(batch):
         return runner.step(batch)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
-
     for _ in range(max(args.warmup, 3)):
         step(None)  # batch already resident in the runner's static device buffers
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(D.local_rank)
     clocks.start()
     _lib.STATS.reset()
-    ms_total = timed(lambda: step(None), args.steps)
+    ms_total = D.timed(lambda: step(None), args.steps)
     # end to end: pinned host batch -> device every step, loss read back every step
     def e2e_step():
         return step(host).item()  # pinned host batch -> static device buffers, replay, loss read back
 
     for _ in range(2):
         e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = D.timed(e2e_step, args.steps)
     clocks.stop_flag = True
     clocks.join()
 
@@ -434,7 +689,7 @@ def run_b200(args):
     # beside the headline, which BASELINE.json defines as fwd+bwd
     # (the headline is complete at this point: the extra legs never take it down -- on one GPU a failure is recorded
     # in the line, on several GPUs they only run on request, since a one-sided failure would strand the other ranks)
-    extra_legs = not args.no_optimizer_leg and (world == 1 or args.extra_legs)
+    extra_legs = not args.no_optimizer_leg and not args.train_only and (world == 1 or args.extra_legs)
     extra_errors = {}
     opt_ms = None
     opt_in_graph = True
@@ -446,7 +701,8 @@ def run_b200(args):
             opt_in_graph = world == 1 or opt_runner._comm_in_graph
             for _ in range(3):
                 opt_runner.step(None)
-            opt_ms = timed(lambda: opt_runner.step(None), args.steps) / args.steps
+            opt_ms = D.timed(lambda: opt_runner.step(None), args.steps) / args.steps
+            del opt_runner
         except Exception as exc:  # noqa: BLE001
             if world > 1:
                 raise
@@ -472,7 +728,8 @@ def run_b200(args):
                                                  optimizer=optim.thermal_nerfacto_optimizers())
             for _ in range(3):
                 dev_runner.step()
-            dev_ms = timed(lambda: dev_runner.step(), args.steps) / args.steps
+            dev_ms = D.timed(lambda: dev_runner.step(), args.steps) / args.steps
+            del dev_runner, src, images
         except Exception as exc:  # noqa: BLE001
             if world > 1:
                 raise
@@ -481,53 +738,47 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = world * R / (ms_step * 1e-3)
     e2e_value = world * R / (ms_e2e / args.steps * 1e-3)
+    peaks = measured_peaks()
+    l2 = None
+    if not args.train_only:
+        try:
+            l2 = l2_probe_leg(D)
+        except Exception as exc:  # noqa: BLE001
+            extra_errors["l2_probe"] = f"{type(exc).__name__}: {exc}"
     line = None
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        kern_ms = sum(ms for _, ms in table.values()) / args.steps
-        enc = {k: v for k, v in table.items() if k.startswith("tn_hash_encode")}
-        dom_tag, (dom_n, dom_ms) = max(enc.items(), key=lambda kv: kv[1][1])
-        L = 16 if "[L16" in dom_tag else 5
-        bwd = "bwd" in dom_tag
-        tb = 2 if (args.half_tables and not bwd) else 4
-        pts = {16: R * 48, 5: R * 256}  # points per launch (proposal level 0: 256, level 1: 96 -> weighted below)
-        n_per_step = dom_n / args.steps
-        if L == 16:
-            pts_per_launch = R * 48
-        else:
-            pts_per_launch = R * (256 + 96) / 2.0  # the two proposal levels share the tag; average launch
-        alg = algorithmic_bytes_per_point(L, 2, tb, bwd, dx="dx" in dom_tag) * pts_per_launch
-        avg_ms = dom_ms / dom_n
-        achieved = alg / (avg_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):  # DRAM bytes per launch of this kernel from the committed ncu capture
-            traffic = json.load(open(tpath)).get(dom_tag)
-        roofline = {"bound": "hbm", "kernel": dom_tag, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "launches_per_step": n_per_step, "avg_launch_ms": avg_ms,
-                    "algorithmic_bytes_per_launch": alg, "share_of_kernel_time": dom_ms / args.steps / kern_ms}
+        kern_ms = sum(ms for _, ms, _u in table.values()) / args.steps
+        roofs = top_rooflines(table, peaks, l2, args.half_tables)
+        traffic = load_traffic()
+        for r in roofs:
+            r["launches_per_step"] = r.pop("launches") / args.steps
+            r["traffic"] = traffic.get(r["kernel"])
+        # the dominant kernel = the launch tag with the largest total time among ALL of this library's kernels
+        roofline = dict(roofs[0]) if roofs else None
+        if roofline is not None:
+            roofline["traffic_source"] = traffic.get("_source")
+            if roofline["kernel"].startswith("tn_hash_encode") or roofline["kernel"].startswith("tn_prop_density"):
+                roofline["bound_detail"] = ("L2 sector requests (row gathers + vector REDs), not DRAM bytes: the tables "
+                                            "are L2-resident; see roofline.l2 for the fraction of the measured L2 rates")
         if args.profile_kernels:
-            for k, (n, ms) in sorted(table.items(), key=lambda kv: -kv[1][1]):
-                print(f"{k:58s} {n / args.steps:6.1f} launches/step {ms / args.steps:8.3f} ms/step", file=sys.stderr)
-            print(f"sum of libtn_b200 kernels {kern_ms:.3f} ms/step; step {ms_step:.3f} ms", file=sys.stderr)
+            print_kernel_table(table, args.steps, ms_step, "train")
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if not args.half_tables else "f32 (f16 table gathers)",
             "data": "synthetic",
-            "config": {"workload": f"thermal-nerfacto train step (fwd + loss + bwd), density_mode={args.density_mode}, "
-                                   f"{R} rays/GPU, main grids 16x2^{args.log2_hashmap_size}x2, proposal grids 5x2^17x2, "
-                                   "samples 256/96+48",
+            "config": {"workload": train_workload(args),
                        "rays_per_gpu": R, "init": args.init, "parallelism": f"dp{world}",
                        "l2": "no explicit flush: tables + gradient buffers touched every step (~310 MB) exceed the 126 MB L2",
+                       "batch": "the timed legs replay one resident batch; the device_pipeline leg draws fresh rays "
+                                "every step and runs at the same speed, so the fixed batch buys no cache advantage",
                        "optimizer_step": "not in the timed region (metric is fwd+bwd)",
                        "launch": "eager" if args.eager else "whole step replayed as one CUDA graph "
                                  "(nerfstudio_thermal_b200.engine.GraphedTrainStep)"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
-            "kernel_ms_per_step": kern_ms, "roofline": roofline, "clocks": clocks.result(),
+            "kernel_ms_per_step": kern_ms, "roofline": roofline, "rooflines": roofs, "clocks": clocks.result(),
         }
         if dev_ms is not None:
             line["device_pipeline"] = {"value": world * R / (dev_ms * 1e-3), "unit": "rays/s", "ms_per_step": dev_ms,
@@ -540,8 +791,47 @@ def run_b200(args):
                                       "what": "the same step plus one fused Adam + LR-schedule launch over all 7 "
                                               "parameter groups (dense, 38.8 M parameters), "
                                               + ("inside the captured graph" if opt_in_graph else "after the all-reduce")}
+
+    # ---- the rest of BASELINE.json's metric, as `legs` of the same line.  The headline above is complete; if a leg
+    # stalls (a one-sided failure at N > 1 would strand the other ranks in a collective) a watchdog on rank 0 prints the
+    # line without the missing legs and ends the process, so the driver's command always returns its JSON line.
+    legs = {}
+    printed = threading.Event()
+
+    def emit():
+        if rank != 0 or printed.is_set():
+            return
+        printed.set()
+        line["legs"] = legs
         for k, v in extra_errors.items():
-            line[k] = {"error": v}
+            line.setdefault("errors", {})[k] = v
+        print(json.dumps(line), flush=True)
+
+    if not args.train_only:
+        def watchdog():
+            if not printed.is_set():
+                extra_errors["legs"] = "watchdog: legs did not finish in time; line printed without them"
+                emit()
+                os._exit(0)
+
+        wd = threading.Timer(max(60.0, 400.0 - (time.perf_counter() - t_start)), watchdog)
+        wd.daemon = True
+        wd.start()
+        if l2 is not None:
+            legs["l2_probe"] = l2
+        leg_steps = max(3, min(args.steps, 10))
+        for name, fn in (("render", lambda: render_leg(args, model, D, 3, 1, peaks, l2, profile=args.profile_kernels)),
+                         ("shared8192", lambda: shared8192_leg(args, D, leg_steps, peaks, l2)),
+                         ("sweep", lambda: sweep_leg(args, model, D, peaks, l2, time.perf_counter() + 60.0))):
+            try:
+                t0 = time.perf_counter()
+                legs[name] = fn()
+                legs[name]["wall_s"] = round(time.perf_counter() - t0, 1)
+            except Exception as exc:  # noqa: BLE001
+                if world > 1:
+                    raise
+                extra_errors[name] = f"{type(exc).__name__}: {exc}"
+        wd.cancel()
     if world > 1:
         dist.barrier()
     if rank == 0:
@@ -552,7 +842,7 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": R / sec, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"1 step of the full {R}-ray batch ({sec:.2f} s) after a 1024-ray warm-up "
                                               f"step ({t_small:.2f} s); total {time.perf_counter() - t0:.1f} s"}
-        print(json.dumps(line), flush=True)
+        emit()
     if world > 1:
         shutdown_distributed()
 

@@ -351,6 +351,17 @@ int tn_grad_unscale_check(const float* grads, int64_t n, const float* inv_scale_
 /* counter_dev[0] += value (the device-side step counter read by tn_adam_step inside a captured graph). */
 int tn_counter_add(int32_t* counter_dev, int value, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aid (bench.py, SURVEY 8d "L2 peak must be measured"): the access pattern of the hash-grid kernels
+ * and nothing else.  Every thread of `ctas` x 256 issues `iters` (multiple of 8) operations at pseudo-random rows
+ * of table[2^log2_rows, 2] (float32, 16-byte aligned; REDs modify it):
+ *   mode 0 8-byte gathers, a row per lane | 1 lanes 2i,2i+1 read an aligned pair of rows | 6 four lanes read one
+ *   32-byte sector | 2 8-byte vector REDs, a row per lane | 3 lane pairs add to an aligned pair of rows |
+ *   4 16-byte vector REDs | 5 4-byte REDs | 7, 8 gathers / 9, 10 REDs by lane pairs at rows (r, r^3) = same sector,
+ *   other 16-byte half / (r, r^7) = same 128-byte line, other sector.   sink: one float, never written in practice.
+ * ------------------------------------------------------------------------------------------------ */
+int tn_l2_probe(int mode, float* table, int log2_rows, int iters, int ctas, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "tn_step_counters_tick": [_P, c_int, c_uint, _P],
     "tn_grad_unscale_check": [_P, c_int64, _P, _P, _P],
     "tn_counter_add": [_P, c_int, _P],
+    "tn_l2_probe": [c_int, _P, c_int, c_int, c_int, _P, _P],
 }
 _RESTYPES = {"tn_last_error_string": c_char_p, "tn_build_arch": c_char_p}
 
@@ -106,8 +107,9 @@ class LaunchStats:
     """Launch counter and optional per-launch CUDA-event timing of the C-ABI calls (bench.py / profiling).
 
     `count` always counts launches.  With `timing=True` every call is bracketed by two events on the current
-    stream; `summary()` (after a synchronize) returns {tag: (launches, total_ms)} where tag = entry point name
-    plus the caller-supplied shape tag."""
+    stream; `summary()` (after a synchronize) returns {tag: (launches, total_ms, total_units)} where tag = entry
+    point name plus the caller-supplied shape tag and units = what the caller says a launch processed (points,
+    samples; 0 when not given) -- the multiplier of the per-unit algorithmic bytes in the rooflines."""
 
     def __init__(self):
         self.count = 0
@@ -120,16 +122,16 @@ class LaunchStats:
 
     def summary(self):
         out = {}
-        for tag, e0, e1 in self.events:
-            n, ms = out.get(tag, (0, 0.0))
-            out[tag] = (n + 1, ms + e0.elapsed_time(e1))
+        for tag, e0, e1, units in self.events:
+            n, ms, u = out.get(tag, (0, 0.0, 0))
+            out[tag] = (n + 1, ms + e0.elapsed_time(e1), u + units)
         return out
 
 
 STATS = LaunchStats()
 
 
-def call(name, *args, tag=""):
+def call(name, *args, tag="", units=0):
     """Invoke an int-returning entry point; map non-zero codes to TnKernelError."""
     lib = load()
     STATS.count += 1
@@ -138,7 +140,7 @@ def call(name, *args, tag=""):
         e0.record()
         rc = getattr(lib, name)(*args)
         e1.record()
-        STATS.events.append((f"{name}{tag}", e0, e1))
+        STATS.events.append((f"{name}{tag}", e0, e1, int(units)))
     else:
         rc = getattr(lib, name)(*args)
     if rc != 0:

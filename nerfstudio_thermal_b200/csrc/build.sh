@@ -26,6 +26,7 @@ build tn_fused.cu
 build tn_model.cu
 build tn_optim.cu
 build tn_api.cu
+build tn_probe.cu
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 $NVCC -shared -gencode arch=compute_100a,code=sm_100a -o "$OUT/libtn_b200.so" "$OBJ"/*.o -lcudart
 echo "built $OUT/libtn_b200.so"

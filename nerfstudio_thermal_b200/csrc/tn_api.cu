@@ -26,6 +26,16 @@ float agg_threshold_enc_patch() {
   static const float v = env_float("TN_AGG_ENC_PATCH", 300.f);
   return v;
 }
+// smallest level scale from which the gathers use the lane-pair access (finer levels: few duplicate cells in a warp)
+float pair_threshold_enc() {
+  static const float v = env_float("TN_PAIR_ENC", 150.f);
+  return v;
+}
+// 1: REDs use the lane-pair access on every level
+int pair_reds() {
+  static const int v = (int)env_float("TN_PAIR_RED", 1.f);
+  return v;
+}
 float agg_threshold_prop() {
   static const float v = env_float("TN_AGG_PROP", 96.f);
   return v;

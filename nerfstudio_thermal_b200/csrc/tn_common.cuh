@@ -43,6 +43,8 @@ constexpr int kNumSMs = 148;  // B200
 float agg_threshold_enc();
 float agg_threshold_enc_patch();
 float agg_threshold_prop();
+float pair_threshold_enc();  // TN_PAIR_ENC: level scale from which gathers use the lane-pair access (tn_encode_core.cuh)
+int pair_reds();             // TN_PAIR_RED: 0 switches the lane-pair REDs off (A/B measurements)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -47,8 +47,8 @@ template <int F, bool HALF, bool WRITE_IDX, bool JAC = false>
 __global__ void __launch_bounds__(kMaxTile, 3) hash_fwd_kernel(const float* __restrict__ x,
                                                                const void* __restrict__ table, LevelScales sc,
                                                                int64_t N, int L, int log2T, int patch_S,
-                                                               float* __restrict__ out, int32_t* __restrict__ idx_out,
-                                                               float* __restrict__ jac) {
+                                                               int pair_from, float* __restrict__ out,
+                                                               int32_t* __restrict__ idx_out, float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   __shared__ float s_scale[TN_MAX_LEVELS];
   float* tile = reinterpret_cast<float*>(smem4);
@@ -76,10 +76,19 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_fwd_kernel(const float* __re
       const int l = min(l0 + b, L - 1);
       c[b] = locate(x0, x1, x2, s_scale[l], mask, (uint32_t)l * T);
     }
+    if (l0 >= pair_from) {  // warp-uniform: fine levels fetch x-neighbour corners by lane pairs (tn_encode_core.cuh)
+      const bool odd = tid & 1;
+      PairRows pr[kLevelBatch];
 #pragma unroll
-    for (int b = 0; b < kLevelBatch; ++b)
+      for (int b = 0; b < kLevelBatch; ++b) pr[b] = exchange_rows(c[b], odd);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c[b].idx[k], f[b][k]);
+      for (int b = 0; b < kLevelBatch; ++b) load_cell_paired<F, HALF>(table, c[b], pr[b], odd, f[b]);
+    } else {
+#pragma unroll
+      for (int b = 0; b < kLevelBatch; ++b)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c[b].idx[k], f[b][k]);
+    }
 #pragma unroll
     for (int b = 0; b < kLevelBatch; ++b) {
       const int l = l0 + b;
@@ -169,8 +178,9 @@ template <int F, bool HALF, bool NEED_DX, bool JAC = false>
 __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __restrict__ x,
                                                                const void* __restrict__ table, LevelScales sc,
                                                                const float* __restrict__ dy, int64_t N, int L,
-                                                               int log2T, int n_agg, int patch_S,
-                                                               float* __restrict__ dtable, float* __restrict__ dx,
+                                                               int log2T, int n_agg, int patch_S, int pair_from,
+                                                               int pair_red, float* __restrict__ dtable,
+                                                               float* __restrict__ dx,
                                                                const float* __restrict__ jac) {
   extern __shared__ float4 smem4[];
   float* tile = reinterpret_cast<float*>(smem4);
@@ -203,9 +213,8 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
   __syncthreads();
   const int rowmod = row_t % L;
   float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
-  // One level per iteration on purpose. Prefetching the next level's corner rows one iteration ahead (16 gathers
-  // in flight) and merging x-neighbour rows into 16-byte accesses were both measured and both lost: the kernel
-  // is bound by RED lanes, not by gather latency ("experiments that lost").
+  // One level per iteration.  (Prefetching the next level's corner rows one iteration ahead -- 16 gathers in flight --
+  // was measured and lost, DESIGN.md "experiments that lost".)
 #pragma unroll 1
   for (int l = 0; l < L; ++l) {
     const float scale = sc.s[l];
@@ -223,48 +232,75 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
       const float* js = jac + ((size_t)l * N + (valid ? p : 0)) * (F * 3);
 #pragma unroll
       for (int q = 0; q < F * 3; ++q) jv[q] = __ldg(js + q);
-    } else if constexpr (NEED_DX) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
     }
-    float dox = 0.f, doy = 0.f, doz = 0.f;
+    const bool odd = lane & 1;
+    PairRows pr;
+    if (pair_red || l >= pair_from) pr = exchange_rows(c, odd);  // (warp-uniform conditions)
+    // The gathers (for dL/dx) are issued first and consumed LAST: the gradient scatter below -- corner weights,
+    // warp aggregation, REDs -- does not depend on them and runs while they are in flight.
+    if constexpr (NEED_DX && !JAC) {
+      if (l >= pair_from) {
+        load_cell_paired_issue<F, HALF>(table, c, pr, odd, f);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) load_row<F, HALF>(table, c.idx[k], f[k]);
+      }
+    }
+    float gq[F][4];  // g03, g12, g56, g47 per feature (reused by dL/dx)
 #pragma unroll
     for (int j = 0; j < F; ++j) {
       const float g0312 = g[j] * c.oz, g4756 = g[j] * mz;
       const float g03 = g0312 * c.oy, g12 = g0312 * my;
       const float g47 = g4756 * c.oy, g56 = g4756 * my;
+      gq[j][0] = g03; gq[j][1] = g12; gq[j][2] = g56; gq[j][3] = g47;
       gc[0][j] = g03 * c.ox; gc[3][j] = g03 * mx;
       gc[1][j] = g12 * c.ox; gc[2][j] = g12 * mx;
       gc[5][j] = g56 * c.ox; gc[6][j] = g56 * mx;
       gc[4][j] = g47 * c.ox; gc[7][j] = g47 * mx;
-      if constexpr (NEED_DX && JAC) {
-        dox += g[j] * jv[j * 3]; doy += g[j] * jv[j * 3 + 1]; doz += g[j] * jv[j * 3 + 2];
-      } else if constexpr (NEED_DX) {
-        const float f03 = f[0][j] * c.ox + f[3][j] * mx;
-        const float f12 = f[1][j] * c.ox + f[2][j] * mx;
-        const float f56 = f[5][j] * c.ox + f[6][j] * mx;
-        const float f47 = f[4][j] * c.ox + f[7][j] * mx;
-        const float f0312 = f03 * c.oy + f12 * my;
-        const float f4756 = f47 * c.oy + f56 * my;
-        dox += g03 * (f[0][j] - f[3][j]) + g12 * (f[1][j] - f[2][j]) + g56 * (f[5][j] - f[6][j]) +
-               g47 * (f[4][j] - f[7][j]);
-        doy += g0312 * (f03 - f12) + g4756 * (f47 - f56);
-        doz += g[j] * (f0312 - f4756);
-      }
-    }
-    if constexpr (NEED_DX && JAC) {
-      dx0 += dox; dx1 += doy; dx2 += doz;  // the stored Jacobian carries the level scale
-    } else if constexpr (NEED_DX) {
-      dx0 += dox * scale; dx1 += doy * scale; dx2 += doz * scale;
     }
     bool issue = valid;
     if (l < n_agg) {  // warp-uniform branch; lanes without a point get a key no other lane has
       const uint64_t key = valid ? c.key : ((1ull << 63) | (uint64_t)lane);
       issue = aggregate_equal_cells<F>(key, lane, gc) && valid;
     }
-    if (issue) {
+    if (pair_red) {
+      red_cell_paired<F>(dtable, c, pr, lane, issue, gc);
+    } else if (issue) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) red_row<F>(dtable, c.idx[k], gc[k]);
+    }
+    // ---- dL/dx of this level
+    if constexpr (NEED_DX && JAC) {
+      float dox = 0.f, doy = 0.f, doz = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        dox += g[j] * jv[j * 3]; doy += g[j] * jv[j * 3 + 1]; doz += g[j] * jv[j * 3 + 2];
+      }
+      dx0 += dox; dx1 += doy; dx2 += doz;  // the stored Jacobian carries the level scale
+    } else if constexpr (NEED_DX) {
+      if (l >= pair_from) {
+        float ff[8][F];
+        load_cell_paired_finish<F>(f, odd, ff);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int j = 0; j < F; ++j) f[k][j] = ff[k][j];
+      }
+      float dox = 0.f, doy = 0.f, doz = 0.f;
+#pragma unroll
+      for (int j = 0; j < F; ++j) {
+        const float f03 = f[0][j] * c.ox + f[3][j] * mx;
+        const float f12 = f[1][j] * c.ox + f[2][j] * mx;
+        const float f56 = f[5][j] * c.ox + f[6][j] * mx;
+        const float f47 = f[4][j] * c.ox + f[7][j] * mx;
+        const float f0312 = f03 * c.oy + f12 * my;
+        const float f4756 = f47 * c.oy + f56 * my;
+        dox += gq[j][0] * (f[0][j] - f[3][j]) + gq[j][1] * (f[1][j] - f[2][j]) + gq[j][2] * (f[5][j] - f[6][j]) +
+               gq[j][3] * (f[4][j] - f[7][j]);
+        doy += (g[j] * c.oz) * (f03 - f12) + (g[j] * mz) * (f47 - f56);
+        doz += g[j] * (f0312 - f4756);
+      }
+      dx0 += dox * scale; dx1 += doy * scale; dx2 += doz * scale;
     }
   }
   if constexpr (NEED_DX) {
@@ -298,22 +334,31 @@ static TileShape tile_shape(int64_t N, int samples_per_ray) {
   return {kPts, 0};
 }
 
+// first level (a multiple of the forward's level batch) whose gathers use the lane-pair access
+static int pair_from_level(const LevelScales& sc, int L) {
+  const float thr = pair_threshold_enc();
+  int l = 0;
+  while (l < L && sc.s[l] < thr) ++l;
+  return (l + kLevelBatch - 1) / kLevelBatch * kLevelBatch;
+}
+
 template <int F>
 static int launch_fwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, int64_t N, int L,
                       int log2_T, int samples_per_ray, float* out, int32_t* idx_out, float* jac, cudaStream_t st) {
   const TileShape ts = tile_shape(N, samples_per_ray);
+  const int pair_from = pair_from_level(sc, L);
   const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
   const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_FWD(H, W)                                                                                         \
   do {                                                                                                       \
     auto k = hash_fwd_kernel<F, H, W>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, out, idx_out, jac);             \
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, idx_out, jac);  \
   } while (0)
   if (jac) {  // (no index dump on this path: checked by the caller)
     auto k = table_dtype == 0 ? hash_fwd_kernel<F, false, false, true> : hash_fwd_kernel<F, true, false, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, out, nullptr, jac);
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, nullptr, jac);
   } else if (table_dtype == 0) {
     if (idx_out) TN_FWD(false, true); else TN_FWD(false, false);
   } else {
@@ -328,18 +373,21 @@ static int launch_bwd(const float* x, const void* table, int table_dtype, const 
                       int64_t N, int L, int log2_T, int n_agg, int samples_per_ray, float* dtable, float* dx,
                       const float* jac, cudaStream_t st) {
   const TileShape ts = tile_shape(N, samples_per_ray);
+  const int pair_from = pair_from_level(sc, L), pair_red = pair_reds();
   const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
   const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_BWD(H, D)                                                                                         \
   do {                                                                                                       \
     auto k = hash_bwd_kernel<F, H, D>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, dtable, dx, jac);    \
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, pair_from, pair_red, \
+                                      dtable, dx, jac);                                                      \
   } while (0)
   if (jac && dx) {
     auto k = table_dtype == 0 ? hash_bwd_kernel<F, false, true, true> : hash_bwd_kernel<F, true, true, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, dtable, dx, jac);
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, pair_from, pair_red, dtable,
+                                      dx, jac);
   } else if (table_dtype == 0) {
     if (dx) TN_BWD(false, true); else TN_BWD(false, false);
   } else {

@@ -153,4 +153,95 @@ __device__ __forceinline__ void red_cell(float* __restrict__ dtable, const Cell&
   }
 }
 
+// ---- lane-pair access of x-neighbour corners -----------------------------------------------------------------
+// Measured (tools/probe_l2.py, profiles/r02_l2_probe.json): the L2 serves ~240 G sector requests/s to gathers and
+// ~160 G/s to REDs whatever their width, and two lanes of ONE instruction that touch the same sector cost one
+// request.  The floor-x and ceil-x corners of a cell sit at rows (x ^ h) and ((x+1) ^ h): the same 32-byte sector
+// for 3 of 4 cells (same 16 bytes when x is even, same sector when x = 1 mod 4).  So instead of "every lane
+// touches corner k of its own cell" (32 sectors per instruction), lanes 2i and 2i+1 touch the floor-x and the
+// ceil-x corner of the SAME cell -- first the even lane's cell, then the odd lane's -- and swap the results with
+// one shuffle: 1.25 sectors per corner pair instead of 2, for the same number of memory instructions.
+// Corner pairs (floor-x corner, ceil-x corner) in the reference's corner numbering:
+__device__ constexpr int kPf[4] = {3, 2, 7, 6};
+__device__ constexpr int kPc[4] = {0, 1, 4, 5};
+
+struct PairRows {
+  uint32_t other[4];  // even lane: the odd lane's floor-x rows; odd lane: the even lane's ceil-x rows
+};
+
+// (whole warp, converged)
+__device__ __forceinline__ PairRows exchange_rows(const Cell& c, bool odd) {
+  PairRows pr;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) pr.other[q] = __shfl_xor_sync(0xffffffffu, odd ? c.idx[kPf[q]] : c.idx[kPc[q]], 1);
+  return pr;
+}
+
+// The pairwise fetch in two steps, so that a caller can put independent work between the loads and their first use:
+// issue: raw[2q] = this lane's share of the even lane's pair q, raw[2q+1] = of the odd lane's pair q
+template <int F, bool HALF>
+__device__ __forceinline__ void load_cell_paired_issue(const void* __restrict__ table, const Cell& c,
+                                                       const PairRows& pr, bool odd, float (&raw)[8][F]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    load_row<F, HALF>(table, odd ? pr.other[q] : c.idx[kPf[q]], raw[2 * q]);      // even lane's cell: floor-x | ceil-x
+    load_row<F, HALF>(table, odd ? c.idx[kPc[q]] : pr.other[q], raw[2 * q + 1]);  // odd lane's cell
+  }
+}
+// finish: swap with the neighbouring lane; f[k] = corner k of this lane's cell (whole warp, converged)
+template <int F>
+__device__ __forceinline__ void load_cell_paired_finish(const float (&raw)[8][F], bool odd, float (&f)[8][F]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      const float recv = __shfl_xor_sync(0xffffffffu, odd ? raw[2 * q][j] : raw[2 * q + 1][j], 1);
+      f[kPf[q]][j] = odd ? recv : raw[2 * q][j];
+      f[kPc[q]][j] = odd ? raw[2 * q + 1][j] : recv;
+    }
+}
+
+// the eight corner rows of this lane's cell, fetched pairwise with the neighbouring lane (values identical to
+// load_cell); whole warp, converged
+template <int F, bool HALF>
+__device__ __forceinline__ void load_cell_paired(const void* __restrict__ table, const Cell& c, const PairRows& pr,
+                                                 bool odd, float (&f)[8][F]) {
+  float raw[8][F];
+  load_cell_paired_issue<F, HALF>(table, c, pr, odd, raw);
+  load_cell_paired_finish<F>(raw, odd, f);
+}
+
+// scatter-add of the eight corner gradients with the same pairing.  `issue`: this lane's cell is to be written
+// (false on lanes without a point and on lanes whose gradients were folded into another lane).  Whole warp, converged.
+template <int F>
+__device__ __forceinline__ void red_cell_paired(float* __restrict__ dtable, const Cell& c, const PairRows& pr, int lane,
+                                                bool issue, const float (&g)[8][F]) {
+  const bool odd = lane & 1;
+  const unsigned issuing = __ballot_sync(0xffffffffu, issue);
+  const bool issue_even = (issuing >> (lane & ~1)) & 1u, issue_odd = (issuing >> (lane | 1)) & 1u;
+  float recv[4][F];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int j = 0; j < F; ++j) recv[q][j] = __shfl_xor_sync(0xffffffffu, odd ? g[kPf[q]][j] : g[kPc[q]][j], 1);
+  if (issue_even) {  // the even lane's cell: even lane adds to the floor-x rows, odd lane to the ceil-x rows
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[F];
+#pragma unroll
+      for (int j = 0; j < F; ++j) v[j] = odd ? recv[q][j] : g[kPf[q]][j];
+      red_row<F>(dtable, odd ? pr.other[q] : c.idx[kPf[q]], v);
+    }
+  }
+  if (issue_odd) {  // the odd lane's cell
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[F];
+#pragma unroll
+      for (int j = 0; j < F; ++j) v[j] = odd ? g[kPc[q]][j] : recv[q][j];
+      red_row<F>(dtable, odd ? c.idx[kPc[q]] : pr.other[q], v);
+    }
+  }
+}
+
 }  // namespace tn

@@ -63,7 +63,8 @@ class _FieldHeadFn(torch.autograd.Function):
         need_mask = any(ctx.needs_input_grad)
         mask = torch.empty((n, 2, 2), device=h.device, dtype=torch.int32) if need_mask else None
         call("tn_field_head_fwd", ptr(h), ptr(sel), ptr(sh), ptr(emb_ray), rays, samples, out_dim, float(scale),
-             ptr_array(ws), ptr_array(bs), out_act, ptr(density), ptr(y), ptr(mask), stream(), tag=f"[63-64x2-{out_dim}]")
+             ptr_array(ws), ptr_array(bs), out_act, ptr(density), ptr(y), ptr(mask), stream(), tag=f"[63-64x2-{out_dim}]",
+             units=n)
         ctx.dims = (rays, samples, float(scale), out_dim, out_act)
         ctx.sinks = sinks
         ctx.set_materialize_grads(False)
@@ -88,7 +89,7 @@ class _FieldHeadFn(torch.autograd.Function):
         call("tn_field_head_bwd", ptr(_f32c(dy)), ptr(mask), ptr(h), ptr(sel), ptr(sh), ptr(emb_ray),
              ptr(None if d_density is None else _f32c(d_density)), rays, samples, out_dim, scale, ptr_array(ws),
              ptr_array(bs), out_act, ptr(dh), ptr(dz1_ray), ptr_array(dws), ptr_array(dbs), stream(),
-             tag=f"[63-64x2-{out_dim}]")
+             tag=f"[63-64x2-{out_dim}]", units=rays * samples)
         demb = dz1_ray @ ws[0][:, 31:63] if ctx.needs_input_grad[3] else None
         grads = []
         for dw, db in zip(dws, dbs):
@@ -157,7 +158,7 @@ class _PropDensityFn(torch.autograd.Function):
         density = torch.empty((r * s,), device=ebins.device)
         call("tn_prop_density_fwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
              spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), float(scale), ptr(density),
-             stream(), tag=f"[L{spec.num_levels},S{s}]")
+             stream(), tag=f"[L{spec.num_levels},S{s}]", units=r * s)
         ctx.spec, ctx.scale, ctx.grad_sink = spec, float(scale), grad_sink
         ctx.save_for_backward(origins, directions, ebins, table, w1, b1, w2, b2)
         return density
@@ -180,7 +181,7 @@ class _PropDensityFn(torch.autograd.Function):
         call("tn_prop_density_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
              spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), ctx.scale,
              ptr(_f32c(d_density)), ptr(dtable), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(d_o), ptr(d_d), stream(),
-             tag=f"[L{spec.num_levels},S{s}{',dx' if need_rays else ''}]")
+             tag=f"[L{spec.num_levels},S{s}{',dx' if need_rays else ''}]", units=r * s)
         dt = dtable if (ctx.needs_input_grad[3] and sink is None) else None
         if ms is not None:
             dw1 = db1 = dw2 = db2 = None

@@ -73,7 +73,7 @@ class _HashEncodeFn(torch.autograd.Function):
             jac = torch.empty((spec.num_levels, n, spec.features, 3), device=x.device)
         call("tn_hash_encode_fwd", ptr(x), ptr(src), dtype, spec._c_scales, n, spec.num_levels, spec.features,
              spec.log2_T, samples_per_ray, ptr(out), None, ptr(jac), stream(),
-             tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',jac' if jac is not None else ''}]")
+             tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',jac' if jac is not None else ''}]", units=n)
         ctx.spec = spec
         ctx.samples_per_ray = samples_per_ray
         ctx.grad_sink = grad_sink
@@ -98,7 +98,7 @@ class _HashEncodeFn(torch.autograd.Function):
         src, dtype = (table_f16, 1) if table_f16 is not None else (table, 0)
         call("tn_hash_encode_bwd", ptr(x), ptr(src), dtype, spec._c_scales, ptr(dy), n, spec.num_levels, spec.features,
              spec.log2_T, ctx.samples_per_ray, ptr(dtable), ptr(dx), ptr(jac if dx is not None else None), stream(),
-             tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',dx' if dx is not None else ''}]")
+             tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',dx' if dx is not None else ''}]", units=n)
         return dx, (dtable if (want_table and sink is None) else None), None, None, None, None
 
 
@@ -192,12 +192,12 @@ class _MlpFn(torch.autograd.Function):
             if MLP_BACKEND["bwd"] == "tc" and any(ctx.needs_input_grad):
                 mask = torch.empty((n, nl - 1, max(1, width // 32)), device=x.device, dtype=torch.int32)
             call("tn_mlp_tc_fwd", ptr(x), n, in_dim, x_stride, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act,
-                 ptr(row_mul), ctx.out_scale, ptr(y), ptr(mask), stream(), tag=tag)
+                 ptr(row_mul), ctx.out_scale, ptr(y), ptr(mask), stream(), tag=tag, units=n)
         else:
             assert row_mul is None and out_scale == 1.0, "output multipliers are a tensor-core epilogue (see mlp())"
             xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
             call("tn_mlp_fwd", ptr(xd), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs), out_act, ptr(y),
-                 stream(), tag=tag)
+                 stream(), tag=tag, units=n)
         ctx.out_act = out_act
         ctx.nl = nl
         ctx.save_for_backward(x, mask, row_mul, *ws, *bs)
@@ -228,12 +228,12 @@ class _MlpFn(torch.autograd.Function):
         if MLP_BACKEND["bwd"] == "tc":
             call("tn_mlp_tc_bwd", ptr(x), ptr(_f32c(dy)), ptr(mask), n, in_dim, x_stride, width, out_dim, nl,
                  ptr_array(ws), ptr_array(bs), ctx.out_act, ptr(row_mul), ctx.out_scale, ptr(dx), ptr_array(dws),
-                 ptr_array(dbs), stream(), tag=tag)
+                 ptr_array(dbs), stream(), tag=tag, units=n)
         else:
             xd = x if x_stride == in_dim else x[:, :in_dim].contiguous()
             dxd = dx if x_stride == in_dim or dx is None else torch.empty_like(xd)
             call("tn_mlp_bwd", ptr(xd), ptr(_f32c(dy)), n, in_dim, width, out_dim, nl, ptr_array(ws), ptr_array(bs),
-                 ctx.out_act, ptr(dxd), ptr_array(dws), ptr_array(dbs), stream(), tag=tag)
+                 ctx.out_act, ptr(dxd), ptr_array(dws), ptr_array(dbs), stream(), tag=tag, units=n)
             if dx is not None and dxd is not dx:
                 dx.zero_()
                 dx[:, :in_dim] = dxd
