@@ -352,6 +352,46 @@ int tn_grad_unscale_check(const float* grads, int64_t n, const float* inv_scale_
 int tn_counter_add(int32_t* counter_dev, int value, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * One launch per sampling level (csrc/tn_level.cu): the composite + resample kernels.  Same arithmetic as the
+ * single-purpose entry points above, so the results are theirs.
+ * ------------------------------------------------------------------------------------------------ */
+/* Proposal level.  replaces: cameras/rays.py:128-150 (get_weights) + renderers.py:547-557 (median depth of the
+ * level, the prop_depth_i outputs of models/nerfacto.py:346-351) + ray_samplers.py:301-372, :602 (annealed PDF
+ * resampling).  sigma[R,S], ebins/sbins [R,S+1] of this level; u_base / jitter / anneal_dev / histogram_padding /
+ * eps as tn_pdf_sample.  weights_out[R,S]; depth_median_out[R] or NULL; sbins_new/ebins_new [R,S_new+1], or both
+ * NULL for the weights (and depth) alone. */
+int tn_level_resample(const float* sigma, const float* ebins, const float* sbins, const float* nears,
+                      const float* fars, const float* u_base, const float* jitter, int jitter_per_sample,
+                      const float* anneal_dev, int64_t R, int S, int S_new, float histogram_padding, float eps,
+                      float* weights_out, float* depth_median_out, float* sbins_new, float* ebins_new,
+                      void* stream);
+/* Final level.  replaces: get_weights + every renderer of models/nerfacto.py:316-320 (arguments as
+ * tn_render_fwd with starts/ends = ebins[:, :-1] / ebins[:, 1:]) + model_components/losses.py:139-158
+ * (distortion) + losses.py:57-135 (interlevel loss against n_prop <= 2 proposal histograms prop_w[q][R,S_q],
+ * prop_sbins[q][R,S_q+1]).  loss_acc: NULL (no losses), or float[2] ACCUMULATED into: [0] += sum over rays of
+ * lossfun_distortion, [1] += sum over rays, levels and fine samples of lossfun_outer (the caller zero-fills and
+ * divides by R resp. R*S).  dw_distortion_out[R,S] / prop_dw[q][R,S_q]: NULL, or the gradients of those two sums
+ * w.r.t. the final / proposal weights, kept for tn_ray_heads_bwd. */
+int tn_ray_heads_fwd(const float* sigma, const float* colour, const float* ebins, const float* sbins, int64_t R,
+                     int S, int C, int bg_mode, const float* bg_host, int eval_mode, int n_prop,
+                     const float* const* prop_w_host_ptrs, const float* const* prop_sbins_host_ptrs,
+                     const int* prop_S_host, float* const* prop_dw_host_ptrs, float* weights_out, float* rgb_out,
+                     float* acc_out, float* depth_median_out, float* depth_expected_out, float* steps_minmax_out,
+                     float* loss_acc, float* dw_distortion_out, void* stream);
+/* The ray-level backward of a whole branch in one launch.  Final level: d_rgb[R,C], d_acc[R], d_depth_expected[R]
+ * (each may be NULL) and g_distortion_dev (device scalar dL/d(mean distortion), NULL = 0) times dw_distortion ->
+ * get_weights backward -> dsigma_out[R,S], dcolour_out[R,S,C] (NULL: not wanted).  Proposal level q:
+ * g_interlevel_dev (device scalar dL/d(mean interlevel loss)) / (R*S) * prop_dw[q] -> get_weights backward with that
+ * level's prop_sigma[q][R,S_q], prop_ebins[q][R,S_q+1] -> prop_dsigma[q][R,S_q]. */
+int tn_ray_heads_bwd(const float* sigma, const float* colour, const float* ebins, const float* weights,
+                     const float* dw_distortion, const float* d_rgb, const float* d_acc,
+                     const float* d_depth_expected, const float* g_distortion_dev, const float* g_interlevel_dev,
+                     int64_t R, int S, int C, int bg_mode, const float* bg_host, int n_prop,
+                     const float* const* prop_sigma_host_ptrs, const float* const* prop_ebins_host_ptrs,
+                     const float* const* prop_dw_host_ptrs, const int* prop_S_host, float* dsigma_out,
+                     float* dcolour_out, float* const* prop_dsigma_host_ptrs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement aid (bench.py, SURVEY 8d "L2 peak must be measured"): the access pattern of the hash-grid kernels
  * and nothing else.  Every thread of `ctas` x 256 issues `iters` (multiple of 8) operations at pseudo-random rows
  * of table[2^log2_rows, 2] (float32, 16-byte aligned; REDs modify it):

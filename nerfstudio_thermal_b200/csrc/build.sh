@@ -20,6 +20,7 @@ build tn_encode.cu -fmad=false
 build tn_geometry.cu -fmad=false
 build tn_ray.cu -fmad=false
 build tn_prop.cu -fmad=false
+build tn_level.cu -fmad=false
 build tn_mlp.cu
 build tn_mlp_tc.cu
 build tn_fused.cu

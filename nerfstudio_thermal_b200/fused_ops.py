@@ -448,3 +448,139 @@ def loss_sum(entries) -> Tuple[Tensor, dict]:
     out = _LossSumFn.apply(tuple(float(s) for _, _, s in entries), tuple(names.index(n) for n, _, _ in entries),
                            *[t for _, t, _ in entries])
     return out[0], dict(zip(names, out[1:]))
+
+
+# ----------------------------------------------------------------------------------- one launch per sampling level
+_HEADS_INIT = {}
+
+
+def _heads_scratch(device) -> Tensor:
+    """[+inf, -inf, 0, 0]: the (min, max) of the sample midpoints and the two loss accumulators of a ray_heads
+    launch, cloned from a cached device constant (no host->device copy: CUDA-graph capture safe)."""
+    k = str(device)
+    if k not in _HEADS_INIT:
+        _HEADS_INIT[k] = torch.tensor([float("inf"), float("-inf"), 0.0, 0.0]).to(device)
+    return _HEADS_INIT[k].clone()
+
+
+@torch.no_grad()
+def level_resample(sigma: Tensor, ebins: Tensor, sbins: Tensor, nears: Tensor, fars: Tensor, num_samples: int,
+                   jitter: Optional[Tensor], anneal: Optional[Tensor] = None, histogram_padding: float = 0.01,
+                   eps: float = 1e-5, want_depth: bool = True):
+    """One proposal level after its density: get_weights -> median depth -> annealed PDF resampling in ONE launch
+    (cameras/rays.py:128-150, renderers.py:547-557, ray_samplers.py:301-372 / :602).  The sampling chain carries no
+    gradient in the reference (ray_samplers.py:360 detaches the bins), so this runs outside autograd.
+    sigma [R,S] -> (weights [R,S], median depth [R,1] | None, sbins_new, ebins_new [R,num_samples+1])."""
+    from . import ops
+
+    sigma, ebins, sbins = _f32c(sigma), _f32c(ebins), _f32c(sbins)
+    r, s = sigma.shape
+    nb = num_samples + 1
+    dev = sigma.device
+    if jitter is None:
+        u = ops._host_linspace(("u_eval", nb), lambda: torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb) + 1.0 / (2 * nb),
+                               dev)
+    else:
+        u = ops._host_linspace(("u_train", nb), lambda: torch.linspace(0.0, 1.0 - (1.0 / nb), steps=nb), dev)
+    jit, per_sample = ops._jitter_arg(jitter, r, nb)
+    w = torch.empty_like(sigma)
+    med = torch.empty((r, 1), device=dev) if want_depth else None
+    sb = torch.empty((r, nb), device=dev)
+    eb = torch.empty_like(sb)
+    call("tn_level_resample", ptr(sigma), ptr(ebins), ptr(sbins), ptr(_f32c(nears).view(-1)), ptr(_f32c(fars).view(-1)),
+         ptr(u), ptr(jit), per_sample, ptr(anneal), r, s, num_samples, float(histogram_padding), float(eps), ptr(w),
+         ptr(med), ptr(sb), ptr(eb), stream(), tag=f"[S{s}->{num_samples}]", units=r * s)
+    return w, med, sb, eb
+
+
+class _RayHeadsFn(torch.autograd.Function):
+    """Final level of a branch as ONE autograd node: get_weights + all renderers + distortion + interlevel loss
+    forward (tn_ray_heads_fwd), and the ray-level backward of the whole branch -- final level and every proposal
+    level -- in one launch (tn_ray_heads_bwd)."""
+
+    @staticmethod
+    def forward(ctx, sigma, colour, ebins, sbins, bg_mode, bg, eval_mode, want_losses, prop_ebins, prop_sbins,
+                prop_weights, *prop_sigma):
+        sigma, colour, ebins, sbins = _f32c(sigma), _f32c(colour), _f32c(ebins), _f32c(sbins)
+        r, s = sigma.shape
+        c = colour.shape[-1]
+        colour = colour.view(r, s, c)
+        dev = sigma.device
+        n_prop = len(prop_weights) if want_losses else 0
+        prop_weights = [_f32c(t).view(r, -1) for t in prop_weights[:n_prop]]
+        prop_sbins = [_f32c(t) for t in prop_sbins[:n_prop]]
+        prop_S = [t.shape[1] for t in prop_weights]
+        need_prop_grad = [want_losses and i < len(prop_sigma) and ctx.needs_input_grad[11 + i] for i in range(n_prop)]
+        prop_dw = [torch.empty_like(prop_weights[i]) if need_prop_grad[i] else None for i in range(n_prop)]
+        w = torch.empty_like(sigma)
+        rgb = torch.empty((r, c), device=dev)
+        acc = torch.empty((r, 1), device=dev)
+        med = torch.empty((r, 1), device=dev)
+        exp = torch.empty((r, 1), device=dev)
+        scratch = _heads_scratch(dev)
+        minmax, loss_acc = scratch[:2], scratch[2:]
+        dw_dist = torch.empty_like(sigma) if (want_losses and ctx.needs_input_grad[0]) else None
+        bg_arr = float_array(bg) if bg is not None else None
+        ints = (ctypes.c_int * max(n_prop, 1))(*(prop_S or [0]))
+        call("tn_ray_heads_fwd", ptr(sigma), ptr(colour), ptr(ebins), ptr(sbins), r, s, c, bg_mode, bg_arr,
+             int(eval_mode), n_prop, ptr_array(prop_weights) if n_prop else None,
+             ptr_array(prop_sbins) if n_prop else None, ints, ptr_array(prop_dw) if n_prop else None, ptr(w), ptr(rgb),
+             ptr(acc), ptr(med), ptr(exp), ptr(minmax), ptr(loss_acc) if want_losses else None, ptr(dw_dist), stream(),
+             tag=f"[S{s},C{c}]", units=r * s)
+        ctx.cfg = (bg_mode, bg, c, [i for i in range(n_prop) if need_prop_grad[i]], prop_S)
+        ctx.set_materialize_grads(False)
+        live = [i for i in range(n_prop) if need_prop_grad[i]]
+        ctx.n_live = len(live)
+        ctx.save_for_backward(sigma, colour, ebins, w, dw_dist, *[_f32c(prop_sigma[i]).view(r, -1) for i in live],
+                              *[_f32c(prop_ebins[i]) for i in live], *[prop_dw[i] for i in live])
+        if want_losses:  # means over rays / over rays x fine samples (losses.py:135, :158)
+            dist, inter = (loss_acc * _loss_scales(dev, r, s)).unbind(0)
+        else:
+            dist = inter = None
+        ctx.mark_non_differentiable(w, med, minmax)
+        return rgb, acc, med, exp, minmax, w, dist, inter
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, _d_med, d_exp, _d_mm, _d_w, g_dist, g_inter):
+        bg_mode, bg, c, live, prop_S = ctx.cfg
+        saved = ctx.saved_tensors
+        sigma, colour, ebins, w, dw_dist = saved[:5]
+        k = ctx.n_live
+        p_sigma, p_ebins, p_dw = saved[5:5 + k], saved[5 + k:5 + 2 * k], saved[5 + 2 * k:5 + 3 * k]
+        r, s = sigma.shape
+        dsigma = torch.empty_like(sigma)
+        dcol = torch.empty_like(colour) if ctx.needs_input_grad[1] else None
+        p_dsigma = [torch.empty_like(t) for t in p_sigma]
+        bg_arr = float_array(bg) if bg is not None else None
+        f = lambda t: None if t is None else _f32c(t)  # noqa: E731
+        ints = (ctypes.c_int * max(k, 1))(*([prop_S[i] for i in live] or [0]))
+        call("tn_ray_heads_bwd", ptr(sigma), ptr(colour), ptr(ebins), ptr(w), ptr(dw_dist), ptr(f(d_rgb)), ptr(f(d_acc)),
+             ptr(f(d_exp)), ptr(f(g_dist)), ptr(f(g_inter)), r, s, c, bg_mode, bg_arr, k,
+             ptr_array(list(p_sigma)) if k else None, ptr_array(list(p_ebins)) if k else None,
+             ptr_array(list(p_dw)) if k else None, ints, ptr(dsigma), ptr(dcol), ptr_array(p_dsigma) if k else None,
+             stream(), tag=f"[S{s},C{c},+{k}]", units=r * s)
+        grads = [None] * len(ctx.needs_input_grad[11:])
+        for j, i in enumerate(live):
+            grads[i] = p_dsigma[j]
+        return (dsigma, dcol, None, None, None, None, None, None, None, None, None, *grads)
+
+
+_LOSS_SCALES = {}
+
+
+def _loss_scales(device, rays: int, samples: int) -> Tensor:
+    k = (str(device), rays, samples)
+    if k not in _LOSS_SCALES:
+        _LOSS_SCALES[k] = torch.tensor([1.0 / rays, 1.0 / (rays * samples)], dtype=torch.float32).to(device)
+    return _LOSS_SCALES[k]
+
+
+def ray_heads(sigma: Tensor, colour: Tensor, ebins: Tensor, sbins: Tensor, *, bg_mode: int, bg, eval_mode: bool,
+              want_losses: bool, prop_sigma=(), prop_ebins=(), prop_sbins=(), prop_weights=()):
+    """sigma [R,S], colour [R,S,C], bin edges [R,S+1] of the final level (+ per proposal level: density [R,S_i] --
+    the differentiable input --, bin edges and the weights tn_level_resample made of it)  ->
+    (rgb [R,C], accumulation [R,1], median depth [R,1], UNCLIPPED expected depth [R,1], (min,max) of the sample
+    midpoints [2], weights [R,S] (no gradient: the losses that read them are inside), mean distortion loss | None,
+    mean interlevel loss summed over the proposal levels | None)."""
+    return _RayHeadsFn.apply(sigma, colour, ebins, sbins, bg_mode, None if bg is None else tuple(bg), eval_mode,
+                             want_losses, tuple(prop_ebins), tuple(prop_sbins), tuple(prop_weights), *prop_sigma)

@@ -20,9 +20,10 @@ from . import fused_ops, ops
 from .field_components import SceneContraction
 from .fields import FieldHeadNames, HashMLPDensityField, ThermalNerfactoField
 from .losses import L1Loss, MSELoss, cross_channel_loss, distortion_loss, interlevel_loss, tv_pixel_loss
-from .rays import RayBundle, RaySamples
+from .rays import RayBundle, RayLayout, RaySamples, samples_from_layout
 from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, RGBTRenderer
-from .samplers import ProposalNetworkSampler, UniformSampler
+from .samplers import (PDFSampler, ProposalNetworkSampler, UniformLinDispPiecewiseSampler, UniformSampler,
+                       _PiecewiseSpacing)
 
 
 # ------------------------------------------------------------------------------------------ camera optimizer
@@ -256,6 +257,9 @@ class ThermalNerfactoModel(nn.Module):
         self.kwargs = dict(metadata=metadata or {}, **kwargs)
         self.device_indicator_param = nn.Parameter(torch.empty(0))  # models/base_model.py:85
         self.fuse_losses = True  # pixel / density loss terms as single kernels (torch expressions otherwise)
+        # one launch per sampling level (csrc/tn_level.cu): weights + resampling per proposal level, weights + all
+        # renderers + distortion + interlevel loss for the final level, one launch for the ray-level backward
+        self.fuse_levels = os.environ.get("TN_FUSE_LEVELS", "1") == "1"
         self.branch_streams = os.environ.get("TN_BRANCH_STREAMS", "1") == "1"
         # eval: off for eager chunk loops (GPU-bound per kernel, measured 4 % slower), on inside the captured
         # chunk graph of engine.GraphedRenderChunk
@@ -431,6 +435,85 @@ class ThermalNerfactoModel(nn.Module):
         outputs["_field_rgb"] = field_outputs[FieldHeadNames.RGB]
         return outputs
 
+    def _levels_fusable(self, ray_bundle: RayBundle, sampler: ProposalNetworkSampler, density_fns, renderer) -> bool:
+        """The per-level launches cover the configuration thermal-nerfacto ships: piecewise initial sampler,
+        PDFSampler without the original bins, proposal fields evaluated on the samplers' ray layout, a background
+        that is the same for every ray, at most two proposal levels."""
+        if not (self.fuse_levels and ray_bundle.origins.is_cuda and ray_bundle.origins.dim() == 2):
+            return False
+        if not (type(sampler.initial_sampler) is UniformLinDispPiecewiseSampler and type(sampler.pdf_sampler) is PDFSampler
+                and not sampler.pdf_sampler.include_original and 1 <= sampler.num_proposal_network_iterations <= 2):
+            return False
+        if self.config.predict_normals or ray_bundle.nears is None or ray_bundle.fars is None:
+            return False
+        for fn in density_fns[:sampler.num_proposal_network_iterations]:
+            owner = getattr(fn, "__self__", None)
+            if not (isinstance(owner, HashMLPDensityField) and getattr(fn, "__name__", "") == "density_fn"):
+                return False
+        bg = renderer.background_color
+        if isinstance(bg, Tensor) or (bg == "random" and self.training):
+            return False
+        return True
+
+    def _branch_fused(self, ray_bundle: RayBundle, sampler: ProposalNetworkSampler, density_fns, field_, renderer,
+                      jitters: Optional[List[Tensor]]) -> Tuple[Dict, RaySamples]:
+        """ProposalNetworkSampler.generate_ray_samples (ray_samplers.py:576-618) + NerfactoModel._get_outputs
+        (models/nerfacto.py:299-353) + the interlevel / distortion terms of get_loss_dict / get_metrics_dict
+        (models/nerfacto.py:355-383) for one branch, with ONE launch per sampling level after its field and one for
+        the ray-level backward (csrc/tn_level.cu).  Returns (outputs of _get_outputs, final RaySamples)."""
+        c = self.config
+        n = sampler.num_proposal_network_iterations
+        updated = sampler.will_update() if sampler._forced_updated is None else sampler._forced_updated
+        dev = ray_bundle.origins.device
+        num_rays = ray_bundle.origins.shape[0]
+        nears, fars = ray_bundle.nears.reshape(-1), ray_bundle.fars.reshape(-1)
+        if jitters is None:
+            jitters = sampler.draw_jitters(num_rays, dev)
+        jit = (lambda i: None) if jitters is None else (lambda i: jitters[i])
+        spacing = _PiecewiseSpacing(ray_bundle.nears, ray_bundle.fars)
+        counts = list(sampler.num_proposal_samples_per_ray[:n]) + [sampler.num_nerf_samples_per_ray]
+        sbins, ebins = ops.piecewise_bins(nears, fars, counts[0], jit(0))
+        anneal = sampler._anneal_tensor(dev)
+        weights_list, ray_samples_list, prop_sigma, prop_depths = [], [], [], []
+        for i in range(n):
+            lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars)
+            rs = samples_from_layout(ray_bundle, lay, spacing)
+            with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
+                sigma = density_fns[i].__self__.get_density(rs)[0].view(num_rays, counts[i])
+            w, med, sbins, ebins = fused_ops.level_resample(
+                sigma.detach(), lay.ebins, lay.sbins, nears, fars, counts[i + 1], jit(i + 1), anneal=anneal,
+                histogram_padding=sampler.pdf_sampler.histogram_padding)
+            weights_list.append(w[..., None])
+            ray_samples_list.append(rs)
+            prop_sigma.append(sigma)
+            prop_depths.append(med)
+        if sampler._forced_updated is None:
+            sampler.mark_sampled(updated)
+        lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars)
+        ray_samples = samples_from_layout(ray_bundle, lay, spacing)
+        field_outputs = field_.forward(ray_samples, compute_normals=False)
+        density, colour = field_outputs[FieldHeadNames.DENSITY], field_outputs[FieldHeadNames.RGB]
+        bg_mode, bg_const, _ = renderer._bg_args(renderer.background_color, colour.shape[-1])
+        grad_props = self.training and updated and torch.is_grad_enabled()
+        rgb, accumulation, depth, exp_raw, minmax, weights, dist, inter = fused_ops.ray_heads(
+            density.view(num_rays, counts[n]), colour, ebins, sbins, bg_mode=bg_mode, bg=bg_const,
+            eval_mode=not self.training, want_losses=self.training,
+            prop_sigma=prop_sigma if grad_props else (), prop_ebins=[r_._layout.ebins for r_ in ray_samples_list],
+            prop_sbins=[r_._layout.sbins for r_ in ray_samples_list], prop_weights=[w_[..., 0] for w_ in weights_list])
+        weights_list.append(weights[..., None])
+        ray_samples_list.append(ray_samples)
+        outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
+                   "expected_depth": torch.clamp(exp_raw, minmax[0], minmax[1]),  # batch-global clip, renderers.py:574
+                   "density": density}
+        if self.training:
+            outputs["weights_list"] = weights_list
+            outputs["ray_samples_list"] = ray_samples_list
+            outputs["_distortion"], outputs["_interlevel"] = dist, inter
+        for i in range(n):
+            outputs[f"prop_depth_{i}"] = prop_depths[i]
+        outputs["_field_rgb"] = colour
+        return outputs, ray_samples
+
     def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
                     jitters_thermal: Optional[List[Tensor]] = None) -> Dict:
         """ThermalNerfactoModel.get_outputs, models/thermal_nerfacto.py:403-489."""
@@ -451,15 +534,11 @@ class ThermalNerfactoModel(nn.Module):
             self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
             if self.training:
                 self.camera_optimizer.apply_to_raybundle(ray_bundle)
-            ray_samples, weights_list, ray_samples_list = self.proposal_sampler(
-                ray_bundle, density_fns=self.density_fns, jitters=jitters)
-            outputs = self._get_outputs(ray_bundle, self.field, renderer_rgb, ray_samples, weights_list,
-                                        ray_samples_list)
+            outputs, ray_samples = self._branch(ray_bundle, self.proposal_sampler, self.density_fns, self.field,
+                                                renderer_rgb, jitters)
             thermal_outputs = ray_samples_thermal = cross = None
             if separate:
-                ray_samples_thermal, wl_t, rsl_t = self._thermal_samples(ray_bundle_thermal, jitters_thermal)
-                thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
-                                                    ray_samples_thermal, wl_t, rsl_t)
+                thermal_outputs, ray_samples_thermal = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
                 if want_cross:
                     # cross-field densities for the density regulariser (:447-458).  The reference runs the full
                     # field forward here and throws the colour away; only the density is evaluated.
@@ -494,13 +573,21 @@ class ThermalNerfactoModel(nn.Module):
                 outputs["removal_thermal"] = self.renderer_thermal(rgb=field_rgb_thermal, weights=w_rm_th)
         return outputs
 
-    def _thermal_samples(self, ray_bundle_thermal: RayBundle, jitters_thermal):
-        """Pose corrections and proposal sampling of the thermal branch (:431-440)."""
+    def _branch(self, ray_bundle, sampler, density_fns, field_, renderer, jitters) -> Tuple[Dict, RaySamples]:
+        """Proposal sampling + _get_outputs of one branch: per-level launches when the configuration allows
+        (_levels_fusable), the component-by-component path of the reference otherwise.  Same outputs."""
+        if self._levels_fusable(ray_bundle, sampler, density_fns, renderer):
+            return self._branch_fused(ray_bundle, sampler, density_fns, field_, renderer, jitters)
+        ray_samples, weights_list, ray_samples_list = sampler(ray_bundle, density_fns=density_fns, jitters=jitters)
+        return self._get_outputs(ray_bundle, field_, renderer, ray_samples, weights_list, ray_samples_list), ray_samples
+
+    def _thermal_branch(self, ray_bundle_thermal: RayBundle, jitters_thermal) -> Tuple[Dict, RaySamples]:
+        """Pose corrections, proposal sampling and outputs of the thermal branch (:431-445)."""
         self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
         if self.training:
             self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
-        return self.proposal_sampler_thermal(ray_bundle_thermal, density_fns=self.density_fns_thermal,
-                                             jitters=jitters_thermal)
+        return self._branch(ray_bundle_thermal, self.proposal_sampler_thermal, self.density_fns_thermal,
+                            self.field_thermal, self.renderer_thermal, jitters_thermal)
 
     def _branches_on_streams(self, ray_bundle, ray_bundle_thermal, jitters, jitters_thermal, want_cross):
         """Training, density_mode="separate", CUDA: the RGB and the thermal branch are independent until the
@@ -522,16 +609,12 @@ class ThermalNerfactoModel(nn.Module):
         side = self._side_stream
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            ray_samples_thermal, wl_t, rsl_t = self._thermal_samples(ray_bundle_thermal, jitters_thermal)
-            thermal_outputs = self._get_outputs(ray_bundle_thermal, self.field_thermal, self.renderer_thermal,
-                                                ray_samples_thermal, wl_t, rsl_t)
+            thermal_outputs, ray_samples_thermal = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
         self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
         if self.training:
             self.camera_optimizer.apply_to_raybundle(ray_bundle)
-        ray_samples, weights_list, ray_samples_list = self.proposal_sampler(ray_bundle, density_fns=self.density_fns,
-                                                                            jitters=jitters)
-        outputs = self._get_outputs(ray_bundle, self.field, self.renderer_rgb, ray_samples, weights_list,
-                                    ray_samples_list)
+        outputs, ray_samples = self._branch(ray_bundle, self.proposal_sampler, self.density_fns, self.field,
+                                            self.renderer_rgb, jitters)
         main.wait_stream(side)
         cross = None
         if want_cross:
@@ -574,8 +657,9 @@ class ThermalNerfactoModel(nn.Module):
         if self.training:
             metrics_dict["distortion"] = 0
             for s in self.output_suffixes:
-                metrics_dict["distortion"] += distortion_loss(outputs[f"weights_list{s}"],
-                                                              outputs[f"ray_samples_list{s}"])
+                fused = outputs.get(f"_distortion{s}")  # made by the final level's launch (_branch_fused)
+                metrics_dict["distortion"] += fused if fused is not None else distortion_loss(
+                    outputs[f"weights_list{s}"], outputs[f"ray_samples_list{s}"])
         self.camera_optimizer.get_metrics_dict(metrics_dict)
         self.shared_camera_optimizer.get_metrics_dict(metrics_dict)
         if self.config.density_mode == "separate":
@@ -634,9 +718,9 @@ class ThermalNerfactoModel(nn.Module):
         if self.training:
             assert metrics_dict is not None and "distortion" in metrics_dict
             for s in self.output_suffixes:
-                entries.append(("interlevel_loss", interlevel_loss(outputs[f"weights_list{s}"],
-                                                                   outputs[f"ray_samples_list{s}"]),
-                                c.interlevel_loss_mult))
+                fused = outputs.get(f"_interlevel{s}")  # made by the final level's launch (_branch_fused)
+                entries.append(("interlevel_loss", fused if fused is not None else interlevel_loss(
+                    outputs[f"weights_list{s}"], outputs[f"ray_samples_list{s}"]), c.interlevel_loss_mult))
             for s in self.output_suffixes:
                 # reference quirk kept: the SUMMED distortion metric is added once per suffix (:368)
                 entries.append(("distortion_loss", metrics_dict["distortion"], c.distortion_loss_mult))

@@ -95,6 +95,17 @@ class RaySamples(_Sliceable):
     times: Optional[Tensor] = None
     _layout: Optional[RayLayout] = field(default=None, repr=False, compare=False)
 
+    def __getattribute__(self, name):
+        # `deltas` of samples made by this package's samplers are formed on first use: the kernels take the bin
+        # edges of the per-ray layout, so the [R,S,1] difference is only materialised for callers that read it
+        v = object.__getattribute__(self, name)
+        if v is None and name == "deltas":
+            lay = object.__getattribute__(self, "_layout")
+            if lay is not None:
+                v = (lay.ebins[:, 1:] - lay.ebins[:, :-1])[..., None]
+                object.__setattr__(self, "deltas", v)
+        return v
+
     @property
     def shape(self):
         return self.frustums.shape
@@ -159,8 +170,13 @@ class RayBundle(_Sliceable):
 def samples_from_layout(bundle: RayBundle, layout: RayLayout, spacing_to_euclidean_fn: Callable) -> RaySamples:
     """Public RaySamples whose tensors are views of the per-ray layout (no [R,S,3] materialisation)."""
     eb, sb = layout.ebins, layout.sbins
-    rs = bundle.get_ray_samples(bin_starts=eb[:, :-1, None], bin_ends=eb[:, 1:, None],
-                                spacing_starts=sb[:, :-1, None], spacing_ends=sb[:, 1:, None],
-                                spacing_to_euclidean_fn=spacing_to_euclidean_fn)
-    rs._layout = layout
-    return rs
+    s = eb.shape[1] - 1
+    expand = lambda t: None if t is None else t[..., None, :].expand(*t.shape[:-1], s, t.shape[-1])  # noqa: E731
+    frustums = Frustums(origins=expand(bundle.origins), directions=expand(bundle.directions), starts=eb[:, :-1, None],
+                        ends=eb[:, 1:, None], pixel_area=expand(bundle.pixel_area))
+    # as RayBundle.get_ray_samples (cameras/rays.py:251-295), with `deltas` left to RaySamples.__getattribute__
+    return RaySamples(frustums=frustums, camera_indices=expand(bundle.camera_indices), deltas=None,
+                      spacing_starts=sb[:, :-1, None], spacing_ends=sb[:, 1:, None],
+                      spacing_to_euclidean_fn=spacing_to_euclidean_fn,
+                      metadata={k: expand(v) for k, v in bundle.metadata.items()} if bundle.metadata else None,
+                      times=expand(bundle.times), _layout=layout)
