@@ -11,11 +11,25 @@ What one replay contains (`GraphedTrainStep._eager` is the captured program):
 
     [source: pixel sampling, collation, ray generation]            optional, `source=DeviceBatchSource(...)`
     gradient-buffer clear                                          on its own stream, beside the forward
-    forward: RGB branch | thermal branch on a second stream        (model._branches_on_streams), cross terms, losses
+    forward: RGB branch | thermal branch on a second stream        (model.sample_phase / render_phase), cross terms, losses
     backward: autograd replays every node on its forward stream
       '- when both main fields' gradients are final (hook): all-reduce of their 134 MB segment [N>1] and Adam on
          that segment [optimizer=], on an auxiliary stream beside the proposal networks' backward
     remaining all-reduce [N>1], Adam on the remaining segment [optimizer=]
+
+Data parallel on several GPUs ("pipeline", the default with NCCL): the step is captured as THREE graphs cut where the
+reference's dependencies allow an exchange to hide --
+
+    A  pose corrections + proposal sampling of both branches        reads only proposal-network / camera parameters
+    B  main fields, renderers, cross terms, losses, backward down to A's outputs     -> main fields' gradients final
+       '- all-reduce of the main fields' 134 MB on the communication stream, started here ...
+    C  backward of A (proposal networks, camera optimizers), all-reduce of the remaining 21 MB
+    A' of the NEXT step                                              ... and hidden behind C and A'
+    (wait for the exchange) B' ...
+
+-- so the 134 MB exchange overlaps ~0.6 ms of work that does not depend on it, with exactly DDP's semantics: every
+gradient is averaged before anything reads it, and a parameter is never read between its gradient's production and
+its update (`optimizer=` steps the main fields on the communication stream right after their all-reduce).
 
 Mirrors what `Trainer.train_iteration` + `VanillaPipeline.get_train_loss_dict` drive in the reference
 (engine/trainer.py:456-500, pipelines/base_pipeline.py:291-304; DDP of base_pipeline.py:280-283; the optimiser and
@@ -62,7 +76,8 @@ class GraphedTrainStep:
 
     def __init__(self, model: ThermalNerfactoModel, example_batch: Dict[str, Tensor], use_graph: bool = True,
                  warmup: int = 3, group=None, optimizer: Optional[Dict[str, AdamGroupConfig]] = None,
-                 overlap_comm: Optional[bool] = None, source: Optional[DeviceBatchSource] = None):
+                 overlap_comm: Optional[bool] = None, source: Optional[DeviceBatchSource] = None,
+                 pipeline: Optional[bool] = None):
         self.model = model
         self.source = source  # batches come from the device-side sampler / ray generator instead of step(batch)
         self.device = model.device
@@ -82,13 +97,20 @@ class GraphedTrainStep:
         self.grads = parallel.FlatGradBuffer.from_param_groups(groups, order=order, device=self.device)
         self.grads.attach_sinks(model)
         self._early_end = max((self.grads.group_ranges[n][1] for n in early), default=0)
-        if overlap_comm is None:
-            # measured (profiles/r01_bench_train_n*.json): the overlapped exchange wins on 2 and 4 GPUs (2.90 vs
-            # 3.02 ms/step on 2); on 8 GPUs, with replays queued back to back, the early collective's spin-waits on
-            # late peers contend with the proposal backward (3.83 ms vs 3.20 with the trailing all-reduce)
-            default = "overlap" if world <= 4 else "after"
-            overlap_comm = os.environ.get("TN_COMM", default) == "overlap"
-        self._comm_in_graph = world > 1 and overlap_comm and torch.distributed.get_backend(group) == "nccl"
+        nccl = world > 1 and torch.distributed.get_backend(group) == "nccl"
+        mode = os.environ.get("TN_COMM", "pipeline" if overlap_comm is None else ("overlap" if overlap_comm else "after"))
+        if mode not in ("pipeline", "overlap", "after"):
+            raise ValueError(f"TN_COMM={mode!r}: expected pipeline | overlap | after")
+        # "pipeline": three graphs per step, the main fields' all-reduce hidden behind the proposal backward and the
+        # NEXT step's proposal forward (module docstring).  "overlap" (round 1): one graph, the early all-reduce
+        # captured inside it -- wins on 2 and 4 GPUs, loses on 8, where the captured collective's spin-waits on late
+        # peers contend with the proposal backward (3.83 ms vs 3.20 with the trailing all-reduce, "after").
+        # (`pipeline=True` runs the three-phase schedule on one GPU as well: the tests compare it with the single graph)
+        want_pipeline = (nccl and mode == "pipeline") if pipeline is None else pipeline
+        self._pipeline = (want_pipeline and use_graph and self._early_end > 0 and getattr(model, "fuse_levels", False)
+                          and source is None)
+        self._comm_in_graph = nccl and mode == "overlap"
+        self._comm_event: Optional[torch.cuda.Event] = None
         self._early_done = False
         self._adam_now = False
         self._zero_in_adam = False
@@ -101,8 +123,10 @@ class GraphedTrainStep:
         self._adam_in_graph = self.optimizer is not None and (world == 1 or self._comm_in_graph)
         # the fields' segment is exchanged AND stepped early (HBM/NVLink-bound work beside the issue-bound proposal
         # backward): both hang off the same backward hook and run on the auxiliary stream
-        self._early_active = self._early_end > 0 and (self._comm_in_graph or self._adam_in_graph)
-        if self._early_active:
+        if self._pipeline:
+            self._adam_in_graph = False
+        self._early_active = self._early_end > 0 and (self._comm_in_graph or self._adam_in_graph) and not self._pipeline
+        if self._early_active or self._pipeline:
             self._comm_stream = torch.cuda.Stream(device=self.device)
         for f in self._fields:  # (also detaches the hooks of an earlier runner of the same model)
             f.grads_ready_callback = self._field_ready if self._early_active else None
@@ -139,7 +163,10 @@ class GraphedTrainStep:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(max(warmup, 2) - 1):  # allocator / cudaFuncSetAttribute / host-constant caches warm
-                    self._eager(apply_optimizer=False, key=key)  # warm-up must not move the parameters
+                    if self._pipeline:
+                        self._phases(key)
+                    else:
+                        self._eager(apply_optimizer=False, key=key)  # warm-up must not move the parameters
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             self._capture(key)
@@ -174,18 +201,85 @@ class GraphedTrainStep:
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
-            self._eager(apply_optimizer=False, key=key)
+            if self._pipeline:
+                self._phases(key)
+            else:
+                self._eager(apply_optimizer=False, key=key)
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.grads.zero_()
-        graph = torch.cuda.CUDAGraph()
-        pool = next(iter(self._variants.values()))[0].pool() if self._variants else None  # variants replay serially
-        with torch.cuda.graph(graph, pool=pool):
-            self._eager(apply_optimizer=True, captured=True, key=key)
+        first = next(iter(self._variants.values()))[0] if self._variants else None
+        pool = (first[0] if isinstance(first, tuple) else first).pool() if first is not None else None  # serial replays
+        if self._pipeline:
+            graphs = []
+            for phase in (self._phase_a, self._phase_b, self._phase_c):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    phase(key)
+                pool = g.pool()
+                graphs.append(g)
+            graph = tuple(graphs)
+        else:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=pool):
+                self._eager(apply_optimizer=True, captured=True, key=key)
         torch.cuda.synchronize(self.device)
         self.graph = graph
         self._variants[key] = (graph, self.total, self.losses)
         return self._variants[key]
+
+    # ---- "pipeline": the step in three phases (module docstring)
+    def _phase_a(self, key: Tuple[bool, ...]) -> None:
+        """Pose corrections + proposal sampling of both branches; its differentiable outputs become leaves."""
+        s = self.static
+        bundle = self.model.collider(RayBundle(origins=s["origins"], directions=s["directions"],
+                                               pixel_area=s["pixel_area"], camera_indices=s["camera_indices"]))
+        for smp, upd in zip(self._samplers, key):
+            smp._forced_updated = upd
+        try:
+            self._state = self.model.sample_phase(bundle)
+        finally:
+            for smp in self._samplers:
+                smp._forced_updated = None
+        self._pairs = self._state.cut()
+        if self._state.streams:  # a phase ends with every stream joined (graph capture requires it)
+            torch.cuda.current_stream(self.device).wait_stream(self.model._side_stream)
+
+    def _phase_b(self, key: Tuple[bool, ...]) -> None:
+        """Gradient clear, main fields + renderers + cross terms + losses, backward down to phase A's outputs."""
+        s = self.static
+        cur = torch.cuda.current_stream(self.device)
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream(device=self.device)
+        self._zero_stream.wait_stream(cur)
+        with torch.cuda.stream(self._zero_stream):
+            self.grads.zero_()
+        batch = {"image": s["image"], "is_thermal": s["is_thermal"]}
+        outputs = self.model.render_phase(self._state)
+        metrics = self.model.get_metrics_dict(outputs, batch)
+        self.losses = self.model.get_loss_dict(outputs, batch, metrics)
+        total = getattr(self.losses, "total", None)
+        self.total = total if total is not None else sum(self.losses.values())
+        cur.wait_stream(self._zero_stream)
+        self.total.backward()
+
+    def _phase_c(self, key: Tuple[bool, ...]) -> None:
+        """Backward of phase A from the gradients phase B left on its leaves: proposal networks, camera optimizers."""
+        live = [(t, leaf.grad) for t, leaf in self._pairs if leaf.grad is not None]
+        if live:
+            torch.autograd.backward([t for t, _ in live], [g for _, g in live])
+
+    def _phases(self, key: Tuple[bool, ...]) -> None:
+        self._phase_a(key)
+        self._phase_b(key)
+        self._phase_c(key)
+
+    def finish_exchange(self) -> None:
+        """Make the current stream wait for the gradient exchange of the last step ("pipeline" leaves the main
+        fields' all-reduce running on the communication stream when step() returns: call this before reading
+        `grads.flat` / `param.grad` on the current stream; the next step() does it at the right place itself)."""
+        if self._comm_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._comm_event)
 
     def _field_ready(self) -> None:
         """Backward hook of a main field (fires on the stream that ran its encode backward).  Once every field has
@@ -260,7 +354,9 @@ class GraphedTrainStep:
         if batch is not None:
             self._load(batch)
         key = self._variant_key()
-        if self.use_graph:
+        if self._pipeline:
+            self._step_pipeline(key)
+        elif self.use_graph:
             variant = self._variants.get(key)
             if variant is None:
                 variant = self._capture(key)
@@ -270,11 +366,41 @@ class GraphedTrainStep:
             self._eager(key=key)
         for smp, upd in zip(self._samplers, key):  # what generate_ray_samples does at its end
             smp.mark_sampled(upd)
+        if self._pipeline:
+            return self.total
         if not self._comm_in_graph:
             self.grads.all_reduce_mean(self.group)
         if self.optimizer is not None and not self._adam_in_graph:
             self.optimizer.step(inactive=[g for g, upd in zip(self._sampler_groups, key) if not upd])
         return self.total
+
+    def _step_pipeline(self, key: Tuple[bool, ...]) -> None:
+        variant = self._variants.get(key)
+        if variant is None:
+            self.finish_exchange()  # a capture synchronises the device anyway
+            variant = self._capture(key)
+        (g_a, g_b, g_c), self.total, self.losses = variant
+        self.graph = variant[0]
+        main, comm = torch.cuda.current_stream(self.device), self._comm_stream
+        inactive = [g for g, upd in zip(self._sampler_groups, key) if not upd]
+        if self.optimizer is not None:
+            self.optimizer.tick(inactive=inactive)
+        g_a.replay()
+        self.finish_exchange()  # B clears and rewrites the gradient buffer (and reads the main fields' parameters)
+        g_b.replay()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        comm.wait_event(ready)
+        with torch.cuda.stream(comm):  # the main fields' segment: hidden behind C and the next step's A
+            self.grads.all_reduce_mean(self.group, begin=0, end=self._early_end)
+            if self.optimizer is not None:
+                self.optimizer.step_range(0, self._early_end, zero_grads=False)
+            self._comm_event = torch.cuda.Event()
+            self._comm_event.record(comm)
+        g_c.replay()
+        self.grads.all_reduce_mean(self.group, begin=self._early_end)
+        if self.optimizer is not None:
+            self.optimizer.step_range(self._early_end, self.grads.flat.numel(), zero_grads=False)
 
     def train_iteration(self, step: int, batch: Optional[Dict[str, Tensor]] = None) -> Tensor:
         """Trainer.train_iteration with its callbacks (engine/trainer.py:262-275, 456-500): the

@@ -218,6 +218,58 @@ class ThermalNerfactoModelConfig:
         return ThermalNerfactoModel(self, **kwargs)
 
 
+class _BranchSamples:
+    """One branch between its proposal phase and its render phase (ThermalNerfactoModel.sample_phase)."""
+
+    def __init__(self, ray_bundle: RayBundle, sampler) -> None:
+        self.ray_bundle = ray_bundle  # after the pose corrections: origins / directions carry the gradient to the poses
+        self.sampler = sampler
+        self.generic = None           # (ray_samples, weights_list, ray_samples_list) of the component-by-component path
+        self.spacing = None
+        self.counts: List[int] = []
+        self.ebins = self.sbins = self.nears = self.fars = None  # final level
+        self.weights_list: List[Tensor] = []
+        self.ray_samples_list: List[RaySamples] = []
+        self.prop_sigma: List[Tensor] = []   # proposal densities [R,S_i]: the interlevel loss reaches the networks here
+        self.prop_depths: List[Tensor] = []
+        self.grad_props = False
+
+    def cut(self) -> List[Tuple[Tensor, Tensor]]:
+        """Replace every differentiable tensor the render phase reads by a detached leaf and return the
+        (original, leaf) pairs: a backward of the render phase then stops at the leaves, and
+        `torch.autograd.backward(originals, [leaf.grad ...])` finishes the job later (engine.GraphedTrainStep runs
+        the gradient exchange of the main fields in between)."""
+        if self.generic is not None:
+            raise NotImplementedError("the two-phase backward needs the per-level launches (fuse_levels)")
+        pairs: List[Tuple[Tensor, Tensor]] = []
+
+        def leaf(t: Tensor) -> Tensor:
+            if not t.requires_grad:
+                return t
+            d = t.detach().requires_grad_(True)
+            pairs.append((t, d))
+            return d
+
+        rb = self.ray_bundle
+        self.ray_bundle = RayBundle(origins=leaf(rb.origins), directions=leaf(rb.directions), pixel_area=rb.pixel_area,
+                                    camera_indices=rb.camera_indices, nears=rb.nears, fars=rb.fars,
+                                    metadata=rb.metadata, times=rb.times)
+        self.prop_sigma = [leaf(t) for t in self.prop_sigma]
+        return pairs
+
+
+class _ForwardState:
+    """sample_phase -> render_phase hand-over."""
+
+    def __init__(self) -> None:
+        self.rgb: Optional[_BranchSamples] = None
+        self.thermal: Optional[_BranchSamples] = None
+        self.streams = False
+
+    def cut(self) -> List[Tuple[Tensor, Tensor]]:
+        return [p for b in (self.rgb, self.thermal) if b is not None for p in b.cut()]
+
+
 class LossDict(dict):
     """The loss dictionary of get_loss_dict plus `.total`, the sum of its values (engine/trainer.py:479)."""
 
@@ -455,13 +507,15 @@ class ThermalNerfactoModel(nn.Module):
             return False
         return True
 
-    def _branch_fused(self, ray_bundle: RayBundle, sampler: ProposalNetworkSampler, density_fns, field_, renderer,
-                      jitters: Optional[List[Tensor]]) -> Tuple[Dict, RaySamples]:
-        """ProposalNetworkSampler.generate_ray_samples (ray_samplers.py:576-618) + NerfactoModel._get_outputs
-        (models/nerfacto.py:299-353) + the interlevel / distortion terms of get_loss_dict / get_metrics_dict
-        (models/nerfacto.py:355-383) for one branch, with ONE launch per sampling level after its field and one for
-        the ray-level backward (csrc/tn_level.cu).  Returns (outputs of _get_outputs, final RaySamples)."""
-        c = self.config
+    def _branch_sample(self, ray_bundle: RayBundle, sampler: ProposalNetworkSampler, density_fns, renderer,
+                       jitters: Optional[List[Tensor]]) -> "_BranchSamples":
+        """Proposal phase of one branch: ProposalNetworkSampler.generate_ray_samples (ray_samplers.py:576-618).  With
+        per-level launches (_levels_fusable) each level is its proposal field + ONE launch (weights, median depth,
+        resampling: csrc/tn_level.cu); otherwise the sampler module runs component by component."""
+        bs = _BranchSamples(ray_bundle, sampler)
+        if not self._levels_fusable(ray_bundle, sampler, density_fns, renderer):
+            bs.generic = sampler(ray_bundle, density_fns=density_fns, jitters=jitters)
+            return bs
         n = sampler.num_proposal_network_iterations
         updated = sampler.will_update() if sampler._forced_updated is None else sampler._forced_updated
         dev = ray_bundle.origins.device
@@ -470,38 +524,53 @@ class ThermalNerfactoModel(nn.Module):
         if jitters is None:
             jitters = sampler.draw_jitters(num_rays, dev)
         jit = (lambda i: None) if jitters is None else (lambda i: jitters[i])
-        spacing = _PiecewiseSpacing(ray_bundle.nears, ray_bundle.fars)
-        counts = list(sampler.num_proposal_samples_per_ray[:n]) + [sampler.num_nerf_samples_per_ray]
-        sbins, ebins = ops.piecewise_bins(nears, fars, counts[0], jit(0))
+        bs.spacing = _PiecewiseSpacing(ray_bundle.nears, ray_bundle.fars)
+        bs.counts = list(sampler.num_proposal_samples_per_ray[:n]) + [sampler.num_nerf_samples_per_ray]
+        sbins, ebins = ops.piecewise_bins(nears, fars, bs.counts[0], jit(0))
         anneal = sampler._anneal_tensor(dev)
-        weights_list, ray_samples_list, prop_sigma, prop_depths = [], [], [], []
         for i in range(n):
             lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars)
-            rs = samples_from_layout(ray_bundle, lay, spacing)
+            rs = samples_from_layout(ray_bundle, lay, bs.spacing)
             with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
-                sigma = density_fns[i].__self__.get_density(rs)[0].view(num_rays, counts[i])
+                sigma = density_fns[i].__self__.get_density(rs)[0].view(num_rays, bs.counts[i])
             w, med, sbins, ebins = fused_ops.level_resample(
-                sigma.detach(), lay.ebins, lay.sbins, nears, fars, counts[i + 1], jit(i + 1), anneal=anneal,
+                sigma.detach(), lay.ebins, lay.sbins, nears, fars, bs.counts[i + 1], jit(i + 1), anneal=anneal,
                 histogram_padding=sampler.pdf_sampler.histogram_padding)
-            weights_list.append(w[..., None])
-            ray_samples_list.append(rs)
-            prop_sigma.append(sigma)
-            prop_depths.append(med)
+            bs.weights_list.append(w[..., None])
+            bs.ray_samples_list.append(rs)
+            bs.prop_sigma.append(sigma)
+            bs.prop_depths.append(med)
         if sampler._forced_updated is None:
             sampler.mark_sampled(updated)
-        lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars)
-        ray_samples = samples_from_layout(ray_bundle, lay, spacing)
+        bs.ebins, bs.sbins, bs.nears, bs.fars = ebins, sbins, nears, fars
+        bs.grad_props = self.training and updated and torch.is_grad_enabled()
+        return bs
+
+    def _branch_render(self, bs: "_BranchSamples", field_, renderer) -> Tuple[Dict, RaySamples]:
+        """Render phase of one branch: NerfactoModel._get_outputs (models/nerfacto.py:299-353) + the interlevel /
+        distortion terms of get_loss_dict / get_metrics_dict (models/nerfacto.py:355-383).  With per-level launches:
+        the field, then ONE launch for weights + all renderers + both losses (and one for the whole ray-level
+        backward).  Returns (outputs of _get_outputs, final RaySamples)."""
+        ray_bundle = bs.ray_bundle
+        if bs.generic is not None:
+            ray_samples, weights_list, ray_samples_list = bs.generic
+            return self._get_outputs(ray_bundle, field_, renderer, ray_samples, weights_list, ray_samples_list), ray_samples
+        n = len(bs.prop_sigma)
+        num_rays = ray_bundle.origins.shape[0]
+        lay = RayLayout(ray_bundle.origins, ray_bundle.directions, bs.ebins, bs.sbins, bs.nears, bs.fars)
+        ray_samples = samples_from_layout(ray_bundle, lay, bs.spacing)
         field_outputs = field_.forward(ray_samples, compute_normals=False)
         density, colour = field_outputs[FieldHeadNames.DENSITY], field_outputs[FieldHeadNames.RGB]
         bg_mode, bg_const, _ = renderer._bg_args(renderer.background_color, colour.shape[-1])
-        grad_props = self.training and updated and torch.is_grad_enabled()
         rgb, accumulation, depth, exp_raw, minmax, weights, dist, inter = fused_ops.ray_heads(
-            density.view(num_rays, counts[n]), colour, ebins, sbins, bg_mode=bg_mode, bg=bg_const,
+            density.view(num_rays, bs.counts[n]), colour, bs.ebins, bs.sbins, bg_mode=bg_mode, bg=bg_const,
             eval_mode=not self.training, want_losses=self.training,
-            prop_sigma=prop_sigma if grad_props else (), prop_ebins=[r_._layout.ebins for r_ in ray_samples_list],
-            prop_sbins=[r_._layout.sbins for r_ in ray_samples_list], prop_weights=[w_[..., 0] for w_ in weights_list])
-        weights_list.append(weights[..., None])
-        ray_samples_list.append(ray_samples)
+            prop_sigma=bs.prop_sigma if bs.grad_props else (),
+            prop_ebins=[r_._layout.ebins for r_ in bs.ray_samples_list],
+            prop_sbins=[r_._layout.sbins for r_ in bs.ray_samples_list],
+            prop_weights=[w_[..., 0] for w_ in bs.weights_list])
+        weights_list = bs.weights_list + [weights[..., None]]
+        ray_samples_list = bs.ray_samples_list + [ray_samples]
         outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
                    "expected_depth": torch.clamp(exp_raw, minmax[0], minmax[1]),  # batch-global clip, renderers.py:574
                    "density": density}
@@ -510,13 +579,17 @@ class ThermalNerfactoModel(nn.Module):
             outputs["ray_samples_list"] = ray_samples_list
             outputs["_distortion"], outputs["_interlevel"] = dist, inter
         for i in range(n):
-            outputs[f"prop_depth_{i}"] = prop_depths[i]
+            outputs[f"prop_depth_{i}"] = bs.prop_depths[i]
         outputs["_field_rgb"] = colour
         return outputs, ray_samples
 
-    def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
-                    jitters_thermal: Optional[List[Tensor]] = None) -> Dict:
-        """ThermalNerfactoModel.get_outputs, models/thermal_nerfacto.py:403-489."""
+    # The forward in two phases.  get_outputs runs them back to back; a data-parallel runner may put work between
+    # them: nothing in the sample phase reads the main fields' parameters (engine.GraphedTrainStep, "pipeline").
+    def sample_phase(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                     jitters_thermal: Optional[List[Tensor]] = None) -> "_ForwardState":
+        """Pose corrections and proposal sampling of every branch (models/thermal_nerfacto.py:403-440): camera
+        optimizers, proposal networks, resampling.  The RGB and the thermal branch are independent: with
+        `branch_streams` the thermal one is issued on a second stream (see _render_phase)."""
         c = self.config
         # the reference deep-copies the bundle so that each path applies its own pose corrections (:407)
         ray_bundle_thermal = RayBundle(origins=ray_bundle.origins, directions=ray_bundle.directions,
@@ -524,21 +597,88 @@ class ThermalNerfactoModel(nn.Module):
                                        nears=ray_bundle.nears, fars=ray_bundle.fars, metadata=ray_bundle.metadata,
                                        times=ray_bundle.times)
         separate = c.density_mode == "separate"
+        st = _ForwardState()
+        st.streams = bool(separate and ray_bundle.origins.is_cuda and (
+            (self.branch_streams and self.training) or (self.eval_branch_streams and not self.training)))
+        renderer_rgb = self.renderer_rgbt if c.density_mode == "shared" else self.renderer_rgb
+        dev = ray_bundle.origins.device
+        if st.streams:
+            # the jitter draws are made first, in the reference's order, so the random stream is unchanged
+            num_rays = ray_bundle.origins.shape[0]
+            if jitters is None:
+                jitters = self.proposal_sampler.draw_jitters(num_rays, dev)
+            if jitters_thermal is None:
+                jitters_thermal = self.proposal_sampler_thermal.draw_jitters(num_rays, dev)
+            main = torch.cuda.current_stream(dev)
+            if self._side_stream is None or self._side_stream.device != dev:
+                self._side_stream = torch.cuda.Stream(device=dev)
+            side = self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                st.thermal = self._thermal_sample(ray_bundle_thermal, jitters_thermal)
+        self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
+        if self.training:
+            self.camera_optimizer.apply_to_raybundle(ray_bundle)
+        st.rgb = self._branch_sample(ray_bundle, self.proposal_sampler, self.density_fns, renderer_rgb, jitters)
+        if separate and not st.streams:
+            st.thermal = self._thermal_sample(ray_bundle_thermal, jitters_thermal)
+        return st
+
+    def _thermal_sample(self, ray_bundle_thermal: RayBundle, jitters_thermal) -> "_BranchSamples":
+        """Pose corrections and proposal sampling of the thermal branch (:431-440)."""
+        self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
+        if self.training:
+            self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
+        return self._branch_sample(ray_bundle_thermal, self.proposal_sampler_thermal, self.density_fns_thermal,
+                                   self.renderer_thermal, jitters_thermal)
+
+    def get_outputs(self, ray_bundle: RayBundle, jitters: Optional[List[Tensor]] = None,
+                    jitters_thermal: Optional[List[Tensor]] = None) -> Dict:
+        """ThermalNerfactoModel.get_outputs, models/thermal_nerfacto.py:403-489."""
+        return self.render_phase(self.sample_phase(ray_bundle, jitters, jitters_thermal))
+
+    def render_phase(self, st: "_ForwardState") -> Dict:
+        """Main fields, renderers, cross-field terms and output assembly (models/thermal_nerfacto.py:441-489) for the
+        samples of `sample_phase`.
+
+        Training, density_mode="separate", CUDA: the RGB and the thermal branch are independent until the cross-field
+        terms, which are independent of each other, and most of their kernels are latency- or issue-bound.  The
+        thermal branch and one cross term are therefore issued on a second stream: in the captured train step they
+        (and, through autograd's stream tracking, their backwards) become parallel arms of the graph.  Measured:
+        2.93 -> 2.83 ms/step with the thermal branch on the second stream, -> 2.67 with the cross terms overlapped as
+        well; a four-stream version (cross terms started right after the samplers) was slower (2.73)."""
+        c = self.config
+        separate = c.density_mode == "separate"
         want_cross = separate and (c.density_loss_mult > 0 or not self.training)
         renderer_rgb = self.renderer_rgbt if c.density_mode == "shared" else self.renderer_rgb
-        if separate and ray_bundle.origins.is_cuda and (
-                (self.branch_streams and self.training) or (self.eval_branch_streams and not self.training)):
-            outputs, thermal_outputs, ray_samples, ray_samples_thermal, cross = self._branches_on_streams(
-                ray_bundle, ray_bundle_thermal, jitters, jitters_thermal, want_cross)
+        thermal_outputs = ray_samples_thermal = cross = None
+        if st.streams:
+            dev = st.rgb.ray_bundle.origins.device
+            main, side = torch.cuda.current_stream(dev), self._side_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                thermal_outputs, ray_samples_thermal = self._branch_render(st.thermal, self.field_thermal,
+                                                                           self.renderer_thermal)
+            outputs, ray_samples = self._branch_render(st.rgb, self.field, renderer_rgb)
+            main.wait_stream(side)
+            if want_cross:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    d2t = self.field_thermal.get_density_only(ray_samples)
+                d2 = self.field.get_density_only(ray_samples_thermal)
+                main.wait_stream(side)
+                cross = (d2, d2t)
+            crossing = list(thermal_outputs.values()) + [ray_samples_thermal._layout.ebins,
+                                                         ray_samples_thermal._layout.sbins]
+            crossing += [cross[1]] if cross is not None else []
+            for v in crossing:  # made on the side stream, consumed (and eventually freed) on the main one
+                if torch.is_tensor(v):
+                    v.record_stream(main)
         else:
-            self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
-            if self.training:
-                self.camera_optimizer.apply_to_raybundle(ray_bundle)
-            outputs, ray_samples = self._branch(ray_bundle, self.proposal_sampler, self.density_fns, self.field,
-                                                renderer_rgb, jitters)
-            thermal_outputs = ray_samples_thermal = cross = None
+            outputs, ray_samples = self._branch_render(st.rgb, self.field, renderer_rgb)
             if separate:
-                thermal_outputs, ray_samples_thermal = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
+                thermal_outputs, ray_samples_thermal = self._branch_render(st.thermal, self.field_thermal,
+                                                                           self.renderer_thermal)
                 if want_cross:
                     # cross-field densities for the density regulariser (:447-458).  The reference runs the full
                     # field forward here and throws the colour away; only the density is evaluated.
@@ -572,64 +712,6 @@ class ThermalNerfactoModel(nn.Module):
                 w_rm_th = ray_samples.get_weights(outputs["density_thermal"] * mask_th)
                 outputs["removal_thermal"] = self.renderer_thermal(rgb=field_rgb_thermal, weights=w_rm_th)
         return outputs
-
-    def _branch(self, ray_bundle, sampler, density_fns, field_, renderer, jitters) -> Tuple[Dict, RaySamples]:
-        """Proposal sampling + _get_outputs of one branch: per-level launches when the configuration allows
-        (_levels_fusable), the component-by-component path of the reference otherwise.  Same outputs."""
-        if self._levels_fusable(ray_bundle, sampler, density_fns, renderer):
-            return self._branch_fused(ray_bundle, sampler, density_fns, field_, renderer, jitters)
-        ray_samples, weights_list, ray_samples_list = sampler(ray_bundle, density_fns=density_fns, jitters=jitters)
-        return self._get_outputs(ray_bundle, field_, renderer, ray_samples, weights_list, ray_samples_list), ray_samples
-
-    def _thermal_branch(self, ray_bundle_thermal: RayBundle, jitters_thermal) -> Tuple[Dict, RaySamples]:
-        """Pose corrections, proposal sampling and outputs of the thermal branch (:431-445)."""
-        self.shared_camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
-        if self.training:
-            self.camera_optimizer_thermal.apply_to_raybundle(ray_bundle_thermal)
-        return self._branch(ray_bundle_thermal, self.proposal_sampler_thermal, self.density_fns_thermal,
-                            self.field_thermal, self.renderer_thermal, jitters_thermal)
-
-    def _branches_on_streams(self, ray_bundle, ray_bundle_thermal, jitters, jitters_thermal, want_cross):
-        """Training, density_mode="separate", CUDA: the RGB and the thermal branch are independent until the
-        cross-field terms, which are independent of each other, and most of their kernels are latency- or
-        issue-bound.  The thermal branch and one cross term are therefore issued on a second stream: in the captured
-        train step they (and, through autograd's stream tracking, their backwards) become parallel arms of the
-        graph.  Measured: 2.93 -> 2.83 ms/step with the thermal branch on the second stream, -> 2.67 with the cross
-        terms overlapped as well; a four-stream version (cross terms started right after the samplers) was slower
-        (2.73).  The jitter draws are made first, in the reference's order, so the random stream is unchanged."""
-        dev = ray_bundle.origins.device
-        num_rays = ray_bundle.origins.shape[0]
-        if jitters is None:
-            jitters = self.proposal_sampler.draw_jitters(num_rays, dev)
-        if jitters_thermal is None:
-            jitters_thermal = self.proposal_sampler_thermal.draw_jitters(num_rays, dev)
-        main = torch.cuda.current_stream(dev)
-        if self._side_stream is None or self._side_stream.device != dev:
-            self._side_stream = torch.cuda.Stream(device=dev)
-        side = self._side_stream
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            thermal_outputs, ray_samples_thermal = self._thermal_branch(ray_bundle_thermal, jitters_thermal)
-        self.shared_camera_optimizer.apply_to_raybundle(ray_bundle)
-        if self.training:
-            self.camera_optimizer.apply_to_raybundle(ray_bundle)
-        outputs, ray_samples = self._branch(ray_bundle, self.proposal_sampler, self.density_fns, self.field,
-                                            self.renderer_rgb, jitters)
-        main.wait_stream(side)
-        cross = None
-        if want_cross:
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                d2t = self.field_thermal.get_density_only(ray_samples)
-            d2 = self.field.get_density_only(ray_samples_thermal)
-            main.wait_stream(side)
-            cross = (d2, d2t)
-        crossing = list(thermal_outputs.values()) + [ray_samples_thermal._layout.ebins, ray_samples_thermal._layout.sbins]
-        crossing += [cross[1]] if cross is not None else []
-        for v in crossing:  # made on the side stream, consumed (and eventually freed) on the main one
-            if torch.is_tensor(v):
-                v.record_stream(main)
-        return outputs, thermal_outputs, ray_samples, ray_samples_thermal, cross
 
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle: RayBundle) -> Dict[str, Tensor]:

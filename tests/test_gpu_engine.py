@@ -213,7 +213,7 @@ def _ddp_worker(rank, world, port, mode, out_dir):
         rays = 1024
         batch = {k: v.to(dev) for k, v in bench.make_batch(rays, 42 + rank, num_cams=8).items()}
         runner = eng.GraphedTrainStep(model, batch, use_graph=True)
-        assert runner._comm_in_graph == (mode == "overlap")
+        assert runner._comm_in_graph == (mode == "overlap") and runner._pipeline == (mode == "pipeline")
         for _ in range(2):
             runner.step(batch)
         torch.cuda.synchronize()
@@ -250,7 +250,7 @@ def _ddp_worker(rank, world, port, mode, out_dir):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["overlap", "after"])
+@pytest.mark.parametrize("mode", ["pipeline", "overlap", "after"])
 def test_nccl_world2_gradients_equal_single_gpu_on_concatenated_batch(tmp_path, mode):
     """SURVEY 8e parity test: N-GPU averaged gradients == 1-GPU gradients of the concatenated batch (every loss term
     is a mean over rays, patches or samples, and the ranks hold equal shares), rel 1e-3, for the overlapped two-segment
@@ -262,3 +262,33 @@ def test_nccl_world2_gradients_equal_single_gpu_on_concatenated_batch(tmp_path, 
     assert len(res) >= 6
     for k, v in res.items():
         assert v <= 1e-3, (mode, k, v)
+
+
+def test_three_phase_schedule_equals_the_single_graph():
+    """engine "pipeline" (sample phase | render phase + backward to the cut | backward of the sample phase, three
+    graphs) gives the losses and gradients of the one-graph step: the cut only re-orders independent work."""
+    from nerfstudio_thermal_b200 import engine as eng
+    import bench
+
+    model, _ = pu.bench_like_model(tn, "separate", 15, "trained", num_cams=8, seed=7)
+    model = model.to(DEV).train()
+    for s in (model.proposal_sampler, model.proposal_sampler_thermal):
+        s.initial_sampler.train_stratified = False  # no jitter: both runners see the same samples
+        s.pdf_sampler.train_stratified = False
+    batch = {k: v.to(DEV) for k, v in bench.make_batch(1024, 3, num_cams=8).items()}
+    res = []
+    for pipeline in (False, True):
+        runner = eng.GraphedTrainStep(model, batch, use_graph=True, pipeline=pipeline)
+        assert runner._pipeline == pipeline
+        for _ in range(2):
+            total = runner.step(batch)
+        runner.finish_exchange()
+        torch.cuda.synchronize()
+        res.append((float(total), {k: float(v) for k, v in runner.losses.items()}, runner.grads.flat.clone(),
+                    dict(runner.grads.group_ranges)))
+    (t0, l0, g0, ranges), (t1, l1, g1, _) = res
+    assert abs(t0 - t1) <= 1e-6 * abs(t0)
+    for k in l0:
+        assert abs(l0[k] - l1[k]) <= 2e-6 * max(abs(l0[k]), 1e-6), k
+    for name, (b, e) in ranges.items():
+        assert pu.rel_l2(g1[b:e], g0[b:e]) <= 2e-5, name

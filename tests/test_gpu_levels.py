@@ -46,9 +46,12 @@ def test_level_resample_equals_the_separate_kernels(S, S_new, train):
     assert torch.equal(sb_new, sb_ref) and torch.equal(eb_new, eb_ref)
 
 
-@pytest.mark.parametrize("C,bg_mode,bg,eval_mode", [(3, ops.BG_LAST_SAMPLE, None, False), (1, ops.BG_LAST_SAMPLE, None, False),
-                                                   (4, ops.BG_CONSTANT, (1.0, 1.0, 1.0, 1.0), False),
-                                                   (3, ops.BG_NONE, None, True)])
+BG_NONE, BG_LAST_SAMPLE, BG_CONSTANT = 0, 1, 2  # ops.BG_* (the package imports only where a GPU is present)
+
+
+@pytest.mark.parametrize("C,bg_mode,bg,eval_mode", [(3, BG_LAST_SAMPLE, None, False), (1, BG_LAST_SAMPLE, None, False),
+                                                   (4, BG_CONSTANT, (1.0, 1.0, 1.0, 1.0), False),
+                                                   (3, BG_NONE, None, True)])
 def test_ray_heads_equal_the_separate_kernels(C, bg_mode, bg, eval_mode):
     from nerfstudio_thermal_b200 import fused_ops as fo
 
@@ -96,13 +99,13 @@ def test_ray_heads_without_losses_or_proposal_gradients():
     sigma, eb, sb, _, _ = (t.to(DEV) for t in _level(R, S, 5))
     colour = torch.rand(R, S, 3, device=DEV)
     with torch.no_grad():  # eval: no losses
-        out = fo.ray_heads(sigma, colour, eb, sb, bg_mode=ops.BG_LAST_SAMPLE, bg=None, eval_mode=True, want_losses=False)
+        out = fo.ray_heads(sigma, colour, eb, sb, bg_mode=BG_LAST_SAMPLE, bg=None, eval_mode=True, want_losses=False)
     assert out[6] is None and out[7] is None and out[0].shape == (R, 3)
     # training while the proposal networks are not updated: the interlevel VALUE is still formed, no gradient flows
     psig, peb, psb, _, _ = (t.to(DEV) for t in _level(R, 96, 6))
     pw = ops.sample_weights(psig, peb[:, 1:] - peb[:, :-1])
     sig = sigma.clone().requires_grad_(True)
-    out = fo.ray_heads(sig, colour, eb, sb, bg_mode=ops.BG_LAST_SAMPLE, bg=None, eval_mode=False, want_losses=True,
+    out = fo.ray_heads(sig, colour, eb, sb, bg_mode=BG_LAST_SAMPLE, bg=None, eval_mode=False, want_losses=True,
                        prop_sigma=(), prop_ebins=[peb], prop_sbins=[psb], prop_weights=[pw])
     ref = fo.interlevel_loss_level(out[5], sb, pw, psb)
     torch.testing.assert_close(out[7], ref, rtol=2e-6, atol=1e-9)
