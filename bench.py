@@ -307,7 +307,12 @@ class Dist:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=self.dev)
+            opts = None
+            if os.environ.get("TN_NCCL_HIGH_PRIO", "1") == "1":
+                # the gradient exchange runs beside compute kernels that fill every SM: a high-priority NCCL stream
+                # gets its CTAs placed as soon as a slot frees instead of after the compute kernel's last wave
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            dist.init_process_group("nccl", device_id=self.dev, pg_options=opts)
         assert self.world == gpus, f"--gpus {gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run"
         self.dist = dist
 

@@ -392,6 +392,17 @@ int tn_ray_heads_bwd(const float* sigma, const float* colour, const float* ebins
                      float* dcolour_out, float* const* prop_dsigma_host_ptrs, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory (replaces, for the main fields' 134 MB, the bucketed all-reduce of
+ * DistributedDataParallel, pipelines/base_pipeline.py:280-283): the bulk moves by copy-engine pulls between
+ * symmetric buffers (host side: parallel.PeerExchange), this is the only kernel of it.
+ * dst[n] = (dst[n] + sum_k src[k * src_stride + n]) * scale for n_src staged copies; n and src_stride multiples of 4,
+ * 16-byte aligned pointers.  max_ctas: grid cap (0 = 2 per SM), so that the reduction can stay out of the way of
+ * compute kernels running beside it.
+ * ------------------------------------------------------------------------------------------------ */
+int tn_shard_mean(float* dst, const float* src, int n_src, int64_t src_stride, int64_t n, float scale, int max_ctas,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Measurement aid (bench.py, SURVEY 8d "L2 peak must be measured"): the access pattern of the hash-grid kernels
  * and nothing else.  Every thread of `ctas` x 256 issues `iters` (multiple of 8) operations at pseudo-random rows
  * of table[2^log2_rows, 2] (float32, 16-byte aligned; REDs modify it):

@@ -82,6 +82,7 @@ _SIGNATURES = {
                          POINTER(c_int), _FPP, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "tn_ray_heads_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int,
                          _FPP, _FPP, _FPP, POINTER(c_int), _P, _P, _FPP, _P],
+    "tn_shard_mean": [_P, _P, c_int, c_int64, c_int64, c_float, c_int, _P],
     "tn_l2_probe": [c_int, _P, c_int, c_int, c_int, _P, _P],
 }
 _RESTYPES = {"tn_last_error_string": c_char_p, "tn_build_arch": c_char_p}

@@ -168,6 +168,22 @@ __global__ void step_counters_tick_kernel(int32_t* c, int n_groups, uint32_t act
   else if (t <= n_groups && ((active_mask >> (t - 1)) & 1u)) c[t] += 1;
 }
 
+// ---- gradient exchange over NVLink peer memory (parallel.PeerExchange): the reduction step.
+// dst[i] = (dst[i] + sum_k src[k*stride + i]) * scale: this rank's shard plus the copies of the same shard that the
+// copy engines pulled from the peers, averaged.  Streaming, float4, grid-stride; the only SM work of the exchange.
+__global__ void __launch_bounds__(256) shard_mean_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                                         int n_src, int64_t stride, int64_t n4, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(dst)[i];
+    for (int k = 0; k < n_src; ++k) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + (size_t)k * stride) + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
@@ -237,4 +253,19 @@ extern "C" int tn_counter_add(int32_t* counter_dev, int value, void* stream) {
   TN_REQUIRE(counter_dev, TN_EINVAL, "counter_add: null pointer");
   counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, value);
   return check_launch("counter_add_kernel");
+}
+
+extern "C" int tn_shard_mean(float* dst, const float* src, int n_src, int64_t src_stride, int64_t n, float scale,
+                             int max_ctas, void* stream) {
+  TN_REQUIRE(dst && (src || n_src == 0), TN_EINVAL, "shard_mean: null pointer");
+  TN_REQUIRE(n >= 0 && n % 4 == 0 && n_src >= 0 && src_stride % 4 == 0 && src_stride >= n, TN_EINVAL,
+             "shard_mean: n=%lld (multiple of 4), n_src=%d, stride=%lld", (long long)n, n_src, (long long)src_stride);
+  TN_REQUIRE(aligned(dst, 16) && aligned(src, 16), TN_EALIGN, "shard_mean: pointers must be 16-byte aligned");
+  if (n == 0) return TN_OK;
+  const int64_t n4 = n / 4;
+  int64_t ctas = (n4 + 255) / 256;
+  const int64_t cap = max_ctas > 0 ? max_ctas : 2 * kNumSMs;
+  if (ctas > cap) ctas = cap;
+  shard_mean_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(dst, src, n_src, src_stride, n4, scale);
+  return check_launch("shard_mean_kernel");
 }

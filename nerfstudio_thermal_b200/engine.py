@@ -94,11 +94,18 @@ class GraphedTrainStep:
         # and both collectives (and the optimiser) are captured inside the CUDA graph.
         early = [n for n in ("fields", "fields_thermal") if n in groups]
         order = early + [n for n in groups if n not in early]
-        self.grads = parallel.FlatGradBuffer.from_param_groups(groups, order=order, device=self.device)
+        nccl = world > 1 and torch.distributed.get_backend(group) == "nccl"
+        # measured (profiles/r02_exchange.md, ms/step at 2 / 4 / 8 GPUs; one GPU: 2.27): "after" 2.61 / - / 2.74,
+        # "overlap" 2.48 / 2.57 / 3.06, "pipeline" 2.57 / 2.69 / 2.64 -- the in-graph overlap wins up to four GPUs, the
+        # three-phase pipeline with the peer-memory exchange beyond
+        default = "overlap" if world <= 4 else "pipeline"
+        mode = os.environ.get("TN_COMM", default if overlap_comm is None else ("overlap" if overlap_comm else "after"))
+        # the main fields' exchange over NVLink peer memory (parallel.PeerExchange) needs a peer-mappable buffer
+        want_peer = nccl and mode == "pipeline" and use_graph and os.environ.get("TN_PEER_EXCHANGE", "1") == "1"
+        self.grads = parallel.FlatGradBuffer.from_param_groups(groups, order=order, device=self.device,
+                                                               symmetric=want_peer)
         self.grads.attach_sinks(model)
         self._early_end = max((self.grads.group_ranges[n][1] for n in early), default=0)
-        nccl = world > 1 and torch.distributed.get_backend(group) == "nccl"
-        mode = os.environ.get("TN_COMM", "pipeline" if overlap_comm is None else ("overlap" if overlap_comm else "after"))
         if mode not in ("pipeline", "overlap", "after"):
             raise ValueError(f"TN_COMM={mode!r}: expected pipeline | overlap | after")
         # "pipeline": three graphs per step, the main fields' all-reduce hidden behind the proposal backward and the
@@ -128,6 +135,18 @@ class GraphedTrainStep:
         self._early_active = self._early_end > 0 and (self._comm_in_graph or self._adam_in_graph) and not self._pipeline
         if self._early_active or self._pipeline:
             self._comm_stream = torch.cuda.Stream(device=self.device)
+        # "pipeline": the main fields' all-reduce gets its OWN communicator.  A process group issues all its
+        # collectives on one internal stream, in order: on a shared communicator the small trailing all-reduce (which
+        # the main stream waits for) would queue behind the big one and put it back on the critical path.
+        self._main_group = group
+        self._peer: Optional[parallel.PeerExchange] = None
+        if self._pipeline and nccl and self.grads.symmetric:
+            # copy-engine pulls over peer memory + one small reduction kernel instead of an NCCL all-reduce whose
+            # CTAs would compete with the proposal kernels it hides behind
+            self._peer = parallel.PeerExchange(self.grads.flat, 0, self._early_end, group)
+        elif self._pipeline and nccl:
+            ranks = torch.distributed.get_process_group_ranks(group) if group is not None else None
+            self._main_group = torch.distributed.new_group(ranks=ranks, backend="nccl")
         for f in self._fields:  # (also detaches the hooks of an earlier runner of the same model)
             f.grads_ready_callback = self._field_ready if self._early_active else None
         self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
@@ -392,7 +411,10 @@ class GraphedTrainStep:
         ready.record(main)
         comm.wait_event(ready)
         with torch.cuda.stream(comm):  # the main fields' segment: hidden behind C and the next step's A
-            self.grads.all_reduce_mean(self.group, begin=0, end=self._early_end)
+            if self._peer is not None:
+                self._peer.all_reduce_mean()
+            else:
+                self.grads.all_reduce_mean(self._main_group, begin=0, end=self._early_end)
             if self.optimizer is not None:
                 self.optimizer.step_range(0, self._early_end, zero_grads=False)
             self._comm_event = torch.cuda.Event()

@@ -23,7 +23,8 @@ from torch import Tensor, nn
 class FlatGradBuffer:
     """All gradients of a module in one contiguous fp32 buffer, laid out group by group."""
 
-    def __init__(self, params: Iterable[nn.Parameter], device=None, group_of: Optional[Dict[int, str]] = None):
+    def __init__(self, params: Iterable[nn.Parameter], device=None, group_of: Optional[Dict[int, str]] = None,
+                 symmetric: bool = False):
         seen, self.params = set(), []
         for p in params:
             if p.requires_grad and p.numel() > 0 and id(p) not in seen:
@@ -35,7 +36,14 @@ class FlatGradBuffer:
         for p in self.params:
             self.offsets.append(total)
             total += (p.numel() + 3) // 4 * 4
-        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        if symmetric:
+            # symmetric (peer-mappable) allocation: the other ranks' copy engines read it directly (PeerExchange)
+            import torch.distributed._symmetric_memory as symm_mem
+            self.flat = symm_mem.empty(total, dtype=torch.float32, device=torch.device(device))
+            self.flat.zero_()
+        else:
+            self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.symmetric = symmetric
         for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
         # named groups = contiguous element ranges [begin, end) (alignment padding inside a group included)
@@ -50,13 +58,14 @@ class FlatGradBuffer:
         self.flat_params: Optional[Tensor] = None
 
     @classmethod
-    def from_param_groups(cls, groups: Dict[str, List[nn.Parameter]], order: Optional[List[str]] = None, device=None):
+    def from_param_groups(cls, groups: Dict[str, List[nn.Parameter]], order: Optional[List[str]] = None, device=None,
+                          symmetric: bool = False):
         names = order if order is not None else list(groups)
         group_of: Dict[int, str] = {}
         for n in names:
             for p in groups[n]:
                 group_of.setdefault(id(p), n)  # a parameter listed twice belongs to its first group
-        return cls([p for n in names for p in groups[n]], device=device, group_of=group_of)
+        return cls([p for n in names for p in groups[n]], device=device, group_of=group_of, symmetric=symmetric)
 
     def group_params(self, name: str) -> List[Tuple[nn.Parameter, int]]:
         """(parameter, element offset) of every parameter of a named group, in buffer order."""
@@ -118,6 +127,63 @@ class FlatGradBuffer:
         work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group, async_op=False)
         part.div_(world)
         return work
+
+
+class PeerExchange:
+    """Average elements [begin, end) of a SYMMETRIC flat gradient buffer over the ranks of one NVLink / NVSwitch
+    domain without NCCL and (almost) without SMs:
+
+        barrier | every rank PULLS its own shard of the segment from each peer (copy engines, peer memory)
+                | one reduction kernel: shard = (own + pulled copies) / world            (tn_shard_mean)
+        barrier | every rank pulls the other ranks' reduced shards into its buffer        (copy engines)
+        barrier   (nobody may rewrite its buffer while a peer still reads it)
+
+    An NCCL all-reduce of the same 134 MB keeps 16-32 CTAs busy for its whole duration and slows the issue-bound
+    proposal kernels it is supposed to hide behind by 50-60 % (profiles/r02_exchange.md); here the bulk moves on the
+    copy engines and the only kernel streams 1/world of the segment once.  Everything is enqueued on the current
+    stream (barriers included: device-side, through the symmetric memory's signal pads), nothing blocks the host.
+    Same result as DistributedDataParallel's averaged gradients (pipelines/base_pipeline.py:280-283) up to the
+    summation order."""
+
+    def __init__(self, flat: Tensor, begin: int, end: int, group=None, max_ctas: int = 32):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from ._lib import call, ptr, stream  # noqa: F401  (fails loudly without the CUDA library)
+
+        group = group if group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(flat, group)  # collective
+        self.flat, self.begin, self.end = flat, begin, end
+        self.world, self.rank = self.handle.world_size, self.handle.rank
+        n = end - begin
+        assert begin % 4 == 0 and n % 4 == 0, "segment must be made of whole 16-byte units"
+        self.shard = ((n + self.world - 1) // self.world + 3) // 4 * 4
+        self.max_ctas = max_ctas
+        self.staging = torch.empty((max(self.world - 1, 1), self.shard), dtype=torch.float32, device=flat.device)
+
+    def _span(self, r: int) -> Tuple[int, int]:
+        b = min(self.begin + r * self.shard, self.end)
+        return b, min(b + self.shard, self.end)
+
+    def all_reduce_mean(self) -> None:
+        from ._lib import call, ptr, stream
+
+        h, w, me = self.handle, self.world, self.rank
+        b, e = self._span(me)
+        h.barrier(channel=0)  # every rank's gradients of the segment are final
+        for step in range(1, w):
+            peer = (me - step) % w
+            if e > b:
+                self.staging[step - 1, :e - b].copy_(h.get_buffer(peer, (e - b,), torch.float32, b))
+        if e > b:
+            call("tn_shard_mean", ptr(self.flat) + 4 * b, ptr(self.staging), w - 1, self.shard, e - b, 1.0 / w,
+                 self.max_ctas, stream(), tag="[exchange]", units=e - b)
+        h.barrier(channel=1)  # every shard is reduced
+        for step in range(1, w):
+            peer = (me - step) % w
+            pb, pe = self._span(peer)
+            if pe > pb:
+                self.flat[pb:pe].copy_(h.get_buffer(peer, (pe - pb,), torch.float32, pb))
+        h.barrier(channel=2)  # every rank has read what it needs: buffers may be rewritten
 
 
 def shard_chunks(num_rays: int, chunk: int, rank: int, world: int) -> List[Tuple[int, int]]:
