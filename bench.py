@@ -207,6 +207,21 @@ def load_traffic():
     return json.load(open(path)) if os.path.exists(path) else {}
 
 
+def l2_request_roofline(tag, avg_launch_ms, traffic, l2):
+    """The launch against the MEASURED L2 request rates, with the request counts ncu counted for it: sectors the L1
+    fetched from L2 for the row gathers (lts__t_sectors_srcunit_tex_op_read) at the probe's gather rate + RED sectors
+    (l1tex__t_sectors_pipe_lsu_mem_global_op_red) at the probe's RED rate, over the live launch time.  The two streams
+    share the L1 -> L2 request path, so the floor is their SUM."""
+    det = (traffic.get("_detail") or {}).get(tag)
+    if not det or not l2:
+        return None
+    floor = det["l2_read_sectors_from_l1"] / (l2["gather8"] * 1e9) + det["l1_red_sectors"] / (l2["red_v2"] * 1e9)
+    return {"read_sectors": det["l2_read_sectors_from_l1"], "red_sectors": det["l1_red_sectors"],
+            "floor_ms_per_launch": floor * 1e3, "frac": floor * 1e3 / avg_launch_ms,
+            "what": "ncu sector counts of this launch (profiles/traffic.json) / measured L2 request rates "
+                    "(legs.l2_probe) / live launch time: the fraction of the L2 request roofline the kernel reaches"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def oracle_step(sd, cfg, batch, jit):
     import oracle
@@ -758,6 +773,9 @@ def run_b200(args):
         for r in roofs:
             r["launches_per_step"] = r.pop("launches") / args.steps
             r["traffic"] = traffic.get(r["kernel"])
+            req = l2_request_roofline(r["kernel"], r["avg_launch_ms"], traffic, l2)
+            if req is not None:
+                r["l2_requests"] = req
         # the dominant kernel = the launch tag with the largest total time among ALL of this library's kernels
         roofline = dict(roofs[0]) if roofs else None
         if roofline is not None:
