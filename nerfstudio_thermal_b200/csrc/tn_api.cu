@@ -37,7 +37,7 @@ int pair_reds() {
   return v;
 }
 float agg_threshold_prop() {
-  static const float v = env_float("TN_AGG_PROP", 96.f);
+  static const float v = env_float("TN_AGG_PROP", 300.f);
   return v;
 }
 }  // namespace tn

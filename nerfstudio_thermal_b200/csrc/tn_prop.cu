@@ -13,15 +13,26 @@
 //
 // Backward per point: recompute features and hidden units, back-propagate to the features, scatter into the
 // table gradient (run-aggregated REDs as in tn_encode.cu), optionally dL/dx -> contraction backward -> per-ray
-// dL/d(origin, direction).  Weight gradients: each 128-point tile stages (dh, features, g*h) in shared memory
-// and 128 threads reduce the 193 entries of (dW1, db1, dW2, db2) into register accumulators that live across the
-// tiles of a persistent CTA; one atomicAdd per entry per CTA at the end.
+// dL/d(origin, direction).  Weight gradients: the kernel is bound by the SM's load/store pipe (gathers, REDs,
+// shuffles and shared-memory traffic share it: ncu l1tex 80 % of peak at 45 % issue), so the 193 sums over points
+// (dW1, db1, dW2, db2) run on the tensor cores instead of as shared-memory dot products: every warp stages
+// (dh, g*h, features) of its 32 points once (conflict-free 4-byte rows) and accumulates
+//     [dh ; g*h]^T (32 x points)  .  [features | 1] (points x 11)
+// with mma.sync.m16n8k8 (tf32 operands split in two terms, three MMAs per product: ~2^-21 relative) in register
+// accumulators that live across the tiles of a persistent CTA; the warps' partial sums are combined in shared
+// memory and leave as one atomicAdd per entry per CTA.
 // Compiled with -fmad=false (index math must round like the reference); the MLP uses explicit fmaf().
 #include "tn_encode_core.cuh"
 #include "tn_geometry.cuh"
 
 namespace tn {
 
+#ifndef TN_PROP_FWD_MB
+#define TN_PROP_FWD_MB 4
+#endif
+#ifndef TN_PROP_BWD_MB
+#define TN_PROP_BWD_MB 4
+#endif
 constexpr int PH = 16;       // hidden width of the proposal MLP
 constexpr int PMAXL = 8;     // levels supported by the fused kernel (F = 2 -> at most 16 input features)
 
@@ -71,19 +82,22 @@ __device__ __forceinline__ void prop_features(const float* __restrict__ table, c
         const float mx = 1.f - ox, my = 1.f - oy, mz = 1.f - oz;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const float f03 = f[b][0][j] * ox + f[b][3][j] * mx;
-          const float f12 = f[b][1][j] * ox + f[b][2][j] * mx;
-          const float f56 = f[b][5][j] * ox + f[b][6][j] * mx;
-          const float f47 = f[b][4][j] * ox + f[b][7][j] * mx;
-          const float f0312 = f03 * oy + f12 * my;
-          const float f4756 = f47 * oy + f56 * my;
-          feat[(l0 + b) * 2 + j] = f0312 * oz + f4756 * mz;
+          // trilinear weights (encodings.py:443-461).  The products may be contracted here (explicit fmaf in a
+          // -fmad=false unit): the proposal densities only steer the sampling, 1-ulp differences are far inside
+          // the 1e-5 parity bar of this field, and the kernels are short of issue slots, not of precision
+          const float f03 = fmaf(f[b][0][j], ox, f[b][3][j] * mx);
+          const float f12 = fmaf(f[b][1][j], ox, f[b][2][j] * mx);
+          const float f56 = fmaf(f[b][5][j], ox, f[b][6][j] * mx);
+          const float f47 = fmaf(f[b][4][j], ox, f[b][7][j] * mx);
+          const float f0312 = fmaf(f03, oy, f12 * my);
+          const float f4756 = fmaf(f47, oy, f56 * my);
+          feat[(l0 + b) * 2 + j] = fmaf(f0312, oz, f4756 * mz);
           if constexpr (JAC) {
             const float sl = s_scale[l0 + b];
             const float e03 = f[b][0][j] - f[b][3][j], e12 = f[b][1][j] - f[b][2][j];
             const float e56 = f[b][5][j] - f[b][6][j], e47 = f[b][4][j] - f[b][7][j];
-            jac[(l0 + b) * 2 + j][0] = ((e03 * oy + e12 * my) * oz + (e47 * oy + e56 * my) * mz) * sl;
-            jac[(l0 + b) * 2 + j][1] = ((f03 - f12) * oz + (f47 - f56) * mz) * sl;
+            jac[(l0 + b) * 2 + j][0] = fmaf(fmaf(e03, oy, e12 * my), oz, fmaf(e47, oy, e56 * my) * mz) * sl;
+            jac[(l0 + b) * 2 + j][1] = fmaf(f03 - f12, oz, (f47 - f56) * mz) * sl;
             jac[(l0 + b) * 2 + j][2] = (f0312 - f4756) * sl;
           }
         }
@@ -107,7 +121,7 @@ __device__ __forceinline__ float prop_mlp(const PropWeights& sw, const float (&f
 }
 
 template <int L>
-__global__ void __launch_bounds__(kPts, 4) prop_fwd_kernel(const float* __restrict__ origins,
+__global__ void __launch_bounds__(kPts, TN_PROP_FWD_MB) prop_fwd_kernel(const float* __restrict__ origins,
                                                            const float* __restrict__ dirs,
                                                            const float* __restrict__ ebins, const float* __restrict__ table,
                                                            LevelScales sc, int log2T, const float* __restrict__ w1,
@@ -136,11 +150,36 @@ __global__ void __launch_bounds__(kPts, 4) prop_fwd_kernel(const float* __restri
   }
 }
 
-constexpr int kStageRows = 2 * PH + 2 * PMAXL + 1;  // dh[16] | g*h[16] | feat[<=16] | g
-constexpr int kStageStride = kPts + 4;              // rows 16-byte aligned; 8 rows x 4 floats cover all 32 banks
+constexpr int kStageRows = 2 * PH + 2 * PMAXL;  // per warp: dh[16] | g*h[16] | feat[<=16], one column per lane
+constexpr int kStageStride = 36;                // = 4 mod 32: the MMA fragment reads (row g, column t) hit 32 banks
+
+// D(16x8) += A(16x8, row) . B(8x8, col), tf32 operands, fp32 accumulate.  Fragments (g = lane/4, t = lane%4):
+// a = {A[g][t], A[g+8][t], A[g][t+4], A[g+8][t+4]}, b = {B[t][g], B[t+4][g]}, d = {D[g][2t], D[g][2t+1], D[g+8][2t], ..}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo exactly; hi holds the top 11 significand bits (a tf32), the tensor core reads the top 11 of lo
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+template <int NV>
+__device__ __forceinline__ void split_frag(const float (&x)[NV], uint32_t (&hi)[NV], uint32_t (&lo)[NV]) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) split_tf32(x[i], hi[i], lo[i]);
+}
+__device__ __forceinline__ void mma_split(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                          const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
 
 template <int L, bool NEED_DX>
-__global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
+__global__ void __launch_bounds__(kPts, TN_PROP_BWD_MB) prop_bwd_kernel(
     const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ ebins,
     const float* __restrict__ table, LevelScales sc, int log2T, int n_coarse, const float* __restrict__ w1,
     const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, float scale,
@@ -149,7 +188,7 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
     float* __restrict__ d_dirs) {
   __shared__ PropWeights sw;
   __shared__ float s_scale[TN_MAX_LEVELS];
-  __shared__ __align__(16) float stage[kStageRows * kStageStride];
+  __shared__ float stage[(kPts / 32) * kStageRows * kStageStride];
   constexpr int IN = 2 * L;
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid < TN_MAX_LEVELS) s_scale[tid] = sc.s[tid];
@@ -158,10 +197,16 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
   const uint32_t T = 1u << log2T, mask = T - 1u;
   const int64_t N = R * S;
   const int64_t tiles = (N + kPts - 1) / kPts;
-  // weight-gradient entries owned by this thread: e0 = tid, e1 = tid + 128 over
-  //   [0, PH*IN): dW1[j][k] ; then db1[PH] ; dW2[PH] ; db2
-  constexpr int NE = PH * IN + 2 * PH + 1;
-  float acc0 = 0.f, acc1 = 0.f;
+  // weight-gradient accumulators of this warp (MMA D fragments): dh x feature tile q (the "ones" column, whose sums
+  // are db1, sits at column IN % 8 of tile IN / 8), g*h x the ones tile (column IN % 8 = dW2), and sum of g (db2)
+  constexpr int NTL = IN / 8 + 1, OT = IN / 8, OC = IN % 8;
+  float accW[NTL][4], accV[4] = {0.f, 0.f, 0.f, 0.f}, acc_g = 0.f;
+#pragma unroll
+  for (int q = 0; q < NTL; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) accW[q][e] = 0.f;
+  float* wst = stage + (tid >> 5) * kStageRows * kStageStride;  // this warp's staging rows
+  const int fg = lane >> 2, ft = lane & 3;                      // fragment coordinates
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t p = t * kPts + tid;
@@ -185,18 +230,18 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
     float dfeat[IN];
 #pragma unroll
     for (int k = 0; k < IN; ++k) dfeat[k] = 0.f;
-    __syncthreads();  // previous tile's reduction has finished reading the stage
+    __syncwarp();  // the previous tile's MMA fragments have been read
 #pragma unroll
     for (int j = 0; j < PH; ++j) {
       const float dh = h[j] > 0.f ? g * sw.w2[j] : 0.f;
-      stage[j * kStageStride + tid] = dh;
-      stage[(PH + j) * kStageStride + tid] = g * h[j];
+      wst[j * kStageStride + lane] = dh;
+      wst[(PH + j) * kStageStride + lane] = g * h[j];
 #pragma unroll
       for (int k = 0; k < IN; ++k) dfeat[k] = fmaf(dh, sw.w1[j][k], dfeat[k]);
     }
 #pragma unroll
-    for (int k = 0; k < IN; ++k) stage[(2 * PH + k) * kStageStride + tid] = feat[k];
-    stage[(2 * PH + 2 * PMAXL) * kStageStride + tid] = g;
+    for (int k = 0; k < IN; ++k) wst[(2 * PH + k) * kStageStride + lane] = feat[k];
+    acc_g += g;
     // ---- dL/dx from the Jacobian of the first pass, then the table scatter
     float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
     if constexpr (NEED_DX) {
@@ -228,9 +273,14 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
         const uint64_t key = valid ? c.key : ~0ull;
         const uint64_t pkey = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = (lane == 0) || (pkey != key);
-        const int run = __popc(__ballot_sync(0xffffffffu, head) & (0xffffffffu >> (31 - lane)));
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int run = __popc(heads & (0xffffffffu >> (31 - lane)));
+        // step d of the tree is needed only if some run is longer than d, i.e. if the non-head lanes contain a
+        // streak of >= d consecutive bits (`need`); fine levels with short runs stop after one or two steps
+        unsigned need = ~heads;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
+          if (need == 0u) break;
           const int orun = __shfl_down_sync(0xffffffffu, run, d);
           const bool take = (lane + d < 32) && (orun == run);
 #pragma unroll
@@ -240,6 +290,7 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
               const float o = __shfl_down_sync(0xffffffffu, gc[k][j], d);
               if (take) gc[k][j] += o;
             }
+          need &= need >> d;
         }
         issue = valid && head;
       }
@@ -273,56 +324,61 @@ __global__ void __launch_bounds__(kPts, 4) prop_bwd_kernel(
         }
       }
     }
-    // ---- weight gradients of this tile: column sums / dot products over the 128 staged points
-    __syncthreads();
+    // ---- weight gradients of this warp's 32 points: four k-steps of 8 points
+    __syncwarp();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int e = tid + half * kPts;
-      if (e < NE) {
-        const float* a;
-        const float* b = nullptr;
-        if (e < PH * IN) {
-          a = stage + (e / IN) * kStageStride;                 // dh[j]
-          b = stage + (2 * PH + e % IN) * kStageStride;        // feat[k]
-        } else if (e < PH * IN + PH) {
-          a = stage + (e - PH * IN) * kStageStride;            // db1[j] = sum dh[j]
-        } else if (e < PH * IN + 2 * PH) {
-          a = stage + (PH + e - PH * IN - PH) * kStageStride;  // dW2[j] = sum g*h[j]
-        } else {
-          a = stage + (2 * PH + 2 * PMAXL) * kStageStride;     // db2 = sum g
-        }
-        // rows are read four points at a time (LDS.128): two loads feed four FMAs
-        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4* a4 = reinterpret_cast<const float4*>(a);
-        if (b) {
-          const float4* b4 = reinterpret_cast<const float4*>(b);
-#pragma unroll 8
-          for (int q = 0; q < kPts / 4; ++q) {
-            const float4 x = a4[q], y = b4[q];
-            s4.x = fmaf(x.x, y.x, s4.x); s4.y = fmaf(x.y, y.y, s4.y);
-            s4.z = fmaf(x.z, y.z, s4.z); s4.w = fmaf(x.w, y.w, s4.w);
-          }
-        } else {
-#pragma unroll 8
-          for (int q = 0; q < kPts / 4; ++q) {
-            const float4 x = a4[q];
-            s4.x += x.x; s4.y += x.y; s4.z += x.z; s4.w += x.w;
-          }
-        }
-        const float sum = (s4.x + s4.y) + (s4.z + s4.w);
-        if (half == 0) acc0 += sum; else acc1 += sum;
+    for (int ks = 0; ks < 4; ++ks) {
+      const float* col = wst + ks * 8 + ft;
+      float a1[4], a2[4];
+      a1[0] = col[fg * kStageStride]; a1[1] = col[(fg + 8) * kStageStride];
+      a1[2] = col[fg * kStageStride + 4]; a1[3] = col[(fg + 8) * kStageStride + 4];
+      a2[0] = col[(PH + fg) * kStageStride]; a2[1] = col[(PH + fg + 8) * kStageStride];
+      a2[2] = col[(PH + fg) * kStageStride + 4]; a2[3] = col[(PH + fg + 8) * kStageStride + 4];
+      uint32_t a1h[4], a1l[4], a2h[4], a2l[4];
+      split_frag<4>(a1, a1h, a1l);
+      split_frag<4>(a2, a2h, a2l);
+#pragma unroll
+      for (int q = 0; q < NTL; ++q) {
+        const int fr = q * 8 + fg;  // this lane's column of tile q: feature fr, the ones column, or padding
+        const int frc = fr < IN ? fr : 0;
+        float b[2];
+        b[0] = col[(2 * PH + frc) * kStageStride];
+        b[1] = col[(2 * PH + frc) * kStageStride + 4];
+        if (fr >= IN) b[0] = b[1] = (q == OT && fg == OC) ? 1.f : 0.f;
+        uint32_t bh[2], bl[2];
+        split_frag<2>(b, bh, bl);
+        mma_split(accW[q], a1h, a1l, bh, bl);
+        if (q == OT) mma_split(accV, a2h, a2l, bh, bl);
       }
     }
   }
-  // ---- flush the weight-gradient accumulators
+  // ---- flush: the warps' fragments -> one [NE] vector per warp in shared memory -> one atomicAdd per entry per CTA
+  //   entries: [0, PH*IN): dW1[j][k] (nn.Linear flattening) ; then db1[PH] ; dW2[PH] ; db2
+  constexpr int NE = PH * IN + 2 * PH + 1;
+  static_assert(NE <= kStageRows * kStageStride, "flush vector must fit in a warp's staging rows");
+  __syncwarp();
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int e = tid + half * kPts;
-    const float v = half == 0 ? acc0 : acc1;
-    if (e < PH * IN) atomicAdd(dw1 + e, v);  // [j][k] row-major with k < IN: same flattening as nn.Linear
+  for (int q = 0; q < NTL; ++q)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = fg + (e >= 2 ? 8 : 0), k = q * 8 + 2 * ft + (e & 1);
+      if (k < IN) wst[j * IN + k] = accW[q][e];
+      else if (q == OT && k - q * 8 == OC) wst[PH * IN + j] = accW[q][e];
+    }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (2 * ft + (e & 1) == OC) wst[PH * IN + PH + fg + (e >= 2 ? 8 : 0)] = accV[e];
+  const float gsum = warp_sum(acc_g);
+  if (lane == 0) wst[PH * IN + 2 * PH] = gsum;
+  __syncthreads();
+  for (int e = tid; e < NE; e += kPts) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kPts / 32; ++w) v += stage[w * kStageRows * kStageStride + e];
+    if (e < PH * IN) atomicAdd(dw1 + e, v);
     else if (e < PH * IN + PH) atomicAdd(db1 + (e - PH * IN), v);
     else if (e < PH * IN + 2 * PH) atomicAdd(dw2 + (e - PH * IN - PH), v);
-    else if (e < NE) atomicAdd(db2, v);
+    else atomicAdd(db2, v);
   }
 }
 
@@ -392,7 +448,7 @@ extern "C" int tn_prop_density_bwd(const float* origins, const float* directions
     if (l < L && l == n_coarse && scales_host[l] <= agg_threshold_prop()) ++n_coarse;
   }
   const int64_t N = R * S;
-  const unsigned grid = (unsigned)min((N + kPts - 1) / kPts, (int64_t)kNumSMs * 4);
+  const unsigned grid = (unsigned)min((N + kPts - 1) / kPts, (int64_t)kNumSMs * TN_PROP_BWD_MB);
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_PB(LL, ...)                                                                 \
   do {                                                                                 \
