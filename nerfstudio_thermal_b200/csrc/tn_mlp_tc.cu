@@ -74,28 +74,45 @@ __device__ __forceinline__ void store_chunk_terms(uint8_t* base, int term_stride
 }
 
 // nn.Linear weight [n_real][k_real] (row-major fp32) -> NT operand tiles with NP rows, KP features.
-// All global loads of a matrix are issued before the first is consumed (one L2 round trip per matrix).
+// A thread converts whole 16-byte chunks (8 consecutive input features of one output row): two 16-byte loads when
+// the rows allow it, one 16-byte shared-memory store per term (consecutive threads -> consecutive rows, no bank
+// conflicts).  All global loads of a matrix are issued before the first is consumed (one L2 round trip per matrix).
 template <int NP, int KP, int NT>
 __device__ __forceinline__ void load_weight_terms(const float* __restrict__ w, int n_real, int k_real, uint8_t* base) {
-  static_assert((NP * KP) % NTH == 0, "weight tile must be a whole number of passes");
-  constexpr int ITERS = NP * KP / NTH;
-  float v[ITERS];
+  constexpr int CHUNKS = NP * KP / 8;
+  constexpr int ITERS = (CHUNKS + NTH - 1) / NTH;
+  const bool vec = ((k_real & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+  float v[ITERS][8];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
-    const int i = threadIdx.x + it * NTH;
-    const int n = i / KP, k = i - n * KP;
-    v[it] = (n < n_real && k < k_real) ? __ldg(w + (size_t)n * k_real + k) : 0.f;
+    const int c = threadIdx.x + it * NTH;
+    const int kc = c / NP, n = c - kc * NP, k0 = kc * 8;
+    const float* src = w + (size_t)n * k_real + k0;
+    if (c < CHUNKS && n < n_real && vec) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + 4 * h < k_real) q = __ldg(reinterpret_cast<const float4*>(src + 4 * h));
+        v[it][4 * h] = q.x; v[it][4 * h + 1] = q.y; v[it][4 * h + 2] = q.z; v[it][4 * h + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[it][i] = (c < CHUNKS && n < n_real && k0 + i < k_real) ? __ldg(src + i) : 0.f;
+    }
   }
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
-    const int i = threadIdx.x + it * NTH;
-    const int n = i / KP, k = i - n * KP;
-    const size_t off = (size_t)(k >> 3) * NP * 16 + (size_t)n * 16 + (k & 7) * 2;
-    uint32_t t[NT];
-    split_pair<NT>(v[it], 0.f, t);
+    const int c = threadIdx.x + it * NTH;
+    if (c < CHUNKS) {
+      const int kc = c / NP, n = c - kc * NP;
+      uint32_t t[4][NT];
 #pragma unroll
-    for (int q = 0; q < NT; ++q)
-      *reinterpret_cast<uint16_t*>(base + (size_t)q * NP * KP * 2 + off) = (uint16_t)(t[q] & 0xffffu);
+      for (int i = 0; i < 4; ++i) split_pair<NT>(v[it][2 * i], v[it][2 * i + 1], t[i]);
+#pragma unroll
+      for (int q = 0; q < NT; ++q)
+        *reinterpret_cast<uint4*>(base + (size_t)q * NP * KP * 2 + (size_t)kc * NP * 16 + (size_t)n * 16) =
+            make_uint4(t[0][q], t[1][q], t[2][q], t[3][q]);
+    }
   }
 }
 
@@ -325,7 +342,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
     fence_async_smem();
     __syncthreads();  // A0 visible to the async proxy
     // ---- layer 1
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_layer<W, IN, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w1));
       mma_commit(bar);
@@ -343,7 +360,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
     __syncthreads();
     // ---- layer 2 (3-layer networks)
     if constexpr (NL == 3) {
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         issue_layer<W, W, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w2));
         mma_commit(bar);
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(NTH, TcSmem<IN, W, NL>::per_sm) mlp_tc_fwd_ker
       __syncthreads();
     }
     // ---- output layer
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_layer<OUTP, W, FT>(tmem, smem_u32(act), L::act_term, smem_u32(sm + L::w3));
       mma_commit(bar);
@@ -439,16 +456,22 @@ struct TcBwdSmem {
   static constexpr int w3 = w2 + (NL == 3 ? BT * W * W * 2 : 0);
   static constexpr int bias = w3 + BT * W * OUTP * 2;
   static constexpr int oh = bias + (2 * W + OUTP) * 4;           // one-hot "ray slot" chunk (head mode), 1 term
-  static constexpr int a0 = oh + CH;                             // BT terms, (IN/8 + 1) chunks each
+  static constexpr int a0 = oh + (IN == 64 && NL == 3 ? CH : 0); // BT terms, (IN/8 + 1) chunks each
   static constexpr int a0_term = (IN / 8 + 1) * CH;
   static constexpr int h1 = a0 + BT * a0_term;                   // BT terms, (W/8 + 1) chunks each
   static constexpr int h_term = (W / 8 + 1) * CH;
   static constexpr int h2 = h1 + BT * h_term;
-  static constexpr int g = h2 + (NL == 3 ? BT * h_term : 0);     // dZ tile: BT terms of 8 chunks
+  // dZ tiles.  Each layer's dW^T MMAs run BEHIND the critical path (they are committed to their own mbarrier and
+  // only awaited at the end of the tile), so a dZ tile must stay intact while the next one is written: the output
+  // layer's dZ (16 features = 2 chunks) has its own tile, the hidden layers' dZ alternate between two tiles.
+  static constexpr int gout = h2 + (NL == 3 ? BT * h_term : 0);  // dZ_out: BT terms of 2 chunks
+  static constexpr int gout_term = 2 * CH;
+  static constexpr int g2 = gout + BT * gout_term;               // dZ of the FIRST hidden layer of 3-layer networks
+  static constexpr int g = g2 + (NL == 3 ? BT * 8 * CH : 0);     // dZ of the last hidden layer: BT terms of 8 chunks
   static constexpr int g_term = 8 * CH;
   static constexpr int g_bytes = BT * g_term + 2048;             // + M=128 over-read slack
-  static constexpr int bar = g + g_bytes;
-  static constexpr int total = bar + 16;
+  static constexpr int bar = g + g_bytes;                        // 4 mbarriers (critical path, dW3, dW2, dW1) + tmem slot
+  static constexpr int total = bar + 64;
   // TMEM columns: forward accumulators / dH / dX, then the three dW^T accumulators
   static constexpr int c_acc = 0;
   static constexpr int acc_cols = (W > IN ? W : IN) > 16 ? (W > IN ? W : IN) : 16;
@@ -591,10 +614,12 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   uint8_t* a0 = sm + L::a0;
   uint8_t* h1 = sm + L::h1;
   uint8_t* h2 = sm + L::h2;
-  uint8_t* gb = sm + L::g;
+  uint8_t* gb = sm + L::g;                    // dZ of the last hidden layer
+  uint8_t* gfirst = NL == 3 ? sm + L::g2 : gb;  // dZ1 (the same tile in 2-layer networks)
+  uint8_t* gout = sm + L::gout;
   uint8_t* hlast = NL == 3 ? h2 : h1;
-  const uint32_t bar = smem_u32(sm + L::bar);
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 8);
+  const uint32_t bar = smem_u32(sm + L::bar);  // critical path; bar + 8 / 16 / 24: the dW^T groups of layers 3 / 2 / 1
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sm + L::bar + 32);
 
   const int64_t tiles = (N + TP - 1) / TP;
   // operands fetched one tile ahead: this thread's half input row, and (column half 0) the point's dy row
@@ -624,7 +649,8 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   }
   if (tid < OUTP) bias[2 * W + tid] = tid < prm.out_dim ? __ldg(prm.b[NL - 1] + tid) : 0.f;
   if (tid == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(bar + 8 * i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<L::tcols>(smem_u32((const void*)tmem_slot));
@@ -641,8 +667,10 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_dw = 0;
   uint32_t dw_acc = 0;  // 0 on the first tile (overwrite), 1 afterwards (accumulate)
+  // the output layer's pre-activations are only needed for the derivative of its activation
+  const bool need_z = prm.out_act != 0;
 
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
@@ -677,7 +705,7 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
     fence_async_smem();
     __syncthreads();
     // ---------------- forward recompute (activation VALUES; gating below uses the forward's masks)
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       issue_layer<W, IN, BT>(tmem + L::c_acc, smem_u32(a0), L::a0_term, smem_u32(sm + L::w1));
       mma_commit(bar);
@@ -689,7 +717,7 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
     tc_fence_before();
     __syncthreads();
     if constexpr (NL == 3) {
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
         issue_layer<W, W, BT>(tmem + L::c_acc, smem_u32(h1), L::h_term, smem_u32(sm + L::w2));
         mma_commit(bar);
@@ -701,44 +729,51 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
       tc_fence_before();
       __syncthreads();
     }
-    if (tid == 0) {
+    if (need_z) {
+      if (warp == 0 && elect_one()) {
+        tc_fence_after();
+        issue_layer<OUTP, W, BT>(tmem + L::c_acc, smem_u32(hlast), L::h_term, smem_u32(sm + L::w3));
+        mma_commit(bar);
+      }
+      mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      issue_layer<OUTP, W, BT>(tmem + L::c_acc, smem_u32(hlast), L::h_term, smem_u32(sm + L::w3));
-      mma_commit(bar);
     }
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
-    // ---------------- dZ_out = dy * act'(z)  -> G tile (16 features = 2 chunks)
+    // ---------------- dZ_out = dy * act'(z)  -> its own tile (16 features = 2 chunks)
     if (half == 0) {
       float z[16];
-      tmem_ld16(tmem_row + L::c_acc, z);
-      tmem_ld_wait();
+      if (need_z) {
+        tmem_ld16(tmem_row + L::c_acc, z);
+        tmem_ld_wait();
+      }
       float u[16];
       const float om = prm.out_scale * xmul;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float gv = dyr[j] * om;  // zero beyond out_dim and for rows past N
-        const float zz = z[j] + bias[2 * W + j];
-        if (prm.out_act == 1) {
-          const float sg = 1.f / (1.f + expf(-zz));
-          gv *= sg * (1.f - sg);
-        } else if (prm.out_act == 2) {
-          gv *= expf(fminf(fmaxf(zz, -15.f), 15.f));
+        if (need_z) {
+          const float zz = z[j] + bias[2 * W + j];
+          if (prm.out_act == 1) {
+            const float sg = 1.f / (1.f + expf(-zz));
+            gv *= sg * (1.f - sg);
+          } else if (prm.out_act == 2) {
+            gv *= expf(fminf(fmaxf(zz, -15.f), 15.f));
+          }
         }
         u[j] = gv;
       }
-      store_chunk_terms<BT>(gb, L::g_term, 0, row, u);
-      store_chunk_terms<BT>(gb, L::g_term, 1, row, u + 8);
+      store_chunk_terms<BT>(gout, L::gout_term, 0, row, u);
+      store_chunk_terms<BT>(gout, L::gout_term, 1, row, u + 8);
     }
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    // ---------------- last layer: dWlast^T, dH_last
-    if (tid == 0) {
+    // ---------------- last layer: dH_last first (the epilogue waits for it), dWlast^T behind it
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
-      issue_dw<OUTP>(tmem + L::c_dw3, smem_u32(hlast), L::h_term, smem_u32(gb), L::g_term, dw_acc);
-      issue_dh<W, OUTP, OUTP>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w3));
+      issue_dh<W, OUTP, OUTP>(tmem + L::c_acc, smem_u32(gout), L::gout_term, smem_u32(sm + L::w3));
       mma_commit(bar);
+      issue_dw<OUTP>(tmem + L::c_dw3, smem_u32(hlast), L::h_term, smem_u32(gout), L::gout_term, dw_acc);
+      mma_commit(bar + 8);
     }
     if (t + gridDim.x < tiles) prefetch(t + gridDim.x);  // xr and dyr are both consumed by now
     mbar_wait(bar, phase); phase ^= 1;
@@ -748,35 +783,40 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
     tc_fence_before();
     __syncthreads();
     if constexpr (NL == 3) {
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after();
-        issue_dw<W>(tmem + L::c_dw2, smem_u32(h1), L::h_term, smem_u32(gb), L::g_term, dw_acc);
         issue_dh<W, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w2));
         mma_commit(bar);
+        issue_dw<W>(tmem + L::c_dw2, smem_u32(h1), L::h_term, smem_u32(gb), L::g_term, dw_acc);
+        mma_commit(bar + 16);
       }
       mbar_wait(bar, phase); phase ^= 1;
       tc_fence_after();
-      dh_epilogue<W>(tmem_row + L::c_acc, have_mask, m_first, h1, gb, L::g_term, row, half);  // dZ1
+      dh_epilogue<W>(tmem_row + L::c_acc, have_mask, m_first, h1, gfirst, L::g_term, row, half);  // dZ1 (second tile)
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
     }
-    // ---------------- first layer: dW1^T (and dX)
-    if (tid == 0) {
+    // ---------------- first layer: what the epilogue reads (dX / the head's sums) first, dW1^T behind it
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
-      issue_dw<W>(tmem + L::c_dw1, smem_u32(a0), L::a0_term, smem_u32(gb), L::g_term, dw_acc);
       if constexpr (HEAD) {
-        issue_ray_sums<W>(tmem + L::c_ray, smem_u32(sm + L::oh), smem_u32(gb), L::g_term);
+        issue_ray_sums<W>(tmem + L::c_ray, smem_u32(sm + L::oh), smem_u32(gfirst), L::g_term);
         // dX restricted to input features 16..31 (geometry features + the first embedding column)
-        issue_dh<16, W, W, IN>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1) + 2 * (W * 16));
+        issue_dh<16, W, W, IN>(tmem + L::c_acc, smem_u32(gfirst), L::g_term, smem_u32(sm + L::w1) + 2 * (W * 16));
+        mma_commit(bar);
       } else if constexpr (NEED_DX) {
-        issue_dh<IN, W, W>(tmem + L::c_acc, smem_u32(gb), L::g_term, smem_u32(sm + L::w1));
+        issue_dh<IN, W, W>(tmem + L::c_acc, smem_u32(gfirst), L::g_term, smem_u32(sm + L::w1));
+        mma_commit(bar);
       }
-      mma_commit(bar);
+      issue_dw<W>(tmem + L::c_dw1, smem_u32(a0), L::a0_term, smem_u32(gfirst), L::g_term, dw_acc);
+      mma_commit(bar + 24);
     }
     dw_acc = 1;
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
+    if constexpr (HEAD || NEED_DX) {
+      mbar_wait(bar, phase); phase ^= 1;
+      tc_fence_after();
+    }
     if constexpr (HEAD) {
       if (half == 0) {  // dh row = [density backward | dX[16:31]]
         float v[16];
@@ -827,6 +867,11 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
         }
       }
     }
+    // the dW^T groups have read their operand tiles (a0, h1, h2 and the dZ tiles are rewritten by the next tile)
+    mbar_wait(bar + 8, phase_dw);
+    if constexpr (NL == 3) mbar_wait(bar + 16, phase_dw);
+    mbar_wait(bar + 24, phase_dw);
+    phase_dw ^= 1;
     tc_fence_before();
     __syncthreads();
   }

@@ -54,6 +54,22 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+// One lane of a CONVERGED warp (call under a warp-uniform condition).  Issuing the MMAs under `warp == 0 &&
+// elect_one()` instead of `tid == 0` matters: behind a divergent predicate ptxas wraps every UTCHMMA (a uniform-
+// datapath instruction) in its own ELECT / BRA.U.ANY loop, ~13 instructions and a branch per MMA, all of it on the
+// tile's critical path (measured: the issuing warp spent a third of the backward kernel in that code).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
