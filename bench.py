@@ -145,6 +145,9 @@ def measured_peaks():
     return 6650.0, 1650.0, "fallback (B200_PROFILING.md)"
 
 
+PROP_SAMPLES = (256, 96)  # num_proposal_samples_per_ray of the timed configuration (models/nerfacto.py:72)
+
+
 def _tag_int(tag, key, default=0):
     """integer that follows `key` in a launch tag, e.g. _tag_int('tn_hash_encode_fwd[L16,T2^19]', 'L') == 16"""
     import re
@@ -182,6 +185,27 @@ def kernel_roofline(tag, launches, ms, units, peaks, l2=None, half_tables=False)
         # and a bin edge, one density leaves (4) instead of L*F features; backward = the density gradient in (4),
         # 8 corner rows of 8 bytes per level reduced into, dL/dx out (12)
         per = (12 + 4 + L * 64 + (12 if ",dx" in tag else 0)) if bwd else (12 + L * 64 + 4)
+        ach = per * units / sec / 1e9
+        return dict(base, bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, bytes_per_unit=per,
+                    peak_source=src)
+    if tag.startswith(("tn_level_resample", "tn_ray_heads")):
+        # composite + resample kernels, one launch per sampling level.  units = rays x samples of
+        # the level.  Per sample: sigma 4, euclidean + spacing bin edges 8, weights 4, colour 4C; per ray the new
+        # level's bin edges / jitter (resample) or the proposal histograms of the interlevel loss (heads).
+        import re
+
+        S = _tag_int(tag, "[S", 48)
+        if tag.startswith("tn_level_resample"):
+            m = re.search(r"->(\d+)", tag)
+            n_new = int(m.group(1)) if m else 0
+            per = 4 + 8 + 4 + 12.0 * (n_new + 1) / S  # new sbins + ebins written, jitter read
+        else:
+            C, n_prop = _tag_int(tag, ",C", 3), _tag_int(tag, ",+", 0)
+            prop = sum(PROP_SAMPLES[:n_prop])
+            if "fwd" in tag:  # train (n_prop > 0): + dw_distortion out; per ray w, sbins in and dw out per histogram
+                per = 4 + 4 * C + 8 + 4 + (4 + 12.0 * prop / S if n_prop else 0)
+            else:  # sigma, colour, ebins, w, dw_distortion in; dsigma, dcolour out; per proposal sample dw, sigma, ebins in, dsigma out
+                per = 4 + 4 * C + 4 + 4 + 4 + 4 + 4 * C + 16.0 * prop / S
         ach = per * units / sec / 1e9
         return dict(base, bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, bytes_per_unit=per,
                     peak_source=src)
@@ -430,6 +454,7 @@ def render_leg(args, model, D, steps, warmup, peaks, l2=None, profile=False):
         print_kernel_table(table, 1, ms_value, "render")
     out_bytes = sum({"rgb": 12}.get(k, 4) for k in keys) * total_rays
     roofs = top_rooflines(table, peaks, l2, args.half_tables, prefix="tn_hash_encode_fwd")
+    all_roofs = top_rooflines(table, peaks, l2, args.half_tables, limit=12)  # every modelled kernel at chunk size
     res = {"metric": "render rays/s, thermal-nerfacto", "value": total_rays / (ms_value * 1e-3), "unit": "rays/s",
            "ms_per_step": ms_value, "steps": steps, "warmup": max(1, warmup), "scaling": "strong",
            "config": {"workload": f"full-frame eval render 640x512 thermal + 1920x1080 RGB, density_mode={args.density_mode}, "
@@ -440,7 +465,9 @@ def render_leg(args, model, D, steps, warmup, peaks, l2=None, profile=False):
            "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": 52 * total_rays,
                    "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e},
            "gpu_launches_per_step": launches,
-           "roofline": roofs[0] if roofs else None}
+           "roofline": roofs[0] if roofs else None,
+           "rooflines": [{k: r[k] for k in ("kernel", "launches", "avg_launch_ms", "units_per_launch", "bound", "achieved",
+                                            "peak", "unit", "frac", "share_of_kernel_time") if k in r} for r in all_roofs]}
     model.train(was_training)
     return res
 
@@ -768,7 +795,7 @@ def run_b200(args):
     line = None
     if rank == 0:
         kern_ms = sum(ms for _, ms, _u in table.values()) / args.steps
-        roofs = top_rooflines(table, peaks, l2, args.half_tables)
+        roofs = top_rooflines(table, peaks, l2, args.half_tables, limit=16)
         traffic = load_traffic()
         for r in roofs:
             r["launches_per_step"] = r.pop("launches") / args.steps

@@ -526,7 +526,7 @@ class _RayHeadsFn(torch.autograd.Function):
              int(eval_mode), n_prop, ptr_array(prop_weights) if n_prop else None,
              ptr_array(prop_sbins) if n_prop else None, ints, ptr_array(prop_dw) if n_prop else None, ptr(w), ptr(rgb),
              ptr(acc), ptr(med), ptr(exp), ptr(minmax), ptr(loss_acc) if want_losses else None, ptr(dw_dist), stream(),
-             tag=f"[S{s},C{c}]", units=r * s)
+             tag=f"[S{s},C{c},+{n_prop}]" if n_prop else f"[S{s},C{c}]", units=r * s)
         ctx.cfg = (bg_mode, bg, c, [i for i in range(n_prop) if need_prop_grad[i]], prop_S)
         ctx.set_materialize_grads(False)
         live = [i for i in range(n_prop) if need_prop_grad[i]]
