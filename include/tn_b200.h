@@ -45,8 +45,9 @@ const char* tn_build_arch(void);          /* "sm_100a" */
  * table_dtype: 0 = float32, 1 = float16 (derived cache of the fp32 parameter; out stays float32).
  * idx_out: NULL, or int32[N,L,8] receiving the eight table rows per (point, level) in the reference's
  *   corner order hashed_0..hashed_7 (encodings.py:431-438) -- the bit-exactness test hook.
- * jac_out: NULL, or float32[L, N, F, 3] receiving d out[n, l*F+f] / d x[n, :] (exclusive with idx_out): handed
- *   back to tn_hash_encode_bwd it saves the backward its second gather of the corner rows.
+ * jac_out: NULL, or float32[L, F*3, N] (planar) receiving d out[n, l*F+f] / d x[n, c] at [l, f*3+c, n] for the
+ *   FINE levels (scale >= 400, TN_JAC_ENC; coarser levels are left untouched) (exclusive with idx_out): handed
+ *   back to tn_hash_encode_bwd it saves the backward its second gather of those levels' corner rows.
  * samples_per_ray: 0, or S when the points are the [R,S] samples of R rays in ray-major order (a HINT: results
  *   do not depend on it).  With S % 8 == 0, S <= 64 and N % 4S == 0 a CTA then owns 4 consecutive rays (one 2x2
  *   pixel patch of data/pixel_samplers.py:389-438) and a warp 8 consecutive samples of each, whose points share
@@ -57,8 +58,9 @@ int tn_hash_encode_fwd(const float* x, const void* table, int table_dtype, const
                        float* jac_out, void* stream);
 
 /* dy[N, L*F].  dtable[L*T, F] float32 is ACCUMULATED into (caller zero-fills for a fresh gradient).
- * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; computed from `jac` (the
- * forward's jac_out) when given, else by gathering the corner rows of `table` again. */
+ * dx: NULL or float32[N,3] (overwritten) = dL/dx through the interpolation offsets; the fine levels' share is
+ * computed from `jac` (the forward's jac_out) when given, everything else by gathering the corner rows of `table`
+ * again. */
 int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const float* scales_host,
                        const float* dy, int64_t N, int L, int F, int log2_T, int samples_per_ray, float* dtable,
                        float* dx, const float* jac, void* stream);

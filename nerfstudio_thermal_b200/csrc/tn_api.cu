@@ -36,6 +36,11 @@ int pair_reds() {
   static const int v = (int)env_float("TN_PAIR_RED", 1.f);
   return v;
 }
+// levels at least this fine keep their Jacobian when the caller passes jac_out (tn_hash_encode_fwd)
+float jac_threshold_enc() {
+  static const float v = env_float("TN_JAC_ENC", 400.f);
+  return v;
+}
 float agg_threshold_prop() {
   static const float v = env_float("TN_AGG_PROP", 300.f);
   return v;

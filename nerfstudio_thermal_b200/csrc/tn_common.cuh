@@ -45,6 +45,7 @@ float agg_threshold_enc_patch();
 float agg_threshold_prop();
 float pair_threshold_enc();  // TN_PAIR_ENC: level scale from which gathers use the lane-pair access (tn_encode_core.cuh)
 int pair_reds();             // TN_PAIR_RED: 0 switches the lane-pair REDs off (A/B measurements)
+float jac_threshold_enc();   // TN_JAC_ENC: level scale from which a saved Jacobian (jac_out / jac) covers the level
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

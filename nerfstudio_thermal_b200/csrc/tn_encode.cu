@@ -36,8 +36,10 @@ __device__ __forceinline__ int tile_pos(int row, int l, int L, int F) {
 
 constexpr int kLevelBatch = 2;  // levels whose 8-corner gathers are issued back to back (16 loads in flight/thread)
 
-// JAC: also store d(feature)/d(x) (times the level scale) as jac[L][N][F][3].  The backward then needs no second
-// gather of the corner rows for dL/dx: 12*F bytes/level of streaming instead of 8 L2 gathers/level.
+// JAC: also store d(feature)/d(x) (times the level scale) of the levels l >= jac_from, PLANAR: jac[l][F*3][N], so
+// that every store (and the backward's load) of a warp is whole 32-byte sectors.  The backward then needs no
+// second gather of those levels' corner rows for dL/dx: 12*F bytes per level of streaming instead of 8 L2 gathers
+// -- worth it exactly on the fine levels, where a gather instruction touches ~20 distinct sectors.
 // tile row owned by a thread: identity, or (patch mode) warp w / lane -> ray lane>>3, sample 8w + (lane&7)
 __device__ __forceinline__ int tile_row(int tid, int patch_S) {
   return patch_S ? ((tid & 31) >> 3) * patch_S + ((tid >> 5) << 3) + (tid & 7) : tid;
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_fwd_kernel(const float* __re
                                                                const void* __restrict__ table, LevelScales sc,
                                                                int64_t N, int L, int log2T, int patch_S,
                                                                int pair_from, float* __restrict__ out,
-                                                               int32_t* __restrict__ idx_out, float* __restrict__ jac) {
+                                                               int32_t* __restrict__ idx_out, float* __restrict__ jac,
+                                                               int jac_from) {
   extern __shared__ float4 smem4[];
   __shared__ float s_scale[TN_MAX_LEVELS];
   float* tile = reinterpret_cast<float*>(smem4);
@@ -115,14 +118,14 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_fwd_kernel(const float* __re
           const float f4756 = f47 * oy + f56 * my;
           dst[j] = f0312 * oz + f4756 * mz;
           if constexpr (JAC) {
-            if (valid) {
+            if (valid && l >= jac_from) {
               const float sl = s_scale[l];
               const float e03 = f[b][0][j] - f[b][3][j], e12 = f[b][1][j] - f[b][2][j];
               const float e56 = f[b][5][j] - f[b][6][j], e47 = f[b][4][j] - f[b][7][j];
-              float* jd = jac + ((size_t)l * N + p) * (F * 3) + j * 3;
+              float* jd = jac + ((size_t)l * (F * 3) + j * 3) * N + p;
               jd[0] = ((e03 * oy + e12 * my) * oz + (e47 * oy + e56 * my) * mz) * sl;
-              jd[1] = ((f03 - f12) * oz + (f47 - f56) * mz) * sl;
-              jd[2] = (f0312 - f4756) * sl;
+              jd[N] = ((f03 - f12) * oz + (f47 - f56) * mz) * sl;
+              jd[2 * N] = (f0312 - f4756) * sl;
             }
           }
         }
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
                                                                int log2T, int n_agg, int patch_S, int pair_from,
                                                                int pair_red, float* __restrict__ dtable,
                                                                float* __restrict__ dx,
-                                                               const float* __restrict__ jac) {
+                                                               const float* __restrict__ jac, int jac_from) {
   extern __shared__ float4 smem4[];
   float* tile = reinterpret_cast<float*>(smem4);
   const int tid = threadIdx.x, lane = tid & 31, kTile = blockDim.x;
@@ -213,6 +216,35 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
   __syncthreads();
   const int rowmod = row_t % L;
   float dx0 = 0.f, dx1 = 0.f, dx2 = 0.f;
+  // dL/dx of the levels whose Jacobian the forward kept: a streaming pre-pass, three levels (9*F independent,
+  // coalesced loads) in flight per thread -- the scatter loop below then has no load to wait for on those levels.
+  if constexpr (NEED_DX && JAC) {
+    constexpr int JB = 3;
+#pragma unroll 1
+    for (int l0 = jac_from; l0 < L; l0 += JB) {
+      float jv[JB][F * 3];
+#pragma unroll
+      for (int b = 0; b < JB; ++b) {
+        const int l = min(l0 + b, L - 1);
+        const float* js = jac + (size_t)l * (F * 3) * N + (valid ? p : 0);
+#pragma unroll
+        for (int q = 0; q < F * 3; ++q) jv[b][q] = __ldg(js + (size_t)q * N);
+      }
+#pragma unroll
+      for (int b = 0; b < JB; ++b) {
+        const int l = l0 + b;
+        if (l < L && valid) {
+          int r = l + rowmod;
+          if (r >= L) r -= L;
+#pragma unroll
+          for (int j = 0; j < F; ++j) {
+            const float gj = tile[(row_t * L + r) * F + j];
+            dx0 += gj * jv[b][j * 3]; dx1 += gj * jv[b][j * 3 + 1]; dx2 += gj * jv[b][j * 3 + 2];
+          }
+        }
+      }
+    }
+  }
   // One level per iteration.  (Prefetching the next level's corner rows one iteration ahead -- 16 gathers in flight --
   // was measured and lost, DESIGN.md "experiments that lost".)
 #pragma unroll 1
@@ -227,18 +259,13 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
     const float mx = 1.f - c.ox, my = 1.f - c.oy, mz = 1.f - c.oz;
     float gc[8][F];
     float f[8][F];
-    float jv[F * 3];
-    if constexpr (NEED_DX && JAC) {  // the forward's Jacobian of this level: one coalesced 12*F-byte read
-      const float* js = jac + ((size_t)l * N + (valid ? p : 0)) * (F * 3);
-#pragma unroll
-      for (int q = 0; q < F * 3; ++q) jv[q] = __ldg(js + q);
-    }
+    const bool use_jac = JAC && l >= jac_from;  // warp-uniform: this level's dL/dx came from the forward's Jacobian
     const bool odd = lane & 1;
     PairRows pr;
     if (pair_red || l >= pair_from) pr = exchange_rows(c, odd);  // (warp-uniform conditions)
     // The gathers (for dL/dx) are issued first and consumed LAST: the gradient scatter below -- corner weights,
     // warp aggregation, REDs -- does not depend on them and runs while they are in flight.
-    if constexpr (NEED_DX && !JAC) {
+    if (NEED_DX && !use_jac) {
       if (l >= pair_from) {
         load_cell_paired_issue<F, HALF>(table, c, pr, odd, f);
       } else {
@@ -270,13 +297,8 @@ __global__ void __launch_bounds__(kMaxTile, 3) hash_bwd_kernel(const float* __re
       for (int k = 0; k < 8; ++k) red_row<F>(dtable, c.idx[k], gc[k]);
     }
     // ---- dL/dx of this level
-    if constexpr (NEED_DX && JAC) {
-      float dox = 0.f, doy = 0.f, doz = 0.f;
-#pragma unroll
-      for (int j = 0; j < F; ++j) {
-        dox += g[j] * jv[j * 3]; doy += g[j] * jv[j * 3 + 1]; doz += g[j] * jv[j * 3 + 2];
-      }
-      dx0 += dox; dx1 += doy; dx2 += doz;  // the stored Jacobian carries the level scale
+    if (NEED_DX && use_jac) {
+      // (pre-pass above)
     } else if constexpr (NEED_DX) {
       if (l >= pair_from) {
         float ff[8][F];
@@ -342,23 +364,33 @@ static int pair_from_level(const LevelScales& sc, int L) {
   return (l + kLevelBatch - 1) / kLevelBatch * kLevelBatch;
 }
 
+// first level whose Jacobian the forward keeps for the backward (levels below it are gathered again: coarse cells
+// are shared by many lanes, their gathers are cheap)
+static int jac_from_level(const LevelScales& sc, int L) {
+  const float thr = jac_threshold_enc();
+  int l = 0;
+  while (l < L && sc.s[l] < thr) ++l;
+  return l;
+}
+
 template <int F>
 static int launch_fwd(const float* x, const void* table, int table_dtype, const LevelScales& sc, int64_t N, int L,
                       int log2_T, int samples_per_ray, float* out, int32_t* idx_out, float* jac, cudaStream_t st) {
   const TileShape ts = tile_shape(N, samples_per_ray);
-  const int pair_from = pair_from_level(sc, L);
+  const int pair_from = pair_from_level(sc, L), jac_from = jac_from_level(sc, L);
   const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
   const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_FWD(H, W)                                                                                         \
   do {                                                                                                       \
     auto k = hash_fwd_kernel<F, H, W>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, idx_out, jac);  \
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, idx_out, jac,   \
+                                      jac_from);                                                            \
   } while (0)
   if (jac) {  // (no index dump on this path: checked by the caller)
     auto k = table_dtype == 0 ? hash_fwd_kernel<F, false, false, true> : hash_fwd_kernel<F, true, false, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, nullptr, jac);
+    k<<<grid, ts.threads, smem, st>>>(x, table, sc, N, L, log2_T, ts.patch_S, pair_from, out, nullptr, jac, jac_from);
   } else if (table_dtype == 0) {
     if (idx_out) TN_FWD(false, true); else TN_FWD(false, false);
   } else {
@@ -373,7 +405,7 @@ static int launch_bwd(const float* x, const void* table, int table_dtype, const 
                       int64_t N, int L, int log2_T, int n_agg, int samples_per_ray, float* dtable, float* dx,
                       const float* jac, cudaStream_t st) {
   const TileShape ts = tile_shape(N, samples_per_ray);
-  const int pair_from = pair_from_level(sc, L), pair_red = pair_reds();
+  const int pair_from = pair_from_level(sc, L), pair_red = pair_reds(), jac_from = jac_from_level(sc, L);
   const unsigned grid = (unsigned)((N + ts.threads - 1) / ts.threads);
   const size_t smem = (size_t)ts.threads * L * F * sizeof(float);
 #define TN_BWD(H, D)                                                                                         \
@@ -381,13 +413,13 @@ static int launch_bwd(const float* x, const void* table, int table_dtype, const 
     auto k = hash_bwd_kernel<F, H, D>;                                                                       \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, pair_from, pair_red, \
-                                      dtable, dx, jac);                                                      \
+                                      dtable, dx, jac, jac_from);                                            \
   } while (0)
   if (jac && dx) {
     auto k = table_dtype == 0 ? hash_bwd_kernel<F, false, true, true> : hash_bwd_kernel<F, true, true, true>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k<<<grid, ts.threads, smem, st>>>(x, table, sc, dy, N, L, log2_T, n_agg, ts.patch_S, pair_from, pair_red, dtable,
-                                      dx, jac);
+                                      dx, jac, jac_from);
   } else if (table_dtype == 0) {
     if (dx) TN_BWD(false, true); else TN_BWD(false, false);
   } else {

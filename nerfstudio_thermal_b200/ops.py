@@ -54,9 +54,11 @@ def hash_encode_indices(x: Tensor, spec: HashGridSpec) -> Tensor:
     return idx
 
 
-# Encode forward keeps d(features)/dx for the backward (no second corner gather there).  Measured: backward 0.638 ->
-# 0.561 ms/step but forward 0.283 -> 0.400 (the 75 MB Jacobian write per call), net -1.4 % => off by default.
-SAVE_JACOBIAN = os.environ.get("TN_SAVE_JAC", "0") == "1"
+# Encode forward keeps d(features)/dx of the FINE levels (scale >= 400: 6 of the 16 main-grid levels) in planar form
+# for the backward, whose dL/dx of those levels becomes a streaming pre-pass instead of 8 latency-exposed gathers
+# per level.  Measured (round 2, profiles/r02_jacobian.txt): backward 0.490 -> 0.445 ms/step, forward 0.231 -> 0.264,
+# step 2.13 -> 2.07 ms.  (Round 1's all-levels, interleaved version lost: 75 MB of badly coalesced stores per call.)
+SAVE_JACOBIAN = os.environ.get("TN_SAVE_JAC", "1") == "1"
 
 
 class _HashEncodeFn(torch.autograd.Function):
@@ -70,7 +72,7 @@ class _HashEncodeFn(torch.autograd.Function):
         # streamed) so that the backward does not gather the corner rows a second time
         jac = None
         if SAVE_JACOBIAN and ctx.needs_input_grad[0]:
-            jac = torch.empty((spec.num_levels, n, spec.features, 3), device=x.device)
+            jac = torch.empty((spec.num_levels, spec.features * 3, n), device=x.device)  # only the fine levels are touched
         call("tn_hash_encode_fwd", ptr(x), ptr(src), dtype, spec._c_scales, n, spec.num_levels, spec.features,
              spec.log2_T, samples_per_ray, ptr(out), None, ptr(jac), stream(),
              tag=f"[L{spec.num_levels},T2^{spec.log2_T}{',jac' if jac is not None else ''}]", units=n)
