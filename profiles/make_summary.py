@@ -1,7 +1,9 @@
-"""Regenerate profiles/r01_ncu_summary.md from the committed ncu exports (profiles/r01_*_ncu_raw.csv, r01_launches.csv).
+"""Regenerate a round's ncu summary from the committed ncu exports (profiles/<tag>_*_ncu_raw.csv, <tag>_launches.csv).
 
-    python profiles/make_summary.py > profiles/r01_ncu_summary.md
+    python profiles/make_summary.py            > profiles/r01_ncu_summary.md
+    python profiles/make_summary.py r02f profiles/r02_preface.md > profiles/r02_ncu_summary.md
 """
+import sys
 import collections
 import csv
 import glob
@@ -53,10 +55,11 @@ def launch_table(path):
 
 
 if __name__ == "__main__":
-    print(PREFACE)
-    print(launch_table(os.path.join(HERE, "r01_launches.csv")))
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    print(open(sys.argv[2]).read() if len(sys.argv) > 2 else PREFACE)
+    print(launch_table(os.path.join(HERE, f"{tag}_launches.csv")))
     print()
-    for path in sorted(glob.glob(os.path.join(HERE, "r01_*_ncu_raw.csv"))):
+    for path in sorted(glob.glob(os.path.join(HERE, f"{tag}_*_ncu_raw.csv"))):
         rows = summarize.load(path)
         cols = ["kernel"] + [s for _, s in summarize.KEEP if any(s in r for r in rows)]
         print(f"## {os.path.basename(path)}")

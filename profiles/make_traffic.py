@@ -20,7 +20,8 @@ def tag_of(name, row):
     if "hash_bwd_kernel<2, 0, 1" in name or "hash_bwd_kernel<(int)2, (bool)0, (bool)1" in name:
         return "tn_hash_encode_bwd[L16,T2^19,dx]"
     if "hash_fwd_kernel<2, 0, 0" in name or "hash_fwd_kernel<(int)2, (bool)0, (bool)0" in name:
-        return "tn_hash_encode_fwd[L16,T2^19]"
+        jac = "hash_fwd_kernel<2, 0, 0, 1>" in name or "(bool)0, (bool)0, (bool)1>" in name
+        return "tn_hash_encode_fwd[L16,T2^19,jac]" if jac else "tn_hash_encode_fwd[L16,T2^19]"
     if "prop_bwd_kernel" in name:
         return "tn_prop_density_bwd[L5,S256,dx]" if row["insts"] > 8e7 else "tn_prop_density_bwd[L5,S96,dx]"
     if "prop_fwd_kernel" in name:
@@ -51,7 +52,7 @@ def main(paths):
             tag = tag_of(r[idx["Kernel Name"]], d)
             if tag:
                 acc.setdefault(tag, []).append(d)
-    out = {"_source": "ncu --set full --clock-control none, one eager train step (profiles/capture_r02.sh); "
+    out = {"_source": "ncu --set full --clock-control none, one eager train step of the round's final code (profiles/capture_r02.sh, r02f_*); "
                       "per launch, averaged over the captured launches of the tag", "_detail": {}}
     for tag, ds in sorted(acc.items()):
         n = len(ds)

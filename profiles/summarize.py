@@ -18,6 +18,9 @@ KEEP = [
     ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1_pct"),
     ("l1tex__t_sector_hit_rate.pct", "l1_hit_pct"),
     ("lts__t_sectors_op_red.sum", "l2_red_sectors"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1_ld_sectors"),
+    ("l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum", "l1_red_sectors"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_wavefronts_pct"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
     ("sm__inst_executed_pipe_tensor.sum", "tensor_inst"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
