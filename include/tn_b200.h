@@ -75,11 +75,12 @@ int tn_hash_encode_bwd(const float* x, const void* table, int table_dtype, const
  * ------------------------------------------------------------------------------------------------ */
 int tn_sample_positions_fwd(const float* origins, const float* directions, const float* ebins, int64_t R,
                             int S, float* x_out, float* selector_out, void* stream);
-/* dx[R*S,3] -> d_origins[R,3], d_directions[R,3] (overwritten).  Bins carry no gradient
- * (model_components/ray_samplers.py:360). */
+/* dx[R*S,3] -> d_origins[R,3], d_directions[R,3]: overwritten, or added onto when accumulate != 0 (the
+ * gradients of a ray bundle's other consumers are then chained through one buffer instead of being summed by
+ * autograd).  Bins carry no gradient (model_components/ray_samplers.py:360). */
 int tn_sample_positions_bwd(const float* origins, const float* directions, const float* ebins,
-                            const float* dx, int64_t R, int S, float* d_origins, float* d_directions,
-                            void* stream);
+                            const float* dx, int64_t R, int S, int accumulate, float* d_origins,
+                            float* d_directions, void* stream);
 /* The same normalisation for free-standing points p[N,3] (Field.density_fn, fields/base_field.py:48-69). */
 int tn_contract_points_fwd(const float* p, int64_t N, float* x_out, float* selector_out, void* stream);
 int tn_contract_points_bwd(const float* p, const float* dx, int64_t N, float* dp, void* stream);
@@ -126,6 +127,12 @@ int tn_mlp_tc_bwd(const float* x, const float* dy, const uint32_t* relu_mask, in
 /* Real spherical-harmonics basis, 4 levels (16 components).
  *   replaces: utils/math.py:29-95 via field_components/encodings.py:792-795.  d[N,3] -> out[N,16]. */
 int tn_sh4(const float* d, int64_t N, float* out, void* stream);
+/* The per-ray inputs of a NerfactoField's colour head in one launch.
+ *   replaces: fields/base_field.py:136-142 (get_normalized_directions) + encodings.py:792-795 (SH of (d+1)/2) +
+ *   field_components/embedding.py:48-55 (appearance embedding of the ray's camera; fields/nerfacto_field.py:284-290).
+ * directions[R,3] -> sh_out[R,16]; emb_out (may be NULL) [R,emb_dim] = embedding[camera_indices[r]]. */
+int tn_ray_features(const float* directions, const float* embedding, const int64_t* camera_indices, int64_t R,
+                    int emb_dim, float* sh_out, float* emb_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Samplers.
@@ -272,20 +279,29 @@ int tn_camera_opt_bwd(const float* pose, const uint8_t* frozen, const int64_t* c
 int tn_pixel_losses(const float* rgb, const float* thermal, const float* image, const float* is_thermal, int64_t R,
                     const float* upstream, float* losses_out, float* d_rgb_out, float* d_thermal_out, void* stream);
 /* replaces: models/thermal_nerfacto.py:328-344 (cross-field density L1 with its stop-gradient pattern).
- * d, d2, dt, d2t [N].  partial_out[n_partial]: per-CTA partial sums of value_mult * (mean|d2-dt| + mean|d-d2t|).
- * Gradients (all four or none): g_dt = -thermal_grad_mult*sgn(d2-dt)/N, g_d2t = -thermal_grad_mult*sgn(d-d2t)/N,
- * g_d2 = rgb_grad_mult*sgn(d2-dt)/N, g_d = rgb_grad_mult*sgn(d-d2t)/N. */
+ * d, d2, dt, d2t [N].  partial_out (may be NULL when only gradients are wanted) [n_partial + 1]: per-CTA partial sums
+ * of value_mult * (mean|d2-dt| + mean|d-d2t|); with `ticket` (a zero-initialised uint32 the caller owns; re-armed by
+ * the kernel) the CTA that finishes last also writes their sum, in index order, to partial_out[n_partial].
+ * Gradients (all four or none), times upstream_dev[0] when given: g_dt = -thermal_grad_mult*sgn(d2-dt)/N,
+ * g_d2t = -thermal_grad_mult*sgn(d-d2t)/N, g_d2 = rgb_grad_mult*sgn(d2-dt)/N, g_d = rgb_grad_mult*sgn(d-d2t)/N. */
 int tn_density_l1(const float* d, const float* d2, const float* dt, const float* d2t, int64_t N, float value_mult,
-                  float thermal_grad_mult, float rgb_grad_mult, float* partial_out, int n_partial, float* g_d,
-                  float* g_d2, float* g_dt, float* g_d2t, void* stream);
+                  float thermal_grad_mult, float rgb_grad_mult, const float* upstream_dev, float* partial_out,
+                  int n_partial, uint32_t* ticket, float* g_d, float* g_d2, float* g_dt, float* g_d2t, void* stream);
 /* replaces: cameras/camera_optimizers.py:188-194 (get_loss_dict) and :200-204 (get_metrics_dict).  pose[num_cameras,6].
  * out3 = {(mean|t_i| * trans_penalty + mean|w_i| * rot_penalty) * penalty_scale, |T|_F, |W|_F}. */
 int tn_camera_reg_fwd(const float* pose, int num_cameras, float trans_penalty, float rot_penalty,
                       float penalty_scale, float* out3, void* stream);
-/* dpose_out[num_cameras,6] (overwritten) = upstream_dev[0] * d out3[0] / d pose (zero rows where a norm is zero,
- * as torch's norm backward). */
+/* dpose_out[num_cameras,6] (overwritten; atomically added onto when accumulate != 0) = upstream_dev[0] * d out3[0] /
+ * d pose (zero rows where a norm is zero, as torch's norm backward). */
 int tn_camera_reg_bwd(const float* pose, const float* upstream_dev, int num_cameras, float trans_penalty,
-                      float rot_penalty, float penalty_scale, float* dpose_out, void* stream);
+                      float rot_penalty, float penalty_scale, int accumulate, float* dpose_out, void* stream);
+/* Gradient of the appearance embedding (field_components/embedding.py:48-55 under autograd) from the colour head's
+ * per-ray first-layer gradient dz1_ray[R,width] (tn_field_head_bwd):
+ *   dweight[camera_indices[r], j] += sum_k dz1_ray[r,k] * w0[k, col0 + j],  j < emb_dim,
+ * w0[width,in_dim] = the head's first nn.Linear weight, col0 = the embedding's first input column.  clear != 0: the
+ * rows of dz1_ray are zeroed after use (a buffer that tn_field_head_bwd accumulates into stays clean between steps). */
+int tn_embed_bwd(float* dz1_ray, const float* w0, const int64_t* camera_indices, int64_t R, int width, int in_dim,
+                 int col0, int emb_dim, int clear, float* dweight, void* stream);
 /* replaces: the loss-dictionary arithmetic of models/thermal_nerfacto.py:284-388 + engine/trainer.py:479
  * (`functools.reduce(torch.add, loss_dict.values())`).  term_host_ptrs[k]: device pointer of scalar term k, which
  * belongs to dictionary entry slot_host[k] in [0, n_slots);
@@ -373,13 +389,19 @@ int tn_level_resample(const float* sigma, const float* ebins, const float* sbins
  * prop_sbins[q][R,S_q+1]).  loss_acc: NULL (no losses), or float[2] ACCUMULATED into: [0] += sum over rays of
  * lossfun_distortion, [1] += sum over rays, levels and fine samples of lossfun_outer (the caller zero-fills and
  * divides by R resp. R*S).  dw_distortion_out[R,S] / prop_dw[q][R,S_q]: NULL, or the gradients of those two sums
- * w.r.t. the final / proposal weights, kept for tn_ray_heads_bwd. */
+ * w.r.t. the final / proposal weights, kept for tn_ray_heads_bwd.
+ * scratch5 (may be NULL): five 4-byte words {+inf, -inf, 0, 0, 0u} owned by the caller and never used by two launches at
+ * a time.  When given, the launch-wide atomics go THERE, and the CTA that finishes last writes the final values --
+ * steps_minmax_out = (min, max), loss_acc = (distortion sum * loss_scale_distortion, interlevel sum *
+ * loss_scale_interlevel), depth_expected_clipped_out[R] = clamp(depth_expected_out, min, max) (renderers.py:574) --
+ * and puts the scratch back into its initial state: no initialisation, scaling or clamp launches around the call. */
 int tn_ray_heads_fwd(const float* sigma, const float* colour, const float* ebins, const float* sbins, int64_t R,
                      int S, int C, int bg_mode, const float* bg_host, int eval_mode, int n_prop,
                      const float* const* prop_w_host_ptrs, const float* const* prop_sbins_host_ptrs,
                      const int* prop_S_host, float* const* prop_dw_host_ptrs, float* weights_out, float* rgb_out,
                      float* acc_out, float* depth_median_out, float* depth_expected_out, float* steps_minmax_out,
-                     float* loss_acc, float* dw_distortion_out, void* stream);
+                     float* loss_acc, float* dw_distortion_out, float* scratch5, float loss_scale_distortion,
+                     float loss_scale_interlevel, float* depth_expected_clipped_out, void* stream);
 /* The ray-level backward of a whole branch in one launch.  Final level: d_rgb[R,C], d_acc[R], d_depth_expected[R]
  * (each may be NULL) and g_distortion_dev (device scalar dL/d(mean distortion), NULL = 0) times dw_distortion ->
  * get_weights backward -> dsigma_out[R,S], dcolour_out[R,S,C] (NULL: not wanted).  Proposal level q:

@@ -33,7 +33,7 @@ _SIGNATURES = {
     "tn_hash_encode_fwd": [_P, _P, c_int, POINTER(c_float), c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tn_hash_encode_bwd": [_P, _P, c_int, POINTER(c_float), _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "tn_sample_positions_fwd": [_P, _P, _P, c_int64, c_int, _P, _P, _P],
-    "tn_sample_positions_bwd": [_P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
+    "tn_sample_positions_bwd": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
     "tn_contract_points_fwd": [_P, c_int64, _P, _P, _P],
     "tn_contract_points_bwd": [_P, _P, c_int64, _P, _P],
     "tn_mlp_fwd": [_P, c_int64, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, _P],
@@ -42,6 +42,7 @@ _SIGNATURES = {
     "tn_mlp_tc_bwd": [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _FPP, _FPP, c_int, _P, c_float, _P, _FPP,
                       _FPP, _P],
     "tn_sh4": [_P, c_int64, _P, _P],
+    "tn_ray_features": [_P, _P, _P, c_int64, c_int, _P, _P, _P],
     "tn_piecewise_bins": [_P, _P, _P, _P, c_int, c_int64, c_int, _P, _P, _P],
     "tn_pdf_sample": [_P, _P, _P, _P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P],
     "tn_weights_fwd": [_P, _P, c_int64, c_int, _P, _P],
@@ -59,14 +60,15 @@ _SIGNATURES = {
     "tn_camera_opt_fwd": [_P, _P, _P, _P, _P, c_int64, c_int, _P, _P, _P],
     "tn_camera_opt_bwd": [_P, _P, _P, _P, _P, _P, c_int64, c_int, _P, _P],
     "tn_pixel_losses": [_P, _P, _P, _P, c_int64, _P, _P, _P, _P, _P],
-    "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, c_int, _P, _P, _P, _P, _P],
+    "tn_density_l1": [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P],
     "tn_distortion_loss": [_P, _P, c_int64, c_int, _P, _P, _P],
     "tn_interlevel_loss": [_P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P],
     "tn_field_head_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_float, _FPP, _FPP, c_int, _P, _P, _P, _P],
     "tn_field_head_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_float, _FPP, _FPP, c_int, _P, _P, _FPP,
                           _FPP, _P],
     "tn_camera_reg_fwd": [_P, c_int, c_float, c_float, c_float, _P, _P],
-    "tn_camera_reg_bwd": [_P, _P, c_int, c_float, c_float, c_float, _P, _P],
+    "tn_camera_reg_bwd": [_P, _P, c_int, c_float, c_float, c_float, c_int, _P, _P],
+    "tn_embed_bwd": [_P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P, _P],
     "tn_loss_sum": [_FPP, POINTER(c_float), POINTER(c_int), c_int, c_int, _P, _P],
     "tn_patch_pixel_indices": [_P, c_int64, c_int, c_int, c_int, c_int, _P, _P],
     "tn_gather_pixels": [_P, c_int, c_int64, c_int, c_int, c_int, _P, _P, _P, c_int64, _P, _P, _P],
@@ -79,7 +81,7 @@ _SIGNATURES = {
     "tn_level_resample": [_P, _P, _P, _P, _P, _P, _P, c_int, _P, c_int64, c_int, c_int, c_float, c_float, _P, _P, _P, _P,
                           _P],
     "tn_ray_heads_fwd": [_P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int, c_int, _FPP, _FPP,
-                         POINTER(c_int), _FPP, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+                         POINTER(c_int), _FPP, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_float, c_float, _P, _P],
     "tn_ray_heads_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, POINTER(c_float), c_int,
                          _FPP, _FPP, _FPP, POINTER(c_int), _P, _P, _FPP, _P],
     "tn_shard_mean": [_P, _P, c_int, c_int64, c_int64, c_float, c_int, _P],

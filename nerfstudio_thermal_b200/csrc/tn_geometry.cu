@@ -24,7 +24,8 @@ __global__ void sample_positions_fwd_kernel(const float* __restrict__ o, const f
 // one warp per ray: reduce the per-sample position gradients into d_origin / d_direction
 __global__ void sample_positions_bwd_kernel(const float* __restrict__ o, const float* __restrict__ d,
                                             const float* __restrict__ ebins, const float* __restrict__ dx, int64_t R,
-                                            int S, float* __restrict__ dorig, float* __restrict__ ddir) {
+                                            int S, int accumulate, float* __restrict__ dorig,
+                                            float* __restrict__ ddir) {
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= R) return;
@@ -44,6 +45,10 @@ __global__ void sample_positions_bwd_kernel(const float* __restrict__ o, const f
   ao0 = warp_sum(ao0); ao1 = warp_sum(ao1); ao2 = warp_sum(ao2);
   ad0 = warp_sum(ad0); ad1 = warp_sum(ad1); ad2 = warp_sum(ad2);
   if (lane == 0) {
+    if (accumulate) {  // one warp owns the ray: plain read-modify-write onto the gradient the caller already holds
+      ao0 += dorig[3 * r]; ao1 += dorig[3 * r + 1]; ao2 += dorig[3 * r + 2];
+      ad0 += ddir[3 * r]; ad1 += ddir[3 * r + 1]; ad2 += ddir[3 * r + 2];
+    }
     dorig[3 * r] = ao0; dorig[3 * r + 1] = ao1; dorig[3 * r + 2] = ao2;
     ddir[3 * r] = ad0; ddir[3 * r + 1] = ad1; ddir[3 * r + 2] = ad2;
   }
@@ -69,12 +74,8 @@ __global__ void contract_points_bwd_kernel(const float* __restrict__ p, const fl
 }
 
 // utils/math.py:29-95, levels = 4
-__global__ void sh4_kernel(const float* __restrict__ d, int64_t N, float* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const float x = __ldg(d + 3 * i), y = __ldg(d + 3 * i + 1), z = __ldg(d + 3 * i + 2);
+__device__ __forceinline__ void sh4_components(float x, float y, float z, float* c) {
   const float xx = x * x, yy = y * y, zz = z * z;
-  float c[16];
   c[0] = 0.28209479177387814f;
   c[1] = 0.4886025119029199f * y;
   c[2] = 0.4886025119029199f * z;
@@ -91,11 +92,40 @@ __global__ void sh4_kernel(const float* __restrict__ d, int64_t N, float* __rest
   c[13] = 0.4570457994644658f * x * (5.f * zz - 1.f);
   c[14] = 1.445305721320277f * z * (xx - yy);
   c[15] = 0.5900435899266435f * x * (xx - 3.f * yy);
+}
+
+__global__ void sh4_kernel(const float* __restrict__ d, int64_t N, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float x = __ldg(d + 3 * i), y = __ldg(d + 3 * i + 1), z = __ldg(d + 3 * i + 2);
+  float c[16];
+  sh4_components(x, y, z, c);
   float4* o4 = reinterpret_cast<float4*>(out + 16 * i);
 #pragma unroll
   for (int k = 0; k < 4; ++k) o4[k] = make_float4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
 }
 
+
+// Per-ray inputs of a NerfactoField's colour head in ONE launch (fields/nerfacto_field.py:284-290, 335-344):
+// SH basis of the normalised directions (d+1)/2 (fields/base_field.py:136-142: the add and the divide round like the
+// reference's two torch ops) and the appearance-embedding row of the ray's camera (field_components/embedding.py:48-55).
+__global__ void ray_features_kernel(const float* __restrict__ d, const float* __restrict__ emb,
+                                    const int64_t* __restrict__ cam, int64_t R, int E, float* __restrict__ sh_out,
+                                    float* __restrict__ emb_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const float x = (__ldg(d + 3 * i) + 1.0f) / 2.0f, y = (__ldg(d + 3 * i + 1) + 1.0f) / 2.0f,
+              z = (__ldg(d + 3 * i + 2) + 1.0f) / 2.0f;
+  float c[16];
+  sh4_components(x, y, z, c);
+  float4* o4 = reinterpret_cast<float4*>(sh_out + 16 * i);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) o4[k] = make_float4(c[4 * k], c[4 * k + 1], c[4 * k + 2], c[4 * k + 3]);
+  if (emb_out) {
+    const float* row = emb + cam[i] * E;
+    for (int k = 0; k < E; ++k) emb_out[i * E + k] = __ldg(row + k);
+  }
+}
 // UniformLinDispPiecewiseSampler spacing (model_components/ray_samplers.py:244-245)
 __device__ __forceinline__ float spacing_fn(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
 __device__ __forceinline__ float spacing_inv(float y) { return y < 0.5f ? 2.f * y : 1.f / (2.f - 2.f * y); }
@@ -222,14 +252,15 @@ extern "C" int tn_sample_positions_fwd(const float* origins, const float* direct
 }
 
 extern "C" int tn_sample_positions_bwd(const float* origins, const float* directions, const float* ebins,
-                                       const float* dx, int64_t R, int S, float* d_origins, float* d_directions,
-                                       void* stream) {
+                                       const float* dx, int64_t R, int S, int accumulate, float* d_origins,
+                                       float* d_directions, void* stream) {
   TN_REQUIRE(origins && directions && ebins && dx && d_origins && d_directions, TN_EINVAL,
              "sample_positions_bwd: null pointer");
   TN_REQUIRE(R >= 0 && S >= 1, TN_EINVAL, "sample_positions_bwd: bad R=%lld S=%d", (long long)R, S);
   if (R == 0) return TN_OK;
   sample_positions_bwd_kernel<<<blocks_for(R * 32, 128), 128, 0, (cudaStream_t)stream>>>(origins, directions, ebins, dx,
-                                                                                        R, S, d_origins, d_directions);
+                                                                                        R, S, accumulate, d_origins,
+                                                                                        d_directions);
   return check_launch("sample_positions_bwd_kernel");
 }
 
@@ -253,6 +284,17 @@ extern "C" int tn_sh4(const float* d, int64_t N, float* out, void* stream) {
   if (N <= 0) return N == 0 ? TN_OK : TN_EINVAL;
   sh4_kernel<<<blocks_for(N, 256), 256, 0, (cudaStream_t)stream>>>(d, N, out);
   return check_launch("sh4_kernel");
+}
+
+extern "C" int tn_ray_features(const float* directions, const float* embedding, const int64_t* camera_indices,
+                               int64_t R, int emb_dim, float* sh_out, float* emb_out, void* stream) {
+  TN_REQUIRE(directions && sh_out, TN_EINVAL, "ray_features: null pointer");
+  TN_REQUIRE(!emb_out || (embedding && camera_indices && emb_dim >= 1), TN_EINVAL,
+             "ray_features: emb_out needs the embedding table, the camera indices and emb_dim >= 1");
+  if (R <= 0) return R == 0 ? TN_OK : TN_EINVAL;
+  ray_features_kernel<<<blocks_for(R, 128), 128, 0, (cudaStream_t)stream>>>(directions, embedding, camera_indices, R,
+                                                                            emb_dim, sh_out, emb_out);
+  return check_launch("ray_features_kernel");
 }
 
 extern "C" int tn_piecewise_bins(const float* unit_bins, const float* nears, const float* fars, const float* jitter,

@@ -218,6 +218,11 @@ struct HeadsFwdArgs {
   float* minmax;     // [2]
   float* loss_acc;   // [2]: += sum over rays of the distortion loss, += sum of the interlevel loss terms (NULL: skip)
   float* dw_dist;    // [R,S] d(distortion of this ray) / d w (NULL: not wanted)
+  // self-resetting launch scratch {min, max, dist sum, inter sum, ticket}: when given, the atomics go there and the
+  // CTA that finishes last writes the FINAL minmax / scaled losses / clipped expected depth and re-arms the scratch
+  float* scratch;
+  float* exp_clip_out;  // [R] expected depth after the launch-wide clip (renderers.py:574)
+  float scale_dist, scale_inter;
 };
 
 // smem per warp: sw[S] | su[S] | (interlevel) cy[Sp+1] | edges[Sp+1] | diff[Sp+1]
@@ -232,6 +237,8 @@ __global__ void __launch_bounds__(32 * kLevelWarps) ray_heads_fwd_kernel(const H
   const int64_t r = (int64_t)blockIdx.x * kLevelWarps + warp;
   const int S = a.S;
   float dist_ray = 0.f, inter_ray = 0.f;
+  float* const mm = a.minmax ? (a.scratch ? a.scratch : a.minmax) : nullptr;          // atomics' targets
+  float* const lacc = a.loss_acc ? (a.scratch ? a.scratch + 2 : a.loss_acc) : nullptr;
   if (r < a.R) {
     const float* eb = a.ebins + r * (S + 1);
     const float* sb = a.sbins + r * (S + 1);
@@ -297,16 +304,16 @@ __global__ void __launch_bounds__(32 * kLevelWarps) ray_heads_fwd_kernel(const H
         a.med_out[r] = (__ldg(eb + idx) + __ldg(eb + idx + 1)) / 2.f;
       }
       if (a.exp_out) a.exp_out[r] = num / (acc + 1e-10f);
-      if (a.minmax) {  // launch-wide extrema of the sample midpoints (renderers.py:574 clips with them)
-        const float cur_min = *reinterpret_cast<volatile float*>(a.minmax);
-        const float cur_max = *reinterpret_cast<volatile float*>(a.minmax + 1);
+      if (mm) {  // launch-wide extrema of the sample midpoints (renderers.py:574 clips with them)
+        const float cur_min = *reinterpret_cast<volatile float*>(mm);
+        const float cur_max = *reinterpret_cast<volatile float*>(mm + 1);
         if (smin < cur_min) {
-          atomicMin(reinterpret_cast<int*>(a.minmax), smin >= 0.f ? __float_as_int(smin) : (int)0x80000000);
-          if (smin < 0.f) atomicMax(reinterpret_cast<unsigned*>(a.minmax), __float_as_uint(smin));
+          atomicMin(reinterpret_cast<int*>(mm), smin >= 0.f ? __float_as_int(smin) : (int)0x80000000);
+          if (smin < 0.f) atomicMax(reinterpret_cast<unsigned*>(mm), __float_as_uint(smin));
         }
         if (smax > cur_max) {
-          if (smax >= 0.f) atomicMax(reinterpret_cast<int*>(a.minmax + 1), __float_as_int(smax));
-          else atomicMin(reinterpret_cast<unsigned*>(a.minmax + 1), __float_as_uint(smax));
+          if (smax >= 0.f) atomicMax(reinterpret_cast<int*>(mm + 1), __float_as_int(smax));
+          else atomicMin(reinterpret_cast<unsigned*>(mm + 1), __float_as_uint(smax));
         }
       }
     }
@@ -399,7 +406,38 @@ __global__ void __launch_bounds__(32 * kLevelWarps) ray_heads_fwd_kernel(const H
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < kLevelWarps; ++w) t += cta_loss[threadIdx.x][w];
-      atomicAdd(a.loss_acc + threadIdx.x, t);
+      atomicAdd(lacc + threadIdx.x, t);
+    }
+  }
+  if (a.scratch) {
+    // The CTA that takes the last ticket sees every other CTA's atomics and stores (fence before the ticket): it turns
+    // the launch-wide accumulators into the final outputs -- what used to be a clone, a multiply and a clamp launch.
+    __shared__ bool last_cta;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      last_cta = atomicAdd(reinterpret_cast<unsigned*>(a.scratch + 4), 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last_cta) {
+      __threadfence();
+      const float mn = __ldcg(a.scratch), mx = __ldcg(a.scratch + 1);
+      __syncthreads();  // every thread holds the extrema before thread 0 re-arms the scratch
+      if (a.exp_clip_out && a.exp_out && a.minmax) {
+        for (int64_t i = threadIdx.x; i < a.R; i += blockDim.x) {
+          const float v = __ldcg(a.exp_out + i);
+          a.exp_clip_out[i] = v < mn ? mn : (v > mx ? mx : v);  // torch.clamp: NaN stays NaN
+        }
+      }
+      if (threadIdx.x == 0) {
+        if (a.minmax) { a.minmax[0] = mn; a.minmax[1] = mx; }
+        if (a.loss_acc) {
+          a.loss_acc[0] = __ldcg(a.scratch + 2) * a.scale_dist;
+          a.loss_acc[1] = __ldcg(a.scratch + 3) * a.scale_inter;
+        }
+        a.scratch[0] = CUDART_INF_F; a.scratch[1] = -CUDART_INF_F; a.scratch[2] = 0.f; a.scratch[3] = 0.f;
+        reinterpret_cast<unsigned*>(a.scratch)[4] = 0u;
+      }
     }
   }
 }
@@ -532,8 +570,12 @@ extern "C" int tn_ray_heads_fwd(const float* sigma, const float* colour, const f
                                 const float* const* prop_w_host_ptrs, const float* const* prop_sbins_host_ptrs,
                                 const int* prop_S_host, float* const* prop_dw_host_ptrs, float* weights_out,
                                 float* rgb_out, float* acc_out, float* depth_median_out, float* depth_expected_out,
-                                float* steps_minmax_out, float* loss_acc, float* dw_distortion_out, void* stream) {
+                                float* steps_minmax_out, float* loss_acc, float* dw_distortion_out, float* scratch5,
+                                float loss_scale_distortion, float loss_scale_interlevel,
+                                float* depth_expected_clipped_out, void* stream) {
   TN_REQUIRE(sigma && ebins && weights_out, TN_EINVAL, "ray_heads_fwd: null pointer");
+  TN_REQUIRE(scratch5 || !depth_expected_clipped_out, TN_EINVAL,
+             "ray_heads_fwd: the clipped expected depth is made by the scratch protocol's last CTA");
   TN_REQUIRE(R >= 0 && S >= 1 && S <= 2048 && C >= 0 && C <= 4, TN_EINVAL, "ray_heads_fwd: bad R=%lld S=%d C=%d",
              (long long)R, S, C);
   TN_REQUIRE(C == 0 || colour, TN_EINVAL, "ray_heads_fwd: colour is null");
@@ -557,6 +599,8 @@ extern "C" int tn_ray_heads_fwd(const float* sigma, const float* colour, const f
   a.smem_floats_per_warp = 2 * S + (n_prop ? 3 * (sp_max + 1) : 0);
   a.w_out = weights_out; a.rgb_out = rgb_out; a.acc_out = acc_out; a.med_out = depth_median_out;
   a.exp_out = depth_expected_out; a.minmax = steps_minmax_out; a.loss_acc = loss_acc; a.dw_dist = dw_distortion_out;
+  a.scratch = scratch5; a.exp_clip_out = depth_expected_clipped_out;
+  a.scale_dist = loss_scale_distortion; a.scale_inter = loss_scale_interlevel;
   const size_t smem = (size_t)kLevelWarps * a.smem_floats_per_warp * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_HF(CC)                                                                                       \

@@ -181,23 +181,26 @@ __global__ void __launch_bounds__(kLossThreads) pixel_losses_kernel(
 // => d(loss)/d(dt) = -m sgn(d2-dt)/N, d/d(d2t) = -m sgn(d-d2t)/N, d/d(d2) = r m sgn(d2-dt)/N, d/d(d) = r m sgn(d-d2t)/N
 __global__ void density_l1_kernel(const float* __restrict__ d, const float* __restrict__ d2, const float* __restrict__ dt,
                                   const float* __restrict__ d2t, int64_t N, float vm, float m, float rm,
-                                  float* __restrict__ partial,
-                                  float* __restrict__ g_d, float* __restrict__ g_d2, float* __restrict__ g_dt,
-                                  float* __restrict__ g_d2t) {
+                                  const float* __restrict__ upstream, float* __restrict__ partial,
+                                  unsigned int* __restrict__ ticket, float* __restrict__ g_d, float* __restrict__ g_d2,
+                                  float* __restrict__ g_dt, float* __restrict__ g_d2t) {
   float acc = 0.f;
   const float invn = 1.f / (float)N;
+  const float up = upstream ? __ldg(upstream) : 1.f;  // gradients = upstream * d(loss)/d(.) (one launch, no scaling pass)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     const float a = d2[i] - dt[i], b = d[i] - d2t[i];
     acc += vm * (fabsf(a) + fabsf(b));
     if (g_d) {
-      g_dt[i] = -m * sgn(a) * invn;
-      g_d2t[i] = -m * sgn(b) * invn;
-      g_d2[i] = rm * sgn(a) * invn;
-      g_d[i] = rm * sgn(b) * invn;
+      g_dt[i] = -m * sgn(a) * invn * up;
+      g_d2t[i] = -m * sgn(b) * invn * up;
+      g_d2[i] = rm * sgn(a) * invn * up;
+      g_d[i] = rm * sgn(b) * invn * up;
     }
   }
+  if (!partial) return;
   acc = warp_sum(acc);
   __shared__ float red[32];
+  __shared__ bool last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) red[warp] = acc;
   __syncthreads();
@@ -205,6 +208,18 @@ __global__ void density_l1_kernel(const float* __restrict__ d, const float* __re
     float v = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) v += red[i];
     partial[blockIdx.x] = v * invn;
+    last = false;
+    if (ticket) {  // the CTA that finishes last adds the partial sums up, in index order (deterministic)
+      __threadfence();
+      last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    if (last) {
+      __threadfence();
+      float t = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(partial + b);
+      partial[gridDim.x] = t;
+      *ticket = 0u;  // ready for the next launch
+    }
   }
 }
 
@@ -235,9 +250,11 @@ __global__ void __launch_bounds__(256) camera_reg_fwd_kernel(const float* __rest
     out[2] = sqrtf(d);
   }
 }
-// dpose[i] (overwritten) = g * scale / C * (trans_pen * t_i/|t_i| , rot_pen * w_i/|w_i|), zero where the norm is zero
+// dpose[i] (overwritten, or atomically added onto) = g * scale / C * (trans_pen * t_i/|t_i| , rot_pen * w_i/|w_i|), zero
+// where the norm is zero
 __global__ void camera_reg_bwd_kernel(const float* __restrict__ pose, const float* __restrict__ g, int C,
-                                      float trans_pen, float rot_pen, float scale, float* __restrict__ dpose) {
+                                      float trans_pen, float rot_pen, float scale, int accumulate,
+                                      float* __restrict__ dpose) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C) return;
   const float* p = pose + 6 * i;
@@ -247,8 +264,55 @@ __global__ void camera_reg_bwd_kernel(const float* __restrict__ pose, const floa
   const float ct = nt > 0.f ? gs * trans_pen / nt : 0.f, cw = nw > 0.f ? gs * rot_pen / nw : 0.f;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
-    dpose[6 * i + k] = ct * p[k];
-    dpose[6 * i + 3 + k] = cw * p[3 + k];
+    if (accumulate) {  // the bundle's pose gradient (camera_opt_bwd_kernel) lands in the same buffer, on another stream
+      atomicAdd(dpose + 6 * i + k, ct * p[k]);
+      atomicAdd(dpose + 6 * i + 3 + k, cw * p[3 + k]);
+    } else {
+      dpose[6 * i + k] = ct * p[k];
+      dpose[6 * i + 3 + k] = cw * p[3 + k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ appearance embedding
+// Gradient of the per-camera appearance embedding from the colour head's per-ray first-layer gradient:
+// d emb[cam[r], j] += sum_k dz1_ray[r, k] * W0[k, col0 + j]  (the [R,64] x [64,E] product and the index_add_ of
+// field_components/embedding.py's autograd in one launch).  A warp owns kRaysPerWarp consecutive rays, lane = j;
+// consecutive rays of a patch-ordered batch share their camera, so the warp adds them up and issues one atomic row per
+// run.  dz1_ray rows are cleared after use when `clear` is set (the caller keeps one self-cleaning buffer).
+constexpr int kEmbRaysPerWarp = 8;
+__global__ void __launch_bounds__(128) embed_bwd_kernel(float* __restrict__ dz1_ray, const float* __restrict__ w0,
+                                                        const int64_t* __restrict__ cam, int64_t R, int width,
+                                                        int in_dim, int col0, int E, int clear,
+                                                        float* __restrict__ dweight) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t r0 = warp * kEmbRaysPerWarp;
+  if (r0 >= R) return;
+  const int64_t r1 = min(r0 + (int64_t)kEmbRaysPerWarp, R);
+  for (int j0 = 0; j0 < E; j0 += 32) {
+    const int j = j0 + lane;
+    float acc = 0.f;
+    int64_t run_cam = cam[r0];
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t c = cam[r];
+      if (c != run_cam) {
+        if (j < E) atomicAdd(dweight + run_cam * E + j, acc);
+        acc = 0.f;
+        run_cam = c;
+      }
+      if (j < E) {
+        const float* z = dz1_ray + r * width;
+        float t = 0.f;
+        for (int k = 0; k < width; ++k) t += z[k] * __ldg(w0 + (int64_t)k * in_dim + col0 + j);
+        acc += t;
+      }
+    }
+    if (j < E) atomicAdd(dweight + run_cam * E + j, acc);
+  }
+  if (clear) {
+    __syncwarp();
+    for (int64_t i = r0 * width + lane; i < r1 * width; i += 32) dz1_ray[i] = 0.f;
   }
 }
 
@@ -312,14 +376,18 @@ extern "C" int tn_pixel_losses(const float* rgb, const float* thermal, const flo
 }
 
 extern "C" int tn_density_l1(const float* d, const float* d2, const float* dt, const float* d2t, int64_t N,
-                             float value_mult, float thermal_grad_mult, float rgb_grad_mult, float* partial_out,
-                             int n_partial, float* g_d, float* g_d2, float* g_dt, float* g_d2t, void* stream) {
-  TN_REQUIRE(d && d2 && dt && d2t && partial_out && n_partial >= 1, TN_EINVAL, "density_l1: null pointer");
+                             float value_mult, float thermal_grad_mult, float rgb_grad_mult, const float* upstream_dev,
+                             float* partial_out, int n_partial, uint32_t* ticket, float* g_d, float* g_d2, float* g_dt,
+                             float* g_d2t, void* stream) {
+  TN_REQUIRE(d && d2 && dt && d2t && n_partial >= 1 && n_partial <= 1024, TN_EINVAL, "density_l1: bad arguments");
+  TN_REQUIRE(partial_out || g_d, TN_EINVAL, "density_l1: nothing to compute");
+  TN_REQUIRE(!ticket || partial_out, TN_EINVAL, "density_l1: a ticket counter without partial_out");
   TN_REQUIRE((g_d != nullptr) == (g_d2 != nullptr) && (g_d != nullptr) == (g_dt != nullptr) &&
                  (g_d != nullptr) == (g_d2t != nullptr), TN_EINVAL, "density_l1: give all four gradient outputs or none");
   if (N <= 0) return N == 0 ? TN_OK : TN_EINVAL;
   density_l1_kernel<<<n_partial, 256, 0, (cudaStream_t)stream>>>(d, d2, dt, d2t, N, value_mult, thermal_grad_mult,
-                                                               rgb_grad_mult, partial_out, g_d, g_d2, g_dt, g_d2t);
+                                                               rgb_grad_mult, upstream_dev, partial_out, ticket, g_d,
+                                                               g_d2, g_dt, g_d2t);
   return check_launch("density_l1_kernel");
 }
 
@@ -332,11 +400,24 @@ extern "C" int tn_camera_reg_fwd(const float* pose, int num_cameras, float trans
 }
 
 extern "C" int tn_camera_reg_bwd(const float* pose, const float* upstream_dev, int num_cameras, float trans_penalty,
-                                 float rot_penalty, float penalty_scale, float* dpose_out, void* stream) {
+                                 float rot_penalty, float penalty_scale, int accumulate, float* dpose_out,
+                                 void* stream) {
   TN_REQUIRE(pose && upstream_dev && dpose_out && num_cameras >= 1, TN_EINVAL, "camera_reg_bwd: bad arguments");
   camera_reg_bwd_kernel<<<(num_cameras + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      pose, upstream_dev, num_cameras, trans_penalty, rot_penalty, penalty_scale, dpose_out);
+      pose, upstream_dev, num_cameras, trans_penalty, rot_penalty, penalty_scale, accumulate, dpose_out);
   return check_launch("camera_reg_bwd_kernel");
+}
+
+extern "C" int tn_embed_bwd(float* dz1_ray, const float* w0, const int64_t* camera_indices, int64_t R, int width,
+                            int in_dim, int col0, int emb_dim, int clear, float* dweight, void* stream) {
+  TN_REQUIRE(dz1_ray && w0 && camera_indices && dweight, TN_EINVAL, "embed_bwd: null pointer");
+  TN_REQUIRE(width >= 1 && emb_dim >= 1 && col0 >= 0 && col0 + emb_dim <= in_dim, TN_EINVAL,
+             "embed_bwd: bad shape width=%d in_dim=%d col0=%d emb_dim=%d", width, in_dim, col0, emb_dim);
+  if (R <= 0) return R == 0 ? TN_OK : TN_EINVAL;
+  const int64_t warps = (R + kEmbRaysPerWarp - 1) / kEmbRaysPerWarp;
+  embed_bwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      dz1_ray, w0, camera_indices, R, width, in_dim, col0, emb_dim, clear, dweight);
+  return check_launch("embed_bwd_kernel");
 }
 
 extern "C" int tn_loss_sum(const float* const* term_host_ptrs, const float* scale_host, const int* slot_host,

@@ -66,6 +66,17 @@ class DeviceBatchSource:
                 "camera_indices": rays.camera_indices, "image": b["image"], "is_thermal": b["is_thermal"]}
 
 
+_WORK_STREAMS: Dict[str, "torch.cuda.Stream"] = {}
+
+
+def _work_stream(device) -> "torch.cuda.Stream":
+    """The one stream per device on which every GraphedTrainStep warms up and captures (see GraphedTrainStep.__init__)."""
+    k = str(device)
+    if k not in _WORK_STREAMS:
+        _WORK_STREAMS[k] = torch.cuda.Stream(device=device)
+    return _WORK_STREAMS[k]
+
+
 class GraphedTrainStep:
     """forward + metrics + loss dict + backward (+ flat gradient all-reduce) for a fixed batch shape.
 
@@ -150,6 +161,13 @@ class GraphedTrainStep:
         for f in self._fields:  # (also detaches the hooks of an earlier runner of the same model)
             f.grads_ready_callback = self._field_ready if self._early_active else None
         self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
+        self._seed = torch.ones((), device=self.device)
+        # Warm-up passes and every capture run on ONE stream.  autograd's AccumulateGrad nodes remember the stream they
+        # were created on and outlive a step (the model and this runner keep parts of the last graph alive); a
+        # parameter whose gradient goes to a sink hands its node an undefined gradient, which synchronises nothing, yet
+        # the engine still joins that node's stream at the end of the backward -- on a stream that is not part of the
+        # capture that is cudaErrorStreamCaptureIsolation.
+        self._work_stream = _work_stream(self.device) if use_graph else None
         self._load(example_batch)
         self.losses: Dict[str, Tensor] = {}
         self.total: Optional[Tensor] = None
@@ -178,7 +196,7 @@ class GraphedTrainStep:
         model.train()
         if use_graph:
             key = self._variant_key()
-            side = torch.cuda.Stream(device=self.device)
+            side = self._work_stream
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(max(warmup, 2) - 1):  # allocator / cudaFuncSetAttribute / host-constant caches warm
@@ -189,6 +207,15 @@ class GraphedTrainStep:
             torch.cuda.current_stream(self.device).wait_stream(side)
             torch.cuda.synchronize(self.device)
             self._capture(key)
+
+    def _drop_old_graphs(self) -> None:
+        """Release what this runner and the model still hold of earlier autograd graphs (and with them AccumulateGrad
+        nodes made on other streams, see `_work_stream`)."""
+        self.total, self.losses = None, {}
+        for m in self.model.modules():
+            for name in ("_sample_locations", "_density_before_activation", "_reg_cache"):
+                if getattr(m, name, None) is not None:
+                    setattr(m, name, None)
 
     def sync_replicas(self) -> None:
         """Data-parallel replicas must start identical: DistributedDataParallel broadcasts rank 0's parameters and
@@ -217,7 +244,8 @@ class GraphedTrainStep:
     def _capture(self, key: Tuple[bool, ...]):
         """Capture the train step for one tuple of "updated" decisions (one extra eager pass first: a variant met for
         the first time mid-training may run kernels that have not been launched yet)."""
-        side = torch.cuda.Stream(device=self.device)
+        side = self._work_stream
+        self._drop_old_graphs()
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):
             if self._pipeline:
@@ -233,14 +261,14 @@ class GraphedTrainStep:
             graphs = []
             for phase in (self._phase_a, self._phase_b, self._phase_c):
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=pool, stream=side):
                     phase(key)
                 pool = g.pool()
                 graphs.append(g)
             graph = tuple(graphs)
         else:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, pool=pool):
+            with torch.cuda.graph(graph, pool=pool, stream=side):
                 self._eager(apply_optimizer=True, captured=True, key=key)
         torch.cuda.synchronize(self.device)
         self.graph = graph
@@ -280,7 +308,7 @@ class GraphedTrainStep:
         total = getattr(self.losses, "total", None)
         self.total = total if total is not None else sum(self.losses.values())
         cur.wait_stream(self._zero_stream)
-        self.total.backward()
+        self.total.backward(gradient=self._seed)  # cached 1.0: no ones_like launch per step
 
     def _phase_c(self, key: Tuple[bool, ...]) -> None:
         """Backward of phase A from the gradients phase B left on its leaves: proposal networks, camera optimizers."""
@@ -360,7 +388,7 @@ class GraphedTrainStep:
             self.optimizer.tick(inactive=[g for g, upd in zip(self._sampler_groups, key) if not upd])
         if zeroed is not None:
             cur.wait_stream(zeroed)
-        self.total.backward()
+        self.total.backward(gradient=self._seed)  # cached 1.0: no ones_like launch per step
         begin = self._early_end if self._early_done else 0
         if self._comm_in_graph:
             self.grads.all_reduce_mean(self.group, begin=begin)

@@ -251,6 +251,8 @@ class Embedding(FieldComponent):
         self.in_dim = in_dim
         self.out_dim = out_dim
         self.embedding = nn.Embedding(in_dim, out_dim)
+        # accumulation target of d(embedding.weight) for the fused head backward (FlatGradBuffer.attach_sinks)
+        self.grad_sink: Optional[Tensor] = None
 
     def mean(self, dim=0):
         return self.embedding.weight.mean(dim)

@@ -36,6 +36,20 @@ def get_normalized_directions(directions: Tensor) -> Tensor:
     return (directions + 1.0) / 2.0
 
 
+def _chained_positions(lay) -> Tuple[Tensor, Tensor]:
+    """ops.sample_positions for a RayLayout.  The layout's origins/directions are replaced by the call's pass-through
+    outputs, so the bundle's consumers form a chain (proposal levels -> main field -> cross-field term) along which
+    ONE gradient buffer is handed back and added onto in place (ops._SamplePositionsFn)."""
+    if not _chainable(lay):  # outputs made under no_grad carry no graph: the layout must keep the originals
+        return ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+    x, selector, lay.origins, lay.directions = ops.sample_positions(lay.origins, lay.directions, lay.ebins, chain=True)
+    return x, selector
+
+
+def _chainable(lay) -> bool:
+    return lay.chain and torch.is_grad_enabled() and (lay.origins.requires_grad or lay.directions.requires_grad)
+
+
 def _is_linf_contraction(sd: Optional[SpatialDistortion]) -> bool:
     return isinstance(sd, SceneContraction) and sd.order == float("inf")
 
@@ -47,6 +61,7 @@ class Field(nn.Module):
         super().__init__()
         self._sample_locations = None
         self.grads_ready_callback = None  # see NerfactoField.forward
+        self._scratch = fused_ops.LaunchScratch()  # persistent, self-cleaning launch buffers (fused_ops.LaunchScratch)
         self._density_before_activation = None
 
     def _grid_coordinates(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
@@ -55,7 +70,7 @@ class Field(nn.Module):
         lay = getattr(ray_samples, "_layout", None)  # None for reference-built RaySamples
         if _is_linf_contraction(self.spatial_distortion):
             if lay is not None:
-                return ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+                return _chained_positions(lay)
             return ops.contract_points(ray_samples.frustums.get_positions().reshape(-1, 3))
         positions = ray_samples.frustums.get_positions()
         if self.spatial_distortion is not None:
@@ -178,7 +193,7 @@ class NerfactoField(Field):
                 or ray_samples.camera_indices is None:
             return super().forward(ray_samples, compute_normals=compute_normals)
         rays, samples = lay.num_rays, lay.num_samples
-        x, selector = ops.sample_positions(lay.origins, lay.directions, lay.ebins)
+        x, selector = _chained_positions(lay)
         if self.grads_ready_callback is not None and torch.is_grad_enabled() and x.requires_grad:
             # dL/dx of the main evaluation is produced by the encode backward, the LAST kernel that touches this
             # field's parameters in a step (heads and density MLP run before it, the cross-field density term, created
@@ -188,17 +203,32 @@ class NerfactoField(Field):
         self._sample_locations = x.view(rays, samples, 3)
         h = self.mlp_base(self._sample_locations).view(rays * samples, -1)
         self._density_before_activation = h.view(rays, samples, -1)[..., :1]
-        sh = self.direction_encoding(get_normalized_directions(lay.directions))
-        emb_ray = None
-        if self.embedding_appearance is not None:
-            if self.training:  # one lookup per ray; the samples of a ray share the camera (:289-290)
-                emb_ray = fused_ops.embed_rows(self.embedding_appearance.embedding.weight,
-                                               ray_samples.camera_indices[:, 0, 0])
-            elif self.use_average_appearance_embedding:
-                emb_ray = self.embedding_appearance.mean(dim=0)[None, :].expand(rays, -1)
-            else:
-                emb_ray = torch.zeros((rays, self.appearance_embedding_dim), device=x.device)
         head = self.mlp_head
+        emb = self.embedding_appearance
+        if emb is not None and self.training and self.direction_encoding.levels == 4:
+            # SH basis + the rays' embedding rows in one launch (:284-290: the samples of a ray share the camera); the
+            # embedding's gradient is formed by the head's backward (fused_ops._FieldHeadFn)
+            cam = ray_samples.camera_indices[:, 0, 0]
+            sh, emb_ray = fused_ops.ray_features(lay.directions, emb.embedding.weight, cam)
+            if fused_ops.field_head_supported(h.shape[-1], self.geo_feat_dim, emb_ray.shape[-1], samples, head):
+                density, rgb = fused_ops.field_head(
+                    h, selector, sh, emb_ray, rays, samples, self.geo_feat_dim, self.average_init_density,
+                    [l.weight for l in head.layers], [l.bias for l in head.layers], head._out_act,
+                    sinks=head.grad_sinks, emb_weight=emb.embedding.weight, cam_idx=cam, emb_sink=emb.grad_sink,
+                    scratch=self._scratch)
+                return {FieldHeadNames.RGB: rgb.view(rays, samples, -1),
+                        FieldHeadNames.DENSITY: density.view(rays, samples, 1)}
+            emb_ray = fused_ops.embed_rows(emb.embedding.weight, cam)  # differentiable lookup for the generic head
+        else:
+            sh = self.direction_encoding(get_normalized_directions(lay.directions))
+            emb_ray = None
+            if emb is not None:
+                if self.training:
+                    emb_ray = fused_ops.embed_rows(emb.embedding.weight, ray_samples.camera_indices[:, 0, 0])
+                elif self.use_average_appearance_embedding:
+                    emb_ray = emb.mean(dim=0)[None, :].expand(rays, -1)
+                else:
+                    emb_ray = torch.zeros((rays, self.appearance_embedding_dim), device=x.device)
         if emb_ray is not None and fused_ops.field_head_supported(h.shape[-1], self.geo_feat_dim, emb_ray.shape[-1],
                                                                   samples, head):
             # split + concatenation + colour head as one autograd node (one backward kernel)
@@ -286,9 +316,12 @@ class HashMLPDensityField(Field):
                 and len(self.mlp_base[1].layers) == 2 and self.mlp_base[1].layer_width == 16):
             # whole field in one kernel: positions -> contraction -> hash grid -> 16-wide MLP -> trunc_exp * selector
             l0, l1 = self.mlp_base[1].layers
-            density = fused_ops.prop_density(lay.origins, lay.directions, lay.ebins, enc.hash_table, l0.weight, l0.bias,
-                                             l1.weight, l1.bias, enc.spec, self.average_init_density, enc.grad_sink,
-                                             self.mlp_base[1].grad_sinks)
+            args = (lay.origins, lay.directions, lay.ebins, enc.hash_table, l0.weight, l0.bias, l1.weight, l1.bias,
+                    enc.spec, self.average_init_density, enc.grad_sink, self.mlp_base[1].grad_sinks)
+            if _chainable(lay):
+                density, lay.origins, lay.directions = fused_ops.prop_density(*args, chain=True)
+            else:
+                density = fused_ops.prop_density(*args)
             return density.view(lay.num_rays, lay.num_samples, 1), None
         x, selector = self._grid_coordinates(ray_samples)
         shape = ray_samples.frustums.shape

@@ -8,6 +8,8 @@ from torch import Tensor
 
 from ._lib import call, float_array, ptr, ptr_array, stream
 from .ops import _f32c
+from .ops import _ray_grad_finish as ops_ray_grad_finish
+from .ops import _ray_grad_targets as ops_ray_grad_targets
 
 
 class _FieldSplitFn(torch.autograd.Function):
@@ -48,12 +50,48 @@ def field_split(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Optional[Tensor], r
     return _FieldSplitFn.apply(h, sel, sh, emb_ray, rays, samples, geo_dim, scale)
 
 
+class LaunchScratch:
+    """Small device buffers a module keeps ACROSS steps for kernels that leave them in their initial state themselves
+    (the ticket / accumulator words of tn_ray_heads_fwd and tn_density_l1, the per-ray buffer tn_field_head_bwd
+    accumulates into and tn_embed_bwd clears): no fill, clone or zeros launch around those calls.  A buffer is only
+    ever created outside CUDA-graph capture (a tensor first made during capture holds nothing until a replay); get()
+    returns None then and the caller takes the self-initialising path for that call."""
+
+    def __init__(self) -> None:
+        self._bufs = {}
+        self.dirty = set()  # keys whose buffer a failed / partial backward may have left non-zero
+
+    def get(self, key, make):
+        t = self._bufs.get(key)
+        if t is None:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                return None
+            if len(self._bufs) > 16:
+                self._bufs.clear()
+            t = self._bufs[key] = make()
+        return t
+
+
+def heads_scratch(scratch: Optional[LaunchScratch], device, slot) -> Optional[Tensor]:
+    """{+inf, -inf, 0, 0, ticket 0}: the launch-wide words of one tn_ray_heads_fwd call site (`slot`: call sites that
+    may run concurrently -- the two branches -- use different words)."""
+    if scratch is None:
+        return None
+    return scratch.get(("heads", str(device), slot),
+                       lambda: torch.tensor([float("inf"), float("-inf"), 0.0, 0.0, 0.0]).to(device))
+
+
 class _FieldHeadFn(torch.autograd.Function):
     """A NerfactoField's colour head with its input assembly as one autograd node: ONE tensor-core kernel each way
-    (tn_field_head_fwd / _bwd).  Neither the 63-wide head input nor its gradient ever reaches HBM."""
+    (tn_field_head_fwd / _bwd).  Neither the 63-wide head input nor its gradient ever reaches HBM.
+
+    emb_weight / cam_idx given: `emb_ray` are rows of that table (ray_features) and the backward turns the head's
+    per-ray first-layer gradient straight into the table's gradient (tn_embed_bwd: no [R,32] gradient, no matmul, no
+    index_add_), into `emb_sink` when there is one."""
 
     @staticmethod
-    def forward(ctx, h, sel, sh, emb_ray, rays, samples, scale, out_act, sinks, *wb):
+    def forward(ctx, h, sel, sh, emb_ray, emb_weight, cam_idx, emb_sink, scratch, rays, samples, scale, out_act, sinks,
+                *wb):
         h, sel, sh, emb_ray = _f32c(h), _f32c(sel), _f32c(sh), _f32c(emb_ray)
         ws = [_f32c(t) for t in wb[0::2]]
         bs = [_f32c(t) for t in wb[1::2]]
@@ -66,16 +104,18 @@ class _FieldHeadFn(torch.autograd.Function):
              ptr_array(ws), ptr_array(bs), out_act, ptr(density), ptr(y), ptr(mask), stream(), tag=f"[63-64x2-{out_dim}]",
              units=n)
         ctx.dims = (rays, samples, float(scale), out_dim, out_act)
-        ctx.sinks = sinks
+        ctx.sinks, ctx.emb_sink, ctx.scratch = sinks, emb_sink, scratch
+        ctx.table = emb_weight is not None and cam_idx is not None
+        ctx.table_rows = emb_weight.shape[0] if ctx.table else 0
         ctx.set_materialize_grads(False)
-        ctx.save_for_backward(h, sel, sh, emb_ray, mask, *ws, *bs)
+        ctx.save_for_backward(h, sel, sh, emb_ray, mask, cam_idx if ctx.table else None, *ws, *bs)
         return density, y
 
     @staticmethod
     def backward(ctx, d_density, dy):
         saved = ctx.saved_tensors
-        h, sel, sh, emb_ray, mask = saved[:5]
-        ws, bs = list(saved[5:8]), list(saved[8:11])
+        h, sel, sh, emb_ray, mask, cam_idx = saved[:6]
+        ws, bs = list(saved[6:9]), list(saved[9:12])
         rays, samples, scale, out_dim, out_act = ctx.dims
         if dy is None:
             dy = torch.zeros((rays * samples, out_dim), device=h.device)
@@ -85,28 +125,78 @@ class _FieldHeadFn(torch.autograd.Function):
         else:
             dws, dbs = [torch.zeros_like(w) for w in ws], [torch.zeros_like(b) for b in bs]
         dh = torch.empty_like(h)
-        dz1_ray = torch.zeros((rays, 64), device=h.device)
+        want_table = ctx.table and ctx.needs_input_grad[4]
+        # dz1_ray: accumulated into by the head kernel; with the table path a persistent buffer that tn_embed_bwd clears
+        key = ("dz1", str(h.device), rays)
+        keep = ctx.scratch.get(key, lambda: torch.zeros((rays, 64), device=h.device)) \
+            if (want_table and ctx.scratch is not None) else None
+        if keep is not None:
+            if key in ctx.scratch.dirty:
+                keep.zero_()
+            ctx.scratch.dirty.add(key)
+            dz1_ray = keep
+        else:
+            dz1_ray = torch.zeros((rays, 64), device=h.device)
         call("tn_field_head_bwd", ptr(_f32c(dy)), ptr(mask), ptr(h), ptr(sel), ptr(sh), ptr(emb_ray),
              ptr(None if d_density is None else _f32c(d_density)), rays, samples, out_dim, scale, ptr_array(ws),
              ptr_array(bs), out_act, ptr(dh), ptr(dz1_ray), ptr_array(dws), ptr_array(dbs), stream(),
              tag=f"[63-64x2-{out_dim}]", units=rays * samples)
-        demb = dz1_ray @ ws[0][:, 31:63] if ctx.needs_input_grad[3] else None
+        demb = dtable = None
+        if want_table:
+            esink = ctx.emb_sink
+            dtab = esink if esink is not None else torch.zeros((ctx.table_rows, 32), device=h.device)
+            call("tn_embed_bwd", ptr(dz1_ray), ptr(ws[0]), ptr(cam_idx), rays, 64, ws[0].shape[1], 31, 32,
+                 int(keep is not None), ptr(dtab), stream())
+            if keep is not None:
+                ctx.scratch.dirty.discard(key)
+            dtable = None if esink is not None else dtab
+        elif ctx.needs_input_grad[3]:
+            demb = dz1_ray @ ws[0][:, 31:63]
         grads = []
         for dw, db in zip(dws, dbs):
             grads += [None, None] if sinks is not None else [dw, db]
-        return (dh, None, None, demb, None, None, None, None, None, *grads)
+        return (dh, None, None, demb, dtable, None, None, None, None, None, None, None, None, *grads)
 
 
 def field_head(h: Tensor, sel: Tensor, sh: Tensor, emb_ray: Tensor, rays: int, samples: int, geo_dim: int,
-               scale: float, weights, biases, out_act: int, sinks=None) -> Tuple[Tensor, Tensor]:
+               scale: float, weights, biases, out_act: int, sinks=None, emb_weight: Optional[Tensor] = None,
+               cam_idx: Optional[Tensor] = None, emb_sink: Optional[Tensor] = None,
+               scratch: Optional[LaunchScratch] = None) -> Tuple[Tensor, Tensor]:
     """(density[R*S], head output [R*S, C]) of a NerfactoField from the density-MLP output h[R*S,16]: trunc_exp *
     selector, the [SH | geo | appearance] concatenation and the 63-64-64-C colour head.
-    fields/nerfacto_field.py:221-228, 335-348."""
+    fields/nerfacto_field.py:221-228, 335-348.
+    emb_weight [num_cameras,32] + cam_idx [R] (int64): emb_ray = emb_weight[cam_idx] (ray_features); the embedding's
+    gradient is then formed by the backward itself (see _FieldHeadFn)."""
     wb = []
     for w, b in zip(weights, biases):
         wb += [w, b]
     assert geo_dim == 15 and emb_ray.shape[-1] == 32 and h.shape[-1] == 16, "see field_head_supported"
-    return _FieldHeadFn.apply(h, sel, sh, emb_ray, rays, samples, scale, out_act, sinks, *wb)
+    if emb_weight is not None:
+        assert emb_weight.shape[-1] == 32 and cam_idx is not None and cam_idx.dtype == torch.int64
+        cam_idx = cam_idx.contiguous()
+    return _FieldHeadFn.apply(h, sel, sh, emb_ray, emb_weight, cam_idx, emb_sink, scratch, rays, samples, scale,
+                              out_act, sinks, *wb)
+
+
+@torch.no_grad()
+def ray_features(directions: Tensor, emb_weight: Optional[Tensor] = None,
+                 cam_idx: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor]]:
+    """(SH basis [R,16] of the normalised directions (d+1)/2, appearance-embedding rows [R,E] | None) of a ray batch in
+    one launch.  fields/base_field.py:136-142 + encodings.py:792-795 (under no_grad in the reference too) +
+    field_components/embedding.py:48-55 (values only: the gradient is _FieldHeadFn's)."""
+    d = _f32c(directions.detach())
+    r = d.shape[0]
+    sh = torch.empty((r, 16), device=d.device)
+    emb = w = None
+    e = 0
+    if emb_weight is not None:
+        w = _f32c(emb_weight.detach())
+        e = w.shape[-1]
+        emb = torch.empty((r, e), device=d.device)
+        cam_idx = cam_idx.contiguous()
+    call("tn_ray_features", ptr(d), ptr(w), ptr(cam_idx if emb is not None else None), r, e, ptr(sh), ptr(emb),
+         stream())
+    return sh, emb
 
 
 def field_head_supported(h_width: int, geo_dim: int, emb_dim: int, samples: int, head) -> bool:
@@ -147,30 +237,35 @@ def density_act(h: Tensor, sel: Tensor, scale: float) -> Tensor:
 
 
 class _PropDensityFn(torch.autograd.Function):
-    """ray samples -> proposal density, one kernel each way (csrc/tn_prop.cu)."""
+    """ray samples -> proposal density, one kernel each way (csrc/tn_prop.cu).  chain: see ops._SamplePositionsFn."""
 
     @staticmethod
-    def forward(ctx, origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks):
+    def forward(ctx, origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks, chain):
         ctx.mlp_sinks = mlp_sinks
-        origins, directions, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
+        o, d, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
         w1, b1, w2, b2 = _f32c(w1), _f32c(b1), _f32c(w2), _f32c(b2)
         r, s = ebins.shape[0], ebins.shape[1] - 1
         density = torch.empty((r * s,), device=ebins.device)
-        call("tn_prop_density_fwd", ptr(origins), ptr(directions), ptr(ebins), ptr(table), spec._c_scales, r, s,
+        call("tn_prop_density_fwd", ptr(o), ptr(d), ptr(ebins), ptr(table), spec._c_scales, r, s,
              spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), float(scale), ptr(density),
              stream(), tag=f"[L{spec.num_levels},S{s}]", units=r * s)
         ctx.spec, ctx.scale, ctx.grad_sink = spec, float(scale), grad_sink
-        ctx.save_for_backward(origins, directions, ebins, table, w1, b1, w2, b2)
-        return density
+        ctx.save_for_backward(o, d, ebins, table, w1, b1, w2, b2)
+        ctx.set_materialize_grads(False)
+        return (density, origins, directions) if chain else density
 
     @staticmethod
-    def backward(ctx, d_density):
+    def backward(ctx, d_density, g_o=None, g_d=None):
         origins, directions, ebins, table, w1, b1, w2, b2 = ctx.saved_tensors
+        if d_density is None:
+            return (g_o, g_d) + (None,) * 11
         spec = ctx.spec
         r, s = ebins.shape[0], ebins.shape[1] - 1
         need_rays = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        d_o = torch.zeros_like(origins) if need_rays else None
-        d_d = torch.zeros_like(directions) if need_rays else None
+        d_o = d_d = None
+        acc = False
+        if need_rays:  # the kernel adds with atomics: onto the later consumers' gradient when there is one
+            d_o, d_d, acc = ops_ray_grad_targets(g_o, g_d, origins, directions, zero=True)
         sink = ctx.grad_sink if ctx.needs_input_grad[3] else None
         dtable = sink if sink is not None else torch.zeros_like(table)
         ms = ctx.mlp_sinks
@@ -182,17 +277,24 @@ class _PropDensityFn(torch.autograd.Function):
              spec.num_levels, spec.log2_T, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2), ctx.scale,
              ptr(_f32c(d_density)), ptr(dtable), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(d_o), ptr(d_d), stream(),
              tag=f"[L{spec.num_levels},S{s}{',dx' if need_rays else ''}]", units=r * s)
+        if need_rays:
+            d_o, d_d = ops_ray_grad_finish(d_o, d_d, g_o, g_d, acc)
+        else:
+            d_o, d_d = g_o, g_d
         dt = dtable if (ctx.needs_input_grad[3] and sink is None) else None
         if ms is not None:
             dw1 = db1 = dw2 = db2 = None
-        return d_o, d_d, None, dt, dw1, db1, dw2, db2, None, None, None, None
+        return d_o, d_d, None, dt, dw1, db1, dw2, db2, None, None, None, None, None
 
 
 def prop_density(origins: Tensor, directions: Tensor, ebins: Tensor, table: Tensor, w1: Tensor, b1: Tensor, w2: Tensor,
-                 b2: Tensor, spec, scale: float, grad_sink: Optional[Tensor] = None, mlp_sinks=None) -> Tensor:
+                 b2: Tensor, spec, scale: float, grad_sink: Optional[Tensor] = None, mlp_sinks=None,
+                 chain: bool = False):
     """HashMLPDensityField.get_density for ray samples, fused end to end.  fields/density_fields.py:95-118.
-    grad_sink / mlp_sinks: optional accumulation targets for the table and [(dW1,db1),(dW2,db2)] gradients."""
-    return _PropDensityFn.apply(origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks)
+    grad_sink / mlp_sinks: optional accumulation targets for the table and [(dW1,db1),(dW2,db2)] gradients.
+    chain=True: returns (density, origins, directions), the last two pass-through for the bundle's next consumer."""
+    return _PropDensityFn.apply(origins, directions, ebins, table, w1, b1, w2, b2, spec, scale, grad_sink, mlp_sinks,
+                                chain)
 
 
 class _EmbedRowsFn(torch.autograd.Function):
@@ -218,17 +320,19 @@ def embed_rows(weight: Tensor, idx: Tensor) -> Tensor:
 
 
 class _CameraOptFn(torch.autograd.Function):
-    """CameraOptimizer.apply_to_raybundle (SO3xR3 / shared) as one kernel each way (csrc/tn_model.cu)."""
+    """CameraOptimizer.apply_to_raybundle (SO3xR3 / shared) as one kernel each way (csrc/tn_model.cu).
+    sink: optional accumulation target for d(pose) (the parameter's slice of a FlatGradBuffer; the kernel adds with
+    atomics): no zeros launch, and autograd has nothing to accumulate."""
 
     @staticmethod
-    def forward(ctx, pose, frozen, cam, origins, directions, shared):
+    def forward(ctx, pose, frozen, cam, origins, directions, shared, sink):
         pose, origins, directions = _f32c(pose), _f32c(origins), _f32c(directions)
         cam = cam.contiguous()
         r = origins.shape[0]
         oo, dd = torch.empty_like(origins), torch.empty_like(directions)
         call("tn_camera_opt_fwd", ptr(pose), ptr(frozen), ptr(cam), ptr(origins), ptr(directions), r, int(shared),
              ptr(oo), ptr(dd), stream())
-        ctx.shared = int(shared)
+        ctx.shared, ctx.sink = int(shared), sink
         ctx.save_for_backward(pose, frozen, cam, directions)
         ctx.set_materialize_grads(False)
         return oo, dd
@@ -236,19 +340,22 @@ class _CameraOptFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_o, g_d):
         pose, frozen, cam, directions = ctx.saved_tensors
-        dpose = torch.zeros_like(pose)
+        if g_o is None and g_d is None:
+            return None, None, None, None, None, None, None
+        sink = ctx.sink
+        dpose = sink if sink is not None else torch.zeros_like(pose)
         call("tn_camera_opt_bwd", ptr(pose), ptr(frozen), ptr(cam), ptr(directions),
              ptr(None if g_o is None else _f32c(g_o)), ptr(None if g_d is None else _f32c(g_d)), directions.shape[0],
              ctx.shared, ptr(dpose), stream())
         # rays are data: the reference's bundle tensors do not require grad either
-        return dpose, None, None, None, None, None
+        return (None if sink is not None else dpose), None, None, None, None, None, None
 
 
 def camera_opt_apply(pose: Tensor, frozen: Optional[Tensor], camera_indices: Tensor, origins: Tensor,
-                     directions: Tensor, shared: bool) -> Tuple[Tensor, Tensor]:
+                     directions: Tensor, shared: bool, sink: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """(origins + t_c, R(w_c) directions) for the per-camera pose adjustments.
     cameras/camera_optimizers.py:132-176, cameras/lie_groups.py:24-59."""
-    return _CameraOptFn.apply(pose, frozen, camera_indices, origins, directions, shared)
+    return _CameraOptFn.apply(pose, frozen, camera_indices, origins, directions, shared, sink)
 
 
 class _PixelLossesFn(torch.autograd.Function):
@@ -296,8 +403,11 @@ _L1_PARTIALS = 64
 
 
 class _DensityL1Fn(torch.autograd.Function):
+    """Value in the forward (per-CTA partial sums; the CTA that finishes last adds them up when the caller lends a
+    ticket word), the four gradients in the backward, already multiplied by the upstream scalar: one launch each way."""
+
     @staticmethod
-    def forward(ctx, d, d2, dt, d2t, mult, rgb_mult):
+    def forward(ctx, d, d2, dt, d2t, mult, rgb_mult, scratch):
         ctx.shape = d.shape
         d, d2, dt, d2t = (_f32c(t).view(-1) for t in (d, d2, dt, d2t))
         n = d.numel()
@@ -305,23 +415,30 @@ class _DensityL1Fn(torch.autograd.Function):
             vm, m, rm = mult, mult, mult
         else:              # asymmetric stop-gradient pattern (:336-344)
             vm, m, rm = mult * (1.0 + rgb_mult), mult, mult * rgb_mult
-        partial = torch.empty((_L1_PARTIALS,), device=d.device)
-        grads = [torch.empty_like(d) for _ in range(4)]
-        call("tn_density_l1", ptr(d), ptr(d2), ptr(dt), ptr(d2t), n, float(vm), float(m), float(rm), ptr(partial),
-             _L1_PARTIALS, ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), ptr(grads[3]), stream())
-        ctx.save_for_backward(*grads)
-        return partial.sum()
+        partial = torch.empty((_L1_PARTIALS + 1,), device=d.device)
+        ticket = None if scratch is None else scratch.get(
+            ("l1", str(d.device)), lambda: torch.zeros((1,), device=d.device, dtype=torch.int32))
+        call("tn_density_l1", ptr(d), ptr(d2), ptr(dt), ptr(d2t), n, float(vm), float(m), float(rm), None, ptr(partial),
+             _L1_PARTIALS, ptr(ticket), None, None, None, None, stream())
+        ctx.mults = (float(vm), float(m), float(rm))
+        ctx.save_for_backward(d, d2, dt, d2t)
+        return partial[_L1_PARTIALS] if ticket is not None else partial[:_L1_PARTIALS].sum()
 
     @staticmethod
     def backward(ctx, g):
+        d, d2, dt, d2t = ctx.saved_tensors
         s = ctx.shape
-        return (*[(t * g).view(s) for t in ctx.saved_tensors], None, None)
+        grads = [torch.empty_like(d) for _ in range(4)]
+        call("tn_density_l1", ptr(d), ptr(d2), ptr(dt), ptr(d2t), d.numel(), *ctx.mults, ptr(_f32c(g)), None,
+             _L1_PARTIALS, None, ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), ptr(grads[3]), stream())
+        return (*[t.view(s) for t in grads], None, None, None)
 
 
-def density_l1(d: Tensor, d2: Tensor, dt: Tensor, d2t: Tensor, mult: float, rgb_mult: float) -> Tensor:
-    """density_loss of ThermalNerfactoModel.get_loss_dict (models/thermal_nerfacto.py:328-344), value and the
-    gradients to all four densities in one launch."""
-    return _DensityL1Fn.apply(d, d2, dt, d2t, mult, rgb_mult)
+def density_l1(d: Tensor, d2: Tensor, dt: Tensor, d2t: Tensor, mult: float, rgb_mult: float,
+               scratch: Optional[LaunchScratch] = None) -> Tensor:
+    """density_loss of ThermalNerfactoModel.get_loss_dict (models/thermal_nerfacto.py:328-344): the value in one
+    launch, the gradients to all four densities in one launch."""
+    return _DensityL1Fn.apply(d, d2, dt, d2t, mult, rgb_mult, scratch)
 
 
 class _DistortionFn(torch.autograd.Function):
@@ -375,12 +492,13 @@ def interlevel_loss_level(w_fine: Tensor, c_fine: Tensor, w_prop: Tensor, c_prop
 
 class _CameraRegFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pose, trans_pen, rot_pen, scale):
+    def forward(ctx, pose, trans_pen, rot_pen, scale, sink):
         pose = _f32c(pose)
         out = torch.empty((3,), device=pose.device)
         call("tn_camera_reg_fwd", ptr(pose), pose.shape[0], float(trans_pen), float(rot_pen), float(scale), ptr(out),
              stream())
         ctx.coef = (float(trans_pen), float(rot_pen), float(scale))
+        ctx.sink = sink
         ctx.save_for_backward(pose)
         ctx.set_materialize_grads(False)
         reg, tn_, rn_ = out.unbind(0)
@@ -391,16 +509,19 @@ class _CameraRegFn(torch.autograd.Function):
     def backward(ctx, g, _gt, _gr):
         (pose,) = ctx.saved_tensors
         if g is None:
-            return None, None, None, None
-        dpose = torch.empty_like(pose)
-        call("tn_camera_reg_bwd", ptr(pose), ptr(_f32c(g)), pose.shape[0], *ctx.coef, ptr(dpose), stream())
-        return dpose, None, None, None
+            return None, None, None, None, None
+        sink = ctx.sink
+        dpose = sink if sink is not None else torch.empty_like(pose)
+        call("tn_camera_reg_bwd", ptr(pose), ptr(_f32c(g)), pose.shape[0], *ctx.coef, int(sink is not None), ptr(dpose),
+             stream())
+        return (None if sink is not None else dpose), None, None, None, None
 
 
-def camera_regularizer(pose: Tensor, trans_pen: float, rot_pen: float, scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+def camera_regularizer(pose: Tensor, trans_pen: float, rot_pen: float, scale: float,
+                       sink: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """(regulariser, |translations|_F, |rotations|_F) of a CameraOptimizer's pose table in one launch.
-    cameras/camera_optimizers.py:188-194, 200-204."""
-    return _CameraRegFn.apply(pose, trans_pen, rot_pen, scale)
+    cameras/camera_optimizers.py:188-194, 200-204.  sink: accumulation target of d(pose) (see camera_opt_apply)."""
+    return _CameraRegFn.apply(pose, trans_pen, rot_pen, scale, sink)
 
 
 _SCALE_CACHE = {}
@@ -498,9 +619,11 @@ class _RayHeadsFn(torch.autograd.Function):
     forward (tn_ray_heads_fwd), and the ray-level backward of the whole branch -- final level and every proposal
     level -- in one launch (tn_ray_heads_bwd)."""
 
+    _FIXED = 12  # positional arguments before *prop_sigma
+
     @staticmethod
     def forward(ctx, sigma, colour, ebins, sbins, bg_mode, bg, eval_mode, want_losses, prop_ebins, prop_sbins,
-                prop_weights, *prop_sigma):
+                prop_weights, scratch, *prop_sigma):
         sigma, colour, ebins, sbins = _f32c(sigma), _f32c(colour), _f32c(ebins), _f32c(sbins)
         r, s = sigma.shape
         c = colour.shape[-1]
@@ -510,44 +633,57 @@ class _RayHeadsFn(torch.autograd.Function):
         prop_weights = [_f32c(t).view(r, -1) for t in prop_weights[:n_prop]]
         prop_sbins = [_f32c(t) for t in prop_sbins[:n_prop]]
         prop_S = [t.shape[1] for t in prop_weights]
-        need_prop_grad = [want_losses and i < len(prop_sigma) and ctx.needs_input_grad[11 + i] for i in range(n_prop)]
+        need_prop_grad = [want_losses and i < len(prop_sigma) and ctx.needs_input_grad[_RayHeadsFn._FIXED + i]
+                          for i in range(n_prop)]
         prop_dw = [torch.empty_like(prop_weights[i]) if need_prop_grad[i] else None for i in range(n_prop)]
         w = torch.empty_like(sigma)
         rgb = torch.empty((r, c), device=dev)
         acc = torch.empty((r, 1), device=dev)
         med = torch.empty((r, 1), device=dev)
         exp = torch.empty((r, 1), device=dev)
-        scratch = _heads_scratch(dev)
-        minmax, loss_acc = scratch[:2], scratch[2:]
         dw_dist = torch.empty_like(sigma) if (want_losses and ctx.needs_input_grad[0]) else None
         bg_arr = float_array(bg) if bg is not None else None
         ints = (ctypes.c_int * max(n_prop, 1))(*(prop_S or [0]))
+        if scratch is not None:
+            # the launch's last CTA writes the FINAL extrema, loss means and clipped depth and re-arms `scratch`
+            out4 = torch.empty((4,), device=dev)
+            minmax, loss_acc = out4[:2], out4[2:]
+            exp_clip = torch.empty((r, 1), device=dev)
+        else:
+            out4 = _heads_scratch(dev)  # accumulated into by the kernel; scaled / used for the clip below
+            minmax, loss_acc = out4[:2], out4[2:]
+            exp_clip = None
         call("tn_ray_heads_fwd", ptr(sigma), ptr(colour), ptr(ebins), ptr(sbins), r, s, c, bg_mode, bg_arr,
              int(eval_mode), n_prop, ptr_array(prop_weights) if n_prop else None,
              ptr_array(prop_sbins) if n_prop else None, ints, ptr_array(prop_dw) if n_prop else None, ptr(w), ptr(rgb),
-             ptr(acc), ptr(med), ptr(exp), ptr(minmax), ptr(loss_acc) if want_losses else None, ptr(dw_dist), stream(),
+             ptr(acc), ptr(med), ptr(exp), ptr(minmax), ptr(loss_acc) if want_losses else None, ptr(dw_dist),
+             ptr(scratch), 1.0 / r, 1.0 / (r * s), ptr(exp_clip), stream(),
              tag=f"[S{s},C{c},+{n_prop}]" if n_prop else f"[S{s},C{c}]", units=r * s)
         ctx.cfg = (bg_mode, bg, c, [i for i in range(n_prop) if need_prop_grad[i]], prop_S)
         ctx.set_materialize_grads(False)
         live = [i for i in range(n_prop) if need_prop_grad[i]]
         ctx.n_live = len(live)
-        ctx.save_for_backward(sigma, colour, ebins, w, dw_dist, *[_f32c(prop_sigma[i]).view(r, -1) for i in live],
+        ctx.save_for_backward(sigma, colour, ebins, w, dw_dist, exp, minmax,
+                              *[_f32c(prop_sigma[i]).view(r, -1) for i in live],
                               *[_f32c(prop_ebins[i]) for i in live], *[prop_dw[i] for i in live])
+        if scratch is None:
+            exp_clip = torch.clamp(exp, minmax[0], minmax[1])  # batch-global clip, renderers.py:574
+        dist = inter = None
         if want_losses:  # means over rays / over rays x fine samples (losses.py:135, :158)
-            dist, inter = (loss_acc * _loss_scales(dev, r, s)).unbind(0)
-        else:
-            dist = inter = None
+            dist, inter = (loss_acc if scratch is not None else loss_acc * _loss_scales(dev, r, s)).unbind(0)
         ctx.mark_non_differentiable(w, med, minmax)
-        return rgb, acc, med, exp, minmax, w, dist, inter
+        return rgb, acc, med, exp_clip, minmax, w, dist, inter
 
     @staticmethod
     def backward(ctx, d_rgb, d_acc, _d_med, d_exp, _d_mm, _d_w, g_dist, g_inter):
         bg_mode, bg, c, live, prop_S = ctx.cfg
         saved = ctx.saved_tensors
-        sigma, colour, ebins, w, dw_dist = saved[:5]
+        sigma, colour, ebins, w, dw_dist, exp_raw, minmax = saved[:7]
         k = ctx.n_live
-        p_sigma, p_ebins, p_dw = saved[5:5 + k], saved[5 + k:5 + 2 * k], saved[5 + 2 * k:5 + 3 * k]
+        p_sigma, p_ebins, p_dw = saved[7:7 + k], saved[7 + k:7 + 2 * k], saved[7 + 2 * k:7 + 3 * k]
         r, s = sigma.shape
+        if d_exp is not None:  # the clip passes the gradient where it did not bite (torch.clamp's rule)
+            d_exp = d_exp * ((exp_raw >= minmax[0]) & (exp_raw <= minmax[1])).to(d_exp.dtype)
         dsigma = torch.empty_like(sigma)
         dcol = torch.empty_like(colour) if ctx.needs_input_grad[1] else None
         p_dsigma = [torch.empty_like(t) for t in p_sigma]
@@ -559,10 +695,10 @@ class _RayHeadsFn(torch.autograd.Function):
              ptr_array(list(p_sigma)) if k else None, ptr_array(list(p_ebins)) if k else None,
              ptr_array(list(p_dw)) if k else None, ints, ptr(dsigma), ptr(dcol), ptr_array(p_dsigma) if k else None,
              stream(), tag=f"[S{s},C{c},+{k}]", units=r * s)
-        grads = [None] * len(ctx.needs_input_grad[11:])
+        grads = [None] * len(ctx.needs_input_grad[_RayHeadsFn._FIXED:])
         for j, i in enumerate(live):
             grads[i] = p_dsigma[j]
-        return (dsigma, dcol, None, None, None, None, None, None, None, None, None, *grads)
+        return (dsigma, dcol, *([None] * (_RayHeadsFn._FIXED - 2)), *grads)
 
 
 _LOSS_SCALES = {}
@@ -576,11 +712,15 @@ def _loss_scales(device, rays: int, samples: int) -> Tensor:
 
 
 def ray_heads(sigma: Tensor, colour: Tensor, ebins: Tensor, sbins: Tensor, *, bg_mode: int, bg, eval_mode: bool,
-              want_losses: bool, prop_sigma=(), prop_ebins=(), prop_sbins=(), prop_weights=()):
+              want_losses: bool, prop_sigma=(), prop_ebins=(), prop_sbins=(), prop_weights=(),
+              scratch: Optional[Tensor] = None):
     """sigma [R,S], colour [R,S,C], bin edges [R,S+1] of the final level (+ per proposal level: density [R,S_i] --
     the differentiable input --, bin edges and the weights tn_level_resample made of it)  ->
-    (rgb [R,C], accumulation [R,1], median depth [R,1], UNCLIPPED expected depth [R,1], (min,max) of the sample
-    midpoints [2], weights [R,S] (no gradient: the losses that read them are inside), mean distortion loss | None,
-    mean interlevel loss summed over the proposal levels | None)."""
+    (rgb [R,C], accumulation [R,1], median depth [R,1], expected depth [R,1] clipped to the launch-wide extrema of the
+    sample midpoints (renderers.py:574), those (min,max) [2], weights [R,S] (no gradient: the losses that read them
+    are inside), mean distortion loss | None, mean interlevel loss summed over the proposal levels | None).
+    scratch: the call site's `heads_scratch` words; with them the kernel's last CTA finishes the extrema, the loss
+    means and the clip itself (otherwise: a clone before and two small torch launches after the kernel)."""
     return _RayHeadsFn.apply(sigma, colour, ebins, sbins, bg_mode, None if bg is None else tuple(bg), eval_mode,
-                             want_losses, tuple(prop_ebins), tuple(prop_sbins), tuple(prop_weights), *prop_sigma)
+                             want_losses, tuple(prop_ebins), tuple(prop_sbins), tuple(prop_weights), scratch,
+                             *prop_sigma)

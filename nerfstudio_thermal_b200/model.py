@@ -75,6 +75,8 @@ class CameraOptimizer(nn.Module):
         self.register_buffer("_frozen_u8", frozen.to(torch.uint8), persistent=False)
         self.fused = True  # single-kernel apply_to_raybundle on CUDA (the torch expression is kept in forward())
         self._reg_cache = None
+        # accumulation target of d(pose_adjustment) for the fused kernels (parallel.FlatGradBuffer.attach_sinks)
+        self.grad_sink: Optional[Tensor] = None
 
     def forward(self, indices: Tensor) -> Tensor:
         if self.config.mode == "off":
@@ -94,7 +96,7 @@ class CameraOptimizer(nn.Module):
             raybundle.origins, raybundle.directions = fused_ops.camera_opt_apply(
                 self.pose_adjustment, self._frozen_u8 if self.has_frozen else None,
                 raybundle.camera_indices.reshape(-1), raybundle.origins, raybundle.directions,
-                self.config.mode == "shared_SO3xR3")
+                self.config.mode == "shared_SO3xR3", sink=self.grad_sink)
             return
         if self.config.mode != "off":
             c = self(raybundle.camera_indices.squeeze(-1))
@@ -104,7 +106,8 @@ class CameraOptimizer(nn.Module):
     def _reg_and_norms(self):
         """(regulariser, |t|_F, |w|_F) of the pose table from one launch (fused_ops.camera_regularizer)."""
         c = self.config
-        return fused_ops.camera_regularizer(self.pose_adjustment, c.trans_l2_penalty, c.rot_l2_penalty, c.penalty_scale)
+        return fused_ops.camera_regularizer(self.pose_adjustment, c.trans_l2_penalty, c.rot_l2_penalty, c.penalty_scale,
+                                            sink=self.grad_sink)
 
     def get_loss_dict(self, loss_dict: dict) -> None:
         if self.config.mode != "off" and self.fused and self.pose_adjustment.is_cuda:
@@ -144,12 +147,23 @@ class NearFarCollider(nn.Module):
     def __init__(self, near_plane: float, far_plane: float, reset_near_plane: bool = True) -> None:
         super().__init__()
         self.near_plane, self.far_plane, self.reset_near_plane = near_plane, far_plane, reset_near_plane
+        self._planes: Dict = {}
 
     def forward(self, ray_bundle: RayBundle) -> RayBundle:
-        ones = torch.ones_like(ray_bundle.origins[..., 0:1])
         near_plane = self.near_plane if (self.training or not self.reset_near_plane) else 0
-        ray_bundle.nears = ones * near_plane
-        ray_bundle.fars = ones * self.far_plane
+        o = ray_bundle.origins
+        # constants: built once per (batch shape, device, planes) instead of ones_like + two multiplies per call
+        key = (tuple(o.shape[:-1]), str(o.device), o.dtype, float(near_plane), float(self.far_plane))
+        planes = self._planes.get(key)
+        if planes is None:
+            planes = (torch.full((*o.shape[:-1], 1), float(near_plane), device=o.device, dtype=o.dtype),
+                      torch.full((*o.shape[:-1], 1), float(self.far_plane), device=o.device, dtype=o.dtype))
+            # (a tensor first made while a CUDA graph is being captured only holds its values after a replay)
+            if not (o.is_cuda and torch.cuda.is_current_stream_capturing()):
+                if len(self._planes) > 8:
+                    self._planes.clear()
+                self._planes[key] = planes
+        ray_bundle.nears, ray_bundle.fars = planes
         return ray_bundle
 
 
@@ -317,6 +331,7 @@ class ThermalNerfactoModel(nn.Module):
         # chunk graph of engine.GraphedRenderChunk
         self.eval_branch_streams = False
         self._side_stream = None
+        self._scratch = fused_ops.LaunchScratch()  # self-re-arming launch words of the per-level / loss kernels
         self._populate(aabb)
 
     @property
@@ -529,10 +544,13 @@ class ThermalNerfactoModel(nn.Module):
         sbins, ebins = ops.piecewise_bins(nears, fars, bs.counts[0], jit(0))
         anneal = sampler._anneal_tensor(dev)
         for i in range(n):
-            lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars)
+            lay = RayLayout(ray_bundle.origins, ray_bundle.directions, ebins, sbins, nears, fars, chain=True)
             rs = samples_from_layout(ray_bundle, lay, bs.spacing)
             with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
                 sigma = density_fns[i].__self__.get_density(rs)[0].view(num_rays, bs.counts[i])
+            # the proposal field handed the bundle on (pass-through outputs, see fields._chained_positions): the next
+            # level / the main field read the chained tensors
+            ray_bundle.origins, ray_bundle.directions = lay.origins, lay.directions
             w, med, sbins, ebins = fused_ops.level_resample(
                 sigma.detach(), lay.ebins, lay.sbins, nears, fars, bs.counts[i + 1], jit(i + 1), anneal=anneal,
                 histogram_padding=sampler.pdf_sampler.histogram_padding)
@@ -557,22 +575,23 @@ class ThermalNerfactoModel(nn.Module):
             return self._get_outputs(ray_bundle, field_, renderer, ray_samples, weights_list, ray_samples_list), ray_samples
         n = len(bs.prop_sigma)
         num_rays = ray_bundle.origins.shape[0]
-        lay = RayLayout(ray_bundle.origins, ray_bundle.directions, bs.ebins, bs.sbins, bs.nears, bs.fars)
+        lay = RayLayout(ray_bundle.origins, ray_bundle.directions, bs.ebins, bs.sbins, bs.nears, bs.fars, chain=True)
         ray_samples = samples_from_layout(ray_bundle, lay, bs.spacing)
         field_outputs = field_.forward(ray_samples, compute_normals=False)
         density, colour = field_outputs[FieldHeadNames.DENSITY], field_outputs[FieldHeadNames.RGB]
         bg_mode, bg_const, _ = renderer._bg_args(renderer.background_color, colour.shape[-1])
-        rgb, accumulation, depth, exp_raw, minmax, weights, dist, inter = fused_ops.ray_heads(
+        rgb, accumulation, depth, expected_depth, _, weights, dist, inter = fused_ops.ray_heads(
             density.view(num_rays, bs.counts[n]), colour, bs.ebins, bs.sbins, bg_mode=bg_mode, bg=bg_const,
             eval_mode=not self.training, want_losses=self.training,
             prop_sigma=bs.prop_sigma if bs.grad_props else (),
             prop_ebins=[r_._layout.ebins for r_ in bs.ray_samples_list],
             prop_sbins=[r_._layout.sbins for r_ in bs.ray_samples_list],
-            prop_weights=[w_[..., 0] for w_ in bs.weights_list])
+            prop_weights=[w_[..., 0] for w_ in bs.weights_list],
+            scratch=fused_ops.heads_scratch(self._scratch, density.device, id(field_)))
         weights_list = bs.weights_list + [weights[..., None]]
         ray_samples_list = bs.ray_samples_list + [ray_samples]
         outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
-                   "expected_depth": torch.clamp(exp_raw, minmax[0], minmax[1]),  # batch-global clip, renderers.py:574
+                   "expected_depth": expected_depth,  # clipped to the batch-global extrema (renderers.py:574) in-kernel
                    "density": density}
         if self.training:
             outputs["weights_list"] = weights_list
@@ -685,6 +704,11 @@ class ThermalNerfactoModel(nn.Module):
                     cross = (self.field.get_density_only(ray_samples_thermal),
                              self.field_thermal.get_density_only(ray_samples))
         field_rgb = outputs.pop("_field_rgb")
+        for rs_ in (ray_samples, ray_samples_thermal, *st.rgb.ray_samples_list,
+                    *(st.thermal.ray_samples_list if st.thermal is not None else ())):
+            lay_ = getattr(rs_, "_layout", None)
+            if lay_ is not None:  # this forward's consumers are all in place: later, independent evaluations of the
+                lay_.chain = False  # returned samples must not hook into its gradient chain (rays.RayLayout.chain)
 
         if c.density_mode == "shared":
             rgbt = outputs["rgb"]
@@ -737,11 +761,13 @@ class ThermalNerfactoModel(nn.Module):
         reporting code, not part of the loss)."""
         metrics_dict = {}
         if self.training:
-            metrics_dict["distortion"] = 0
+            total = None  # the reference starts from 0 and adds (:255-262): 0 + a == a, one launch less
             for s in self.output_suffixes:
                 fused = outputs.get(f"_distortion{s}")  # made by the final level's launch (_branch_fused)
-                metrics_dict["distortion"] += fused if fused is not None else distortion_loss(
+                term = fused if fused is not None else distortion_loss(
                     outputs[f"weights_list{s}"], outputs[f"ray_samples_list{s}"])
+                total = term if total is None else total + term
+            metrics_dict["distortion"] = total
         self.camera_optimizer.get_metrics_dict(metrics_dict)
         self.shared_camera_optimizer.get_metrics_dict(metrics_dict)
         if self.config.density_mode == "separate":
@@ -784,7 +810,7 @@ class ThermalNerfactoModel(nn.Module):
             d, d2, dt, d2t = (outputs["density"], outputs["density2"], outputs["density_thermal"],
                               outputs["density2_thermal"])
             if self.fuse_losses:  # the four L1 terms and their stop-gradient pattern (:328-344) in one launch
-                entries.append(("density_loss", fused_ops.density_l1(d, d2, dt, d2t, m, r), 1.0))
+                entries.append(("density_loss", fused_ops.density_l1(d, d2, dt, d2t, m, r, scratch=self._scratch), 1.0))
             elif r == 1:
                 entries.append(("density_loss", self.density_loss(d2, dt) + self.density_loss(d, d2t), m))
             else:  # asymmetric stop-gradient pattern, :336-344

@@ -115,32 +115,56 @@ def hash_encode(x: Tensor, table: Tensor, spec: HashGridSpec, table_f16: Optiona
 
 
 # ----------------------------------------------------------------------------------- positions
+def _ray_grad_targets(g_o, g_d, like_o, like_d, zero: bool):
+    """Where a ray-bundle consumer's backward puts d(origins), d(directions): onto the gradient handed down by the
+    bundle's later consumers when there is one (returns accumulate=True), else into fresh buffers."""
+    if g_o is not None and g_d is not None:
+        return _f32c(g_o), _f32c(g_d), True
+    make = torch.zeros_like if zero else torch.empty_like
+    return make(like_o), make(like_d), False
+
+
+def _ray_grad_finish(do, dd, g_o, g_d, accumulated: bool):
+    if not accumulated:  # a lone upstream gradient (never on the model's path)
+        do = do if g_o is None else do + g_o
+        dd = dd if g_d is None else dd + g_d
+    return do, dd
+
+
 class _SamplePositionsFn(torch.autograd.Function):
+    """chain=True also returns origins/directions as pass-through outputs: the bundle's NEXT consumer takes those,
+    so that in the backward its gradient arrives here and this kernel adds onto it in place -- a bundle read by k
+    consumers costs no zero-fills and no autograd additions (it used to cost 2k fills and 2(k-1) adds)."""
+
     @staticmethod
-    def forward(ctx, origins, directions, ebins):
-        origins, directions, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
+    def forward(ctx, origins, directions, ebins, chain):
+        o, d, ebins = _f32c(origins), _f32c(directions), _f32c(ebins)
         r, s = ebins.shape[0], ebins.shape[1] - 1
         x = torch.empty((r * s, 3), device=ebins.device)
         sel = torch.empty((r * s,), device=ebins.device)
-        call("tn_sample_positions_fwd", ptr(origins), ptr(directions), ptr(ebins), r, s, ptr(x), ptr(sel), stream())
-        ctx.save_for_backward(origins, directions, ebins)
+        call("tn_sample_positions_fwd", ptr(o), ptr(d), ptr(ebins), r, s, ptr(x), ptr(sel), stream())
+        ctx.save_for_backward(o, d, ebins)
         ctx.mark_non_differentiable(sel)
-        return x, sel
+        ctx.set_materialize_grads(False)
+        return (x, sel, origins, directions) if chain else (x, sel)
 
     @staticmethod
-    def backward(ctx, dx, _dsel):
+    def backward(ctx, dx, _dsel, g_o=None, g_d=None):
         origins, directions, ebins = ctx.saved_tensors
+        if dx is None:
+            return g_o, g_d, None, None
         r, s = ebins.shape[0], ebins.shape[1] - 1
-        do = torch.empty_like(origins)
-        dd = torch.empty_like(directions)
-        call("tn_sample_positions_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(_f32c(dx)), r, s, ptr(do),
-             ptr(dd), stream())
-        return do, dd, None
+        do, dd, acc = _ray_grad_targets(g_o, g_d, origins, directions, zero=False)
+        call("tn_sample_positions_bwd", ptr(origins), ptr(directions), ptr(ebins), ptr(_f32c(dx)), r, s, int(acc),
+             ptr(do), ptr(dd), stream())
+        do, dd = _ray_grad_finish(do, dd, g_o, g_d, acc)
+        return do, dd, None, None
 
 
-def sample_positions(origins: Tensor, directions: Tensor, ebins: Tensor) -> Tuple[Tensor, Tensor]:
-    """Ray samples -> contracted, normalised grid coordinates x[R*S,3] and selector[R*S]."""
-    return _SamplePositionsFn.apply(origins, directions, ebins)
+def sample_positions(origins: Tensor, directions: Tensor, ebins: Tensor, chain: bool = False):
+    """Ray samples -> contracted, normalised grid coordinates x[R*S,3] and selector[R*S]
+    (+ the pass-through origins/directions for the bundle's next consumer when chain=True)."""
+    return _SamplePositionsFn.apply(origins, directions, ebins, chain)
 
 
 class _ContractPointsFn(torch.autograd.Function):

@@ -88,7 +88,7 @@ class FlatGradBuffer:
         """Let every HashEncoding of `module` scatter its table gradient directly into this buffer (the
         backward kernel accumulates into the parameter's slice; no temporary, no extra add pass).  The caller
         must `zero_()` the buffer once per step.  Returns the number of tables attached."""
-        from .field_components import MLP, HashEncoding
+        from .field_components import MLP, Embedding, HashEncoding
 
         n = 0
         for m in module.modules():
@@ -98,6 +98,12 @@ class FlatGradBuffer:
             elif isinstance(m, MLP) and all(l.weight.grad is not None and l.bias.grad is not None for l in m.layers):
                 # MLP backward kernels add dW/db straight into the buffer too (no temporaries, no accumulate pass)
                 m.grad_sinks = [(l.weight.grad, l.bias.grad) for l in m.layers]
+                n += 1
+            elif isinstance(m, Embedding) and m.embedding.weight.grad is not None:
+                m.grad_sink = m.embedding.weight.grad  # fused colour-head backward (fused_ops._FieldHeadFn)
+                n += 1
+            elif hasattr(m, "pose_adjustment") and hasattr(m, "grad_sink") and m.pose_adjustment.grad is not None:
+                m.grad_sink = m.pose_adjustment.grad  # CameraOptimizer: ray-bundle and regulariser backward kernels
                 n += 1
         return n
 

@@ -24,6 +24,11 @@ class RayLayout:
     sbins: Tensor  # [R,S+1] spacing-domain bin edges
     nears: Tensor  # [R]
     fars: Tensor  # [R]
+    # Set by the model for the layouts of ONE forward whose consumers are all differentiated by one backward: each
+    # consumer then replaces origins/directions by its pass-through outputs, so that the bundle's gradient travels back
+    # along that chain through one buffer (fields._chained_positions).  Off for layouts a caller may evaluate and
+    # differentiate several times independently.
+    chain: bool = False
 
     @property
     def num_rays(self) -> int:

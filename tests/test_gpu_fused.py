@@ -294,3 +294,138 @@ def test_field_head_fused_backward_equals_unfused(rays, samples, out_dim):
     ref = gd * 0.9 * sel * torch.exp(h.detach()[:, 0].clamp(-15, 15))
     close(h.grad[:, 0], ref, 1e-6, 1e-5)
     assert torch.count_nonzero(h.grad[:, 1:]) == 0
+
+
+# ------------------------------------------------------------------------------- launch-count reductions (round 2)
+def test_ray_gradient_chain_equals_autograd_accumulation():
+    """A bundle read by several consumers (two proposal levels, the main field, a cross-field term): the chained
+    pass-through outputs (`chain=True`: one gradient buffer handed back and added onto in place) give the gradients
+    autograd's own accumulation gives."""
+    from nerfstudio_thermal_b200 import ops
+    from nerfstudio_thermal_b200.field_components import HashEncoding
+    torch.manual_seed(11)
+    R = 130
+    o = (torch.randn(R, 3, device=DEV) * 0.3)
+    d = torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
+    bins = [torch.sort(torch.rand(R, s + 1, device=DEV) * 4 + 0.05, dim=-1).values for s in (96, 48, 48)]
+    enc = HashEncoding(num_levels=5, min_res=16, max_res=128, log2_hashmap_size=12).to(DEV)
+    with torch.no_grad():
+        enc.hash_table.mul_(300.0)
+    w1, b1 = torch.randn(16, 10, device=DEV) * 0.3, torch.randn(16, device=DEV) * 0.1
+    w2, b2 = torch.randn(1, 16, device=DEV) * 0.3, torch.randn(1, device=DEV) * 0.1
+    gs = [torch.randn(R * 96, device=DEV), torch.randn(R * 48, 3, device=DEV), torch.randn(R * 48, 3, device=DEV)]
+
+    def run(chain):
+        og, dg = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
+        oc, dc = og * 1.0, dg * 1.0  # non-leaf, as after the pose correction
+        prop = lambda a, b: fused_ops.prop_density(a, b, bins[0], enc.hash_table.detach(), w1, b1, w2, b2, enc.spec,  # noqa: E731
+                                                   1.0, chain=chain)
+        if chain:
+            sig, oc, dc = prop(oc, dc)
+            x1, _, oc, dc = ops.sample_positions(oc, dc, bins[1], chain=True)
+            x2, _, oc, dc = ops.sample_positions(oc, dc, bins[2], chain=True)
+        else:
+            sig = prop(oc, dc)
+            x1, _ = ops.sample_positions(oc, dc, bins[1])
+            x2, _ = ops.sample_positions(oc, dc, bins[2])
+        ((sig * gs[0]).sum() + (x1 * gs[1]).sum() + (x2 * gs[2]).sum()).backward()
+        return og.grad, dg.grad
+
+    (o0, d0), (o1, d1) = run(False), run(True)
+    close(o1, o0, 1e-5, 1e-5)
+    close(d1, d0, 1e-5, 1e-5)
+
+
+def test_ray_features_equal_sh_of_normalised_directions_and_embedding_rows():
+    from nerfstudio_thermal_b200 import ops
+    from nerfstudio_thermal_b200.fields import get_normalized_directions
+    torch.manual_seed(12)
+    R, cams = 333, 9
+    d = torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
+    w = torch.randn(cams, 32, device=DEV)
+    idx = torch.randint(0, cams, (R,), device=DEV)
+    sh, emb = fused_ops.ray_features(d, w, idx)
+    assert torch.equal(sh, ops.sh4(get_normalized_directions(d)))
+    assert torch.equal(emb, w[idx])
+    sh2, none = fused_ops.ray_features(d)
+    assert torch.equal(sh2, sh) and none is None
+
+
+@pytest.mark.parametrize("with_sink", [False, True])
+def test_field_head_forms_the_embedding_gradient_itself(with_sink):
+    """emb_weight/cam_idx path of _FieldHeadFn (tn_embed_bwd: [R,64]x[64,32] product + index_add in one launch, into
+    a sink when given, persistent self-cleaning dz1 buffer) against the differentiable lookup + matmul path."""
+    from nerfstudio_thermal_b200 import ops
+    torch.manual_seed(13)
+    rays, samples, out_dim, cams = 52, 48, 3, 7
+    n = rays * samples
+    h = (torch.randn(n, 16, device=DEV) * 1.5).requires_grad_(True)
+    sel = (torch.rand(n, device=DEV) > 0.2).float()
+    d = torch.nn.functional.normalize(torch.randn(rays, 3, device=DEV), dim=-1)
+    table = torch.randn(cams, 32, device=DEV).requires_grad_(True)
+    idx = (torch.arange(rays, device=DEV) // 4) % cams  # patch-ordered: runs of four rays per camera
+    dims = [63, 64, 64, out_dim]
+    ws = [(torch.randn(dims[i + 1], dims[i], device=DEV) / dims[i] ** 0.5) for i in range(3)]
+    bs = [(torch.randn(dims[i + 1], device=DEV) * 0.1) for i in range(3)]
+    gd, gy = torch.randn(n, device=DEV), torch.randn(n, out_dim, device=DEV)
+    sh, emb_rows = fused_ops.ray_features(d, table, idx)
+    # reference: differentiable lookup, gradient by the head's matmul + index_add_
+    emb = fused_ops.embed_rows(table, idx)
+    dens, y = fused_ops.field_head(h, sel, sh, emb, rays, samples, 15, 0.9, ws, bs, ops.ACT_SIGMOID)
+    ((dens * gd).sum() + (y * gy).sum()).backward()
+    ref_table, ref_h = table.grad.clone(), h.grad.clone()
+    keep = fused_ops.LaunchScratch()
+    sink = torch.zeros_like(table) if with_sink else None
+    for rep in range(2):  # the second pass reuses the persistent dz1 buffer: it must have been left clean
+        table.grad = h.grad = None
+        dens2, y2 = fused_ops.field_head(h, sel, sh, emb_rows, rays, samples, 15, 0.9, ws, bs, ops.ACT_SIGMOID,
+                                         emb_weight=table, cam_idx=idx, emb_sink=sink, scratch=keep)
+        assert torch.equal(dens2, dens) and torch.equal(y2, y)
+        ((dens2 * gd).sum() + (y2 * gy).sum()).backward()
+        got = sink / (rep + 1) if with_sink else table.grad
+        if with_sink:
+            assert table.grad is None
+        rel = ((got - ref_table).norm() / ref_table.norm()).item()
+        assert rel <= 1e-5, rel
+        assert torch.equal(h.grad, ref_h)
+    buf = keep._bufs[("dz1", str(h.device), rays)]
+    assert torch.count_nonzero(buf) == 0
+
+
+def test_camera_kernels_accumulate_into_a_sink():
+    torch.manual_seed(14)
+    R, cams = 256, 8
+    pose = (torch.randn(cams, 6, device=DEV) * 0.05).requires_grad_(True)
+    idx = torch.randint(0, cams, (R,), device=DEV)
+    o, d = torch.randn(R, 3, device=DEV), torch.nn.functional.normalize(torch.randn(R, 3, device=DEV), dim=-1)
+    go, gd = torch.randn(R, 3, device=DEV), torch.randn(R, 3, device=DEV)
+
+    def run(sink):
+        pose.grad = None
+        oo, dd = fused_ops.camera_opt_apply(pose, None, idx, o, d, False, sink=sink)
+        reg, _, _ = fused_ops.camera_regularizer(pose, 0.01, 0.001, 10.0, sink=sink)
+        ((oo * go).sum() + (dd * gd).sum() + 3.0 * reg).backward()
+        return pose.grad
+
+    ref = run(None).clone()
+    sink = torch.zeros_like(pose)
+    assert run(sink) is None
+    close(sink, ref, 1e-6, 1e-5)
+
+
+def test_density_l1_total_by_the_last_cta():
+    torch.manual_seed(15)
+    ts = [(torch.rand(4096 * 48, device=DEV) * 5).requires_grad_(True) for _ in range(4)]
+    ref = fused_ops.density_l1(*ts, 0.001, 0.01)
+    keep = fused_ops.LaunchScratch()
+    for _ in range(3):  # the ticket word re-arms itself
+        got = fused_ops.density_l1(*ts, 0.001, 0.01, scratch=keep)
+        close(got, ref, 1e-9, 2e-6)
+    assert keep._bufs[("l1", str(ts[0].device))].item() == 0
+    got.backward()
+    g = [t.grad.clone() for t in ts]
+    for t in ts:
+        t.grad = None
+    (2.5 * ref).backward()
+    for a, t in zip(g, ts):
+        close(2.5 * a, t.grad, 1e-12, 1e-6)

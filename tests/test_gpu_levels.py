@@ -72,24 +72,32 @@ def test_ray_heads_equal_the_separate_kernels(C, bg_mode, bg, eval_mode):
         wp = ops.sample_weights(pg, peb[:, 1:] - peb[:, :-1])
         pw.append(wp.detach())
         inter_r = inter_r + fo.interlevel_loss_level(w_r, sb, wp, psb)
+    exp_r = torch.clamp(exp_r, mm_r[0], mm_r[1])  # ray_heads returns the clipped depth (renderers.py:574)
     g_rgb, g_acc, g_exp = torch.randn_like(rgb_r), torch.randn_like(acc_r), torch.randn_like(exp_r)
     loss_r = (rgb_r * g_rgb).sum() + (acc_r * g_acc).sum() + (exp_r * g_exp).sum() + 0.3 * dist_r + 1.7 * inter_r
     loss_r.backward()
 
-    sig, col = sigma.clone().requires_grad_(True), colour.clone().requires_grad_(True)
-    psig = [p[0].clone().requires_grad_(True) for p in plev]
-    rgb, acc, med, exp, mm, w, dist, inter = fo.ray_heads(
-        sig, col, eb, sb, bg_mode=bg_mode, bg=bg, eval_mode=eval_mode, want_losses=True, prop_sigma=psig,
-        prop_ebins=[p[1] for p in plev], prop_sbins=[p[2] for p in plev], prop_weights=pw)
-    assert torch.equal(w, w_r.detach()) and torch.equal(rgb, rgb_r.detach()) and torch.equal(acc, acc_r.detach())
-    assert torch.equal(med, med_r) and torch.equal(exp, exp_r.detach()) and torch.equal(mm, mm_r)
-    torch.testing.assert_close(dist, dist_r.detach(), rtol=2e-6, atol=1e-9)  # sums over rays in another order
-    torch.testing.assert_close(inter, inter_r.detach(), rtol=2e-6, atol=1e-9)
-    ((rgb * g_rgb).sum() + (acc * g_acc).sum() + (exp * g_exp).sum() + 0.3 * dist + 1.7 * inter).backward()
-    torch.testing.assert_close(sig.grad, sig_r.grad, rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(col.grad, col_r.grad, rtol=1e-6, atol=1e-7)
-    for a, b in zip(psig, psig_r):
-        torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-8)
+    # both launch protocols: self-initialising (clone before, scale + clamp after the kernel) and with the call
+    # site's persistent scratch words, which the kernel's last CTA re-arms -- the SECOND and THIRD pass reuse them
+    keep = fo.LaunchScratch()
+    for scratch in (None, fo.heads_scratch(keep, DEV, 0), fo.heads_scratch(keep, DEV, 0)):
+        sig, col = sigma.clone().requires_grad_(True), colour.clone().requires_grad_(True)
+        psig = [p[0].clone().requires_grad_(True) for p in plev]
+        rgb, acc, med, exp, mm, w, dist, inter = fo.ray_heads(
+            sig, col, eb, sb, bg_mode=bg_mode, bg=bg, eval_mode=eval_mode, want_losses=True, prop_sigma=psig,
+            prop_ebins=[p[1] for p in plev], prop_sbins=[p[2] for p in plev], prop_weights=pw, scratch=scratch)
+        assert torch.equal(w, w_r.detach()) and torch.equal(rgb, rgb_r.detach()) and torch.equal(acc, acc_r.detach())
+        assert torch.equal(med, med_r) and torch.equal(exp, exp_r.detach()) and torch.equal(mm, mm_r)
+        torch.testing.assert_close(dist, dist_r.detach(), rtol=2e-6, atol=1e-9)  # sums over rays in another order
+        torch.testing.assert_close(inter, inter_r.detach(), rtol=2e-6, atol=1e-9)
+        ((rgb * g_rgb).sum() + (acc * g_acc).sum() + (exp * g_exp).sum() + 0.3 * dist + 1.7 * inter).backward()
+        torch.testing.assert_close(sig.grad, sig_r.grad, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(col.grad, col_r.grad, rtol=1e-6, atol=1e-7)
+        for a, b in zip(psig, psig_r):
+            torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-8)
+        if scratch is not None:  # left in its initial state
+            assert scratch[:4].tolist() == [float("inf"), float("-inf"), 0.0, 0.0]
+            assert scratch.view(torch.int32)[4].item() == 0
 
 
 def test_ray_heads_without_losses_or_proposal_gradients():
