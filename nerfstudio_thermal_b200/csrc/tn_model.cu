@@ -280,39 +280,45 @@ __global__ void camera_reg_bwd_kernel(const float* __restrict__ pose, const floa
 // field_components/embedding.py's autograd in one launch).  A warp owns kRaysPerWarp consecutive rays, lane = j;
 // consecutive rays of a patch-ordered batch share their camera, so the warp adds them up and issues one atomic row per
 // run.  dz1_ray rows are cleared after use when `clear` is set (the caller keeps one self-cleaning buffer).
-constexpr int kEmbRaysPerWarp = 8;
+constexpr int kEmbRaysPerWarp = 4;  // one 2x2 patch: the rays of a patch share their camera
+template <int WIDTH>
 __global__ void __launch_bounds__(128) embed_bwd_kernel(float* __restrict__ dz1_ray, const float* __restrict__ w0,
-                                                        const int64_t* __restrict__ cam, int64_t R, int width,
-                                                        int in_dim, int col0, int E, int clear,
-                                                        float* __restrict__ dweight) {
+                                                        const int64_t* __restrict__ cam, int64_t R, int in_dim,
+                                                        int col0, int E, int clear, float* __restrict__ dweight) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t r0 = warp * kEmbRaysPerWarp;
   if (r0 >= R) return;
   const int64_t r1 = min(r0 + (int64_t)kEmbRaysPerWarp, R);
   for (int j0 = 0; j0 < E; j0 += 32) {
-    const int j = j0 + lane;
+    const int j = min(j0 + lane, E - 1);  // lanes past E compute a duplicate column and do not store
+    float wcol[WIDTH];                    // this lane's column of W0: loaded once, all loads in flight together
+#pragma unroll
+    for (int k = 0; k < WIDTH; ++k) wcol[k] = __ldg(w0 + (int64_t)k * in_dim + col0 + j);
     float acc = 0.f;
     int64_t run_cam = cam[r0];
     for (int64_t r = r0; r < r1; ++r) {
       const int64_t c = cam[r];
       if (c != run_cam) {
-        if (j < E) atomicAdd(dweight + run_cam * E + j, acc);
+        if (j0 + lane < E) atomicAdd(dweight + run_cam * E + j, acc);
         acc = 0.f;
         run_cam = c;
       }
-      if (j < E) {
-        const float* z = dz1_ray + r * width;
-        float t = 0.f;
-        for (int k = 0; k < width; ++k) t += z[k] * __ldg(w0 + (int64_t)k * in_dim + col0 + j);
-        acc += t;
+      const float4* z4 = reinterpret_cast<const float4*>(dz1_ray + r * WIDTH);  // same address in every lane: broadcast
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < WIDTH / 4; ++k) {
+        const float4 z = z4[k];
+        t += z.x * wcol[4 * k] + z.y * wcol[4 * k + 1] + z.z * wcol[4 * k + 2] + z.w * wcol[4 * k + 3];
       }
+      acc += t;
     }
-    if (j < E) atomicAdd(dweight + run_cam * E + j, acc);
+    if (j0 + lane < E) atomicAdd(dweight + run_cam * E + j, acc);
   }
   if (clear) {
     __syncwarp();
-    for (int64_t i = r0 * width + lane; i < r1 * width; i += 32) dz1_ray[i] = 0.f;
+    float4* z4 = reinterpret_cast<float4*>(dz1_ray + r0 * WIDTH);
+    for (int64_t i = lane; i < (r1 - r0) * (WIDTH / 4); i += 32) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -411,12 +417,12 @@ extern "C" int tn_camera_reg_bwd(const float* pose, const float* upstream_dev, i
 extern "C" int tn_embed_bwd(float* dz1_ray, const float* w0, const int64_t* camera_indices, int64_t R, int width,
                             int in_dim, int col0, int emb_dim, int clear, float* dweight, void* stream) {
   TN_REQUIRE(dz1_ray && w0 && camera_indices && dweight, TN_EINVAL, "embed_bwd: null pointer");
-  TN_REQUIRE(width >= 1 && emb_dim >= 1 && col0 >= 0 && col0 + emb_dim <= in_dim, TN_EINVAL,
-             "embed_bwd: bad shape width=%d in_dim=%d col0=%d emb_dim=%d", width, in_dim, col0, emb_dim);
+  TN_REQUIRE(width == 64 && emb_dim >= 1 && col0 >= 0 && col0 + emb_dim <= in_dim, TN_EINVAL,
+             "embed_bwd: bad shape width=%d (64) in_dim=%d col0=%d emb_dim=%d", width, in_dim, col0, emb_dim);
   if (R <= 0) return R == 0 ? TN_OK : TN_EINVAL;
   const int64_t warps = (R + kEmbRaysPerWarp - 1) / kEmbRaysPerWarp;
-  embed_bwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-      dz1_ray, w0, camera_indices, R, width, in_dim, col0, emb_dim, clear, dweight);
+  embed_bwd_kernel<64><<<(unsigned)((warps + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+      dz1_ray, w0, camera_indices, R, in_dim, col0, emb_dim, clear, dweight);
   return check_launch("embed_bwd_kernel");
 }
 
