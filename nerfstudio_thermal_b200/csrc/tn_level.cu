@@ -424,10 +424,28 @@ __global__ void __launch_bounds__(32 * kLevelWarps) ray_heads_fwd_kernel(const H
       const float mn = __ldcg(a.scratch), mx = __ldcg(a.scratch + 1);
       __syncthreads();  // every thread holds the extrema before thread 0 re-arms the scratch
       if (a.exp_clip_out && a.exp_out && a.minmax) {
-        for (int64_t i = threadIdx.x; i < a.R; i += blockDim.x) {
-          const float v = __ldcg(a.exp_out + i);
-          a.exp_clip_out[i] = v < mn ? mn : (v > mx ? mx : v);  // torch.clamp: NaN stays NaN
+        // one CTA walks all R rays: 16-byte accesses, eight independent loads in flight per thread (a scalar loop
+        // of dependent L2 round trips took 100 us at 32768 rays)
+        auto clip = [&](float v) { return v < mn ? mn : (v > mx ? mx : v); };  // torch.clamp: NaN stays NaN
+        const bool vec = ((reinterpret_cast<uintptr_t>(a.exp_out) | reinterpret_cast<uintptr_t>(a.exp_clip_out)) & 15) == 0;
+        const int64_t n4 = vec ? a.R / 4 : 0;
+        const float4* src = reinterpret_cast<const float4*>(a.exp_out);
+        float4* dst = reinterpret_cast<float4*>(a.exp_clip_out);
+        constexpr int U = 8;
+        for (int64_t i0 = threadIdx.x; i0 < n4; i0 += (int64_t)blockDim.x * U) {
+          float4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            v[u] = i < n4 ? __ldcg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            if (i < n4) dst[i] = make_float4(clip(v[u].x), clip(v[u].y), clip(v[u].z), clip(v[u].w));
+          }
         }
+        for (int64_t i = 4 * n4 + threadIdx.x; i < a.R; i += blockDim.x) a.exp_clip_out[i] = clip(__ldcg(a.exp_out + i));
       }
       if (threadIdx.x == 0) {
         if (a.minmax) { a.minmax[0] = mn; a.minmax[1] = mx; }

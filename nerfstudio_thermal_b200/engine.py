@@ -106,10 +106,10 @@ class GraphedTrainStep:
         early = [n for n in ("fields", "fields_thermal") if n in groups]
         order = early + [n for n in groups if n not in early]
         nccl = world > 1 and torch.distributed.get_backend(group) == "nccl"
-        # measured (profiles/r02_exchange.md, ms/step at 2 / 4 / 8 GPUs; one GPU: 2.27): "after" 2.61 / - / 2.74,
-        # "overlap" 2.48 / 2.57 / 3.06, "pipeline" 2.57 / 2.69 / 2.64 -- the in-graph overlap wins up to four GPUs, the
-        # three-phase pipeline with the peer-memory exchange beyond
-        default = "overlap" if world <= 4 else "pipeline"
+        # measured at the end of round 2 (profiles/r02_exchange/summary.txt, ms/step at 2 / 4 / 8 GPUs; one GPU: 2.10):
+        # "after" 2.42 / - / -, "overlap" 2.35 / 2.39 / 4.60, "pipeline" 2.30 / 2.39 / 2.43 -- the three-phase pipeline
+        # with the peer-memory exchange is never behind (its end-to-end time is the lowest at every size)
+        default = "pipeline"
         mode = os.environ.get("TN_COMM", default if overlap_comm is None else ("overlap" if overlap_comm else "after"))
         # the main fields' exchange over NVLink peer memory (parallel.PeerExchange) needs a peer-mappable buffer
         want_peer = nccl and mode == "pipeline" and use_graph and os.environ.get("TN_PEER_EXCHANGE", "1") == "1"

@@ -587,7 +587,10 @@ class ThermalNerfactoModel(nn.Module):
             prop_ebins=[r_._layout.ebins for r_ in bs.ray_samples_list],
             prop_sbins=[r_._layout.sbins for r_ in bs.ray_samples_list],
             prop_weights=[w_[..., 0] for w_ in bs.weights_list],
-            scratch=fused_ops.heads_scratch(self._scratch, density.device, id(field_)))
+            # training (a few thousand rays, launch-bound): the kernel's last CTA finishes extrema / loss means / clip.
+            # Eval chunks (32768 rays = 8192 CTAs): one ticket per CTA and a one-CTA clip pass cost more (+40 us) than
+            # the two small launches they replace, so the self-initialising path is kept there.
+            scratch=fused_ops.heads_scratch(self._scratch, density.device, id(field_)) if self.training else None)
         weights_list = bs.weights_list + [weights[..., None]]
         ray_samples_list = bs.ray_samples_list + [ray_samples]
         outputs = {"rgb": rgb, "accumulation": accumulation, "depth": depth,
