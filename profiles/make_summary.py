@@ -1,7 +1,7 @@
 """Regenerate a round's ncu summary from the committed ncu exports (profiles/<tag>_*_ncu_raw.csv, <tag>_launches.csv).
 
     python profiles/make_summary.py            > profiles/r01_ncu_summary.md
-    python profiles/make_summary.py r02f profiles/r02_preface.md > profiles/r02_ncu_summary.md
+    python profiles/make_summary.py r02g profiles/r02_preface.md > profiles/r02_ncu_summary.md
 """
 import sys
 import collections
@@ -37,7 +37,7 @@ def launch_table(path):
     ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     names = [r[ik] for r in rows[1:]]
     t = [float(r[iv].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}[r[iu]] for r in rows[1:]]
-    marks = [i for i, n in enumerate(names) if "density_l1" in n]  # launched once per step
+    marks = [i for i, n in enumerate(names) if "loss_sum_kernel" in n]  # launched once per step
     a, b = marks[-2], marks[-1]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in zip(names[a:b], t[a:b]):

@@ -52,7 +52,7 @@ def main(paths):
             tag = tag_of(r[idx["Kernel Name"]], d)
             if tag:
                 acc.setdefault(tag, []).append(d)
-    out = {"_source": "ncu --set full --clock-control none, one eager train step of the round's final code (profiles/capture_r02.sh, r02f_*); "
+    out = {"_source": "ncu --set full --clock-control none, one eager train step of the round's final code (profiles/capture_r02.sh, r02g_*); "
                       "per launch, averaged over the captured launches of the tag", "_detail": {}}
     for tag, ds in sorted(acc.items()):
         n = len(ds)
