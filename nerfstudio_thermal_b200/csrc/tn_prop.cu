@@ -211,6 +211,11 @@ __global__ void __launch_bounds__(kPts, TN_PROP_BWD_MB) prop_bwd_kernel(
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t p = t * kPts + tid;
     const bool valid = p < N;
+    // The interlevel loss is a hinge (losses.py:87-103): rays whose proposal histogram already bounds the fine
+    // weights send exactly zero down here.  A warp whose 32 samples all carry a zero upstream gradient contributes
+    // nothing to any output (table, weights, rays): it skips the tile before the first gather.
+    const float up = valid ? __ldg(d_density + p) : 0.f;
+    if (!__any_sync(0xffffffffu, up != 0.f)) continue;
     const int64_t r = valid ? p / S : 0;
     const int s = valid ? (int)(p - r * S) : 0;
     float st = 0.f, en = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f;
@@ -226,7 +231,7 @@ __global__ void __launch_bounds__(kPts, TN_PROP_BWD_MB) prop_bwd_kernel(
     prop_features<L, NEED_DX>(table, s_scale, mask, T, x0, x1, x2, feat, jac);
     const float raw = prop_mlp<L>(sw, feat, h);
     // d(density)/d(raw) = scale * sel * exp(clamp(raw, -15, 15))   (activations.py:41)
-    const float g = valid ? __ldg(d_density + p) * scale * sel * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
+    const float g = valid ? up * scale * sel * expf(fminf(fmaxf(raw, -15.f), 15.f)) : 0.f;
     float dfeat[IN];
 #pragma unroll
     for (int k = 0; k < IN; ++k) dfeat[k] = 0.f;

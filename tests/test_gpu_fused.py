@@ -152,6 +152,10 @@ def test_fused_proposal_field_vs_oracle(S, max_res):
                                   log2_hashmap_size=12)
     close(dens, ref, 1e-5, 2e-5)
     g = torch.rand_like(ref)
+    # the interlevel hinge sends exact zeros for whole stretches of a ray: the backward kernel skips warps whose 32
+    # samples all carry a zero upstream gradient -- rays 10..39 entirely, and ragged tails of the others
+    g[10:40] = 0.0
+    g[40:, S // 2 + 3:] = 0.0
     (ref * g).sum().backward()
     (dens * g.to(DEV)).sum().backward()
 
