@@ -81,6 +81,15 @@ def make_batch(rays, seed, num_cams=NUM_CAMERAS):
                 is_thermal=is_thermal)
 
 
+def pinned_batch(runner, batch):
+    """The runner's own pinned host batch (`GraphedTrainStep.host_batch`: one pinned buffer laid out like the device-side
+    inputs, what a data loader would collate into) filled with `batch`: one host-to-device copy per step."""
+    host = runner.host_batch()
+    for k, v in batch.items():
+        host[k].copy_(v)
+    return host
+
+
 def build_model(args):
     import nerfstudio_thermal_b200 as tn
 
@@ -554,6 +563,8 @@ def shared8192_leg(args, D, steps, peaks, l2):
     for _ in range(3):
         runner.step(None)
     ms = D.timed(lambda: runner.step(None), steps) / steps
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    host = pinned_batch(runner, host)
     for _ in range(2):
         runner.step(host).item()
     ms_e2e = D.timed(lambda: runner.step(host).item(), steps) / steps
@@ -563,7 +574,7 @@ def shared8192_leg(args, D, steps, peaks, l2):
            "config": {"workload": train_workload(a), "rays_per_gpu": a.rays, "parallelism": f"dp{D.world}",
                       "density_loss_mult": c.density_loss_mult, "cross_channel_loss_mult": c.cross_channel_loss_mult},
            "e2e": {"value": D.world * a.rays / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e,
-                   "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                   "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4}}
     del runner, model
     torch.cuda.empty_cache()
@@ -707,8 +718,10 @@ def run_b200(args):
     _lib.STATS.reset()
     ms_total = D.timed(lambda: step(None), args.steps)
     # end to end: pinned host batch -> device every step, loss read back every step
+    host = pinned_batch(runner, host)
+
     def e2e_step():
-        return step(host).item()  # pinned host batch -> static device buffers, replay, loss read back
+        return step(host).item()  # pinned host batch -> static device buffers (one copy), replay, loss read back
 
     for _ in range(2):
         e2e_step()

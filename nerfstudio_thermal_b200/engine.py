@@ -160,7 +160,15 @@ class GraphedTrainStep:
             self._main_group = torch.distributed.new_group(ranks=ranks, backend="nccl")
         for f in self._fields:  # (also detaches the hooks of an earlier runner of the same model)
             f.grads_ready_callback = self._field_ready if self._early_active else None
-        self.static = {k: torch.empty_like(example_batch[k], device=self.device) for k in BATCH_KEYS}
+        # the step's inputs live in ONE device buffer (16-byte aligned slices): a host batch laid out the same way
+        # (`host_batch()`) reaches the device with a single copy instead of one per tensor
+        self._static_layout, nbytes = [], 0
+        for k in BATCH_KEYS:
+            t = example_batch[k]
+            self._static_layout.append((k, nbytes, t.dtype, tuple(t.shape)))
+            nbytes += (t.numel() * t.element_size() + 15) // 16 * 16
+        self._static_bytes = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.static = self._views(self._static_bytes)
         self._seed = torch.ones((), device=self.device)
         # Warm-up passes and every capture run on ONE stream.  autograd's AccumulateGrad nodes remember the stream they
         # were created on and outlive a step (the model and this runner keep parts of the last graph alive); a
@@ -348,7 +356,27 @@ class GraphedTrainStep:
                 self.optimizer.step_range(0, self._early_end, zero_grads=self._zero_in_adam)
         self._early_done = True
 
+    def _views(self, buf: Tensor) -> Dict[str, Tensor]:
+        out = {}
+        for k, off, dtype, shape in self._static_layout:
+            n = int(torch.tensor(shape).prod().item()) if len(shape) else 1
+            out[k] = buf[off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+        return out
+
+    def host_batch(self) -> Dict[str, Tensor]:
+        """Pinned host tensors (one per batch key, same shapes and dtypes as the example batch) that are views of ONE
+        pinned buffer laid out like the device-side input buffer: fill them (a data loader collates into them) and
+        pass the dict to `step()` -- the whole batch then moves with a single host-to-device copy."""
+        buf = torch.empty(self._static_bytes.numel(), dtype=torch.uint8).pin_memory()
+        views = self._views(buf)
+        views["_packed"] = buf
+        return views
+
     def _load(self, batch: Dict[str, Tensor]) -> None:
+        packed = batch.get("_packed")
+        if packed is not None and packed.numel() == self._static_bytes.numel() and packed.dtype == torch.uint8:
+            self._static_bytes.copy_(packed, non_blocking=True)
+            return
         for k in BATCH_KEYS:
             self.static[k].copy_(batch[k], non_blocking=True)
 

@@ -292,3 +292,24 @@ def test_three_phase_schedule_equals_the_single_graph():
         assert abs(l0[k] - l1[k]) <= 2e-6 * max(abs(l0[k]), 1e-6), k
     for name, (b, e) in ranges.items():
         assert pu.rel_l2(g1[b:e], g0[b:e]) <= 2e-5, name
+
+
+def test_packed_host_batch_moves_with_one_copy_and_equals_the_per_tensor_load():
+    """`GraphedTrainStep.host_batch()`: pinned views of one buffer laid out like the device-side inputs; a step fed
+    with it gives the loss of a step fed with the separate tensors."""
+    model, batch, _ = _small()
+    _no_jitter(model)
+    runner = engine.GraphedTrainStep(model, batch, use_graph=True)
+    cpu = {k: v.cpu() for k, v in batch.items()}
+    ref = float(runner.step(cpu))
+    host = runner.host_batch()
+    assert host["_packed"].is_pinned() and set(cpu) <= set(host)
+    for k, v in cpu.items():
+        assert host[k].shape == v.shape and host[k].dtype == v.dtype
+        host[k].copy_(v)
+    for k in cpu:  # scribble over the device inputs: the packed copy must restore every one of them
+        runner.static[k].zero_()
+    got = float(runner.step(host))
+    assert got == ref
+    for k, v in cpu.items():
+        assert torch.equal(runner.static[k].cpu(), v), k
