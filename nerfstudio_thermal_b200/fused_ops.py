@@ -64,7 +64,8 @@ class LaunchScratch:
     def get(self, key, make):
         t = self._bufs.get(key)
         if t is None:
-            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+            if (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()) \
+                    or torch.is_inference_mode_enabled():
                 return None
             if len(self._bufs) > 16:
                 self._bufs.clear()

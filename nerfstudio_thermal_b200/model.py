@@ -159,7 +159,8 @@ class NearFarCollider(nn.Module):
             planes = (torch.full((*o.shape[:-1], 1), float(near_plane), device=o.device, dtype=o.dtype),
                       torch.full((*o.shape[:-1], 1), float(self.far_plane), device=o.device, dtype=o.dtype))
             # (a tensor first made while a CUDA graph is being captured only holds its values after a replay)
-            if not (o.is_cuda and torch.cuda.is_current_stream_capturing()):
+            # (nor is an inference-mode tensor kept: a later training forward could not use it under autograd)
+            if not (o.is_cuda and torch.cuda.is_current_stream_capturing()) and not torch.is_inference_mode_enabled():
                 if len(self._planes) > 8:
                     self._planes.clear()
                 self._planes[key] = planes

@@ -326,3 +326,48 @@ def test_draw_jitters_reproduces_the_samplers_random_stream():
     model.proposal_sampler.initial_sampler.single_jitter = False
     j = model.proposal_sampler.draw_jitters(10, "cpu")
     assert j[0].shape == (10, 257) and j[1].shape == (10, 1)
+
+
+def test_gradient_sinks_cover_tables_mlps_embeddings_and_poses():
+    """FlatGradBuffer.attach_sinks hands every fused backward its accumulation target: hash tables, MLP layers, the
+    appearance embeddings and the camera optimizers' pose tables all alias their slice of the ONE flat buffer."""
+    cfg = tn.ThermalNerfactoModelConfig(density_mode="separate", log2_hashmap_size=8, proposal_net_args_list=[
+        {"hidden_dim": 16, "log2_hashmap_size": 8, "num_levels": 5, "max_res": m, "use_linear": False} for m in (64, 128)])
+    model = cfg.setup(num_train_data=6, metadata={"is_thermal": [0, 0, 0, 1, 1, 1]})
+    grads = parallel.FlatGradBuffer.from_param_groups(model.get_param_groups())
+    n = grads.attach_sinks(model)
+    base = grads.flat.untyped_storage().data_ptr()
+    sinks = []
+    for m in model.modules():
+        if isinstance(m, tn.field_components.HashEncoding):
+            sinks.append(m.grad_sink)
+        elif isinstance(m, tn.field_components.MLP):
+            sinks += [t for pair in m.grad_sinks for t in pair]
+        elif isinstance(m, tn.field_components.Embedding):
+            sinks.append(m.grad_sink)
+        elif isinstance(m, tn.CameraOptimizer) and m.config.mode != "off":
+            sinks.append(m.grad_sink)
+    assert n >= 12 and len(sinks) >= 12 and all(s is not None for s in sinks)
+    assert all(s.untyped_storage().data_ptr() == base for s in sinks)
+    emb = model.field.embedding_appearance
+    assert emb.grad_sink.data_ptr() == emb.embedding.weight.grad.data_ptr()
+    cam = model.camera_optimizer
+    assert cam.grad_sink.shape == cam.pose_adjustment.shape
+    assert cam.grad_sink.data_ptr() == cam.pose_adjustment.grad.data_ptr()
+    # "off" optimizers (shared pose tables are disabled by default) have no parameter and no sink
+    assert model.shared_camera_optimizer.config.mode == "off" and model.shared_camera_optimizer.grad_sink is None
+
+
+def test_launch_scratch_and_chain_defaults():
+    from nerfstudio_thermal_b200 import fused_ops
+    from nerfstudio_thermal_b200.rays import RayLayout
+    keep = fused_ops.LaunchScratch()
+    made = []
+    a = keep.get("k", lambda: made.append(1) or torch.zeros(3))
+    b = keep.get("k", lambda: made.append(1) or torch.zeros(3))
+    assert a is b and len(made) == 1  # made once, then the same buffer
+    with torch.inference_mode():
+        assert keep.get("other", lambda: torch.zeros(1)) is None  # never created where it could not be reused
+    lay = RayLayout(torch.zeros(2, 3), torch.zeros(2, 3), torch.zeros(2, 5), torch.zeros(2, 5), torch.zeros(2),
+                    torch.ones(2))
+    assert lay.chain is False  # gradient chaining is opt-in (the model sets it for the layouts of one forward)
