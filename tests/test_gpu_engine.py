@@ -310,6 +310,6 @@ def test_packed_host_batch_moves_with_one_copy_and_equals_the_per_tensor_load():
     for k in cpu:  # scribble over the device inputs: the packed copy must restore every one of them
         runner.static[k].zero_()
     got = float(runner.step(host))
-    assert got == ref
+    assert abs(got - ref) <= 1e-6 * abs(ref)  # (the ray-level loss sums are atomics: last-bit differences between replays)
     for k, v in cpu.items():
         assert torch.equal(runner.static[k].cpu(), v), k
