@@ -675,6 +675,30 @@ __global__ void __launch_bounds__(NTH, TcBwdSmem<IN, W, NL>::per_sm) mlp_tc_bwd_
   for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
     const int64_t row0 = t * TP;
     const int rows = (int)min((int64_t)TP, N - row0);
+    if constexpr (HEAD) {
+      // A tile whose 128 rows all carry a zero colour gradient needs no product at all: dX, dW and the per-ray sums
+      // are exactly zero and only the density backward (column 0 of dh) is left.  This is not a corner case: the RGB
+      // loss is masked to the rays of RGB cameras (models/thermal_nerfacto.py:315-318), so in the RGB branch every
+      // sample of a thermal camera's ray arrives here with dy == 0 (41-50 % of the tiles of that launch).
+      bool nz = false;
+      if (half == 0) {
+#pragma unroll
+        for (int j = 0; j < OUTP; ++j) nz |= dyr[j] != 0.f;
+      }
+      if (!__syncthreads_or(nz)) {
+        if (half == 0 && row < rows) {
+          const int64_t p = row0 + row;
+          const float sel = __ldg(hd.sel + p);
+          const float dd = hd.d_density ? __ldg(hd.d_density + p) : 0.f;
+          const float dh0 = dd * hd.scale * sel * expf(fminf(fmaxf(xh0, -15.f), 15.f));
+          float4* dst = reinterpret_cast<float4*>(hd.dh + p * 16);
+          dst[0] = make_float4(dh0, 0.f, 0.f, 0.f);
+          dst[1] = dst[2] = dst[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (t + gridDim.x < tiles) prefetch(t + gridDim.x);
+        continue;  // no barrier phase, no TMEM accumulator and no operand tile was touched
+      }
+    }
     // this thread's word (its 32 columns) of the ReLU masks of hidden layer 1 and of the last hidden layer
     uint32_t m_first = 0, m_last = 0;
     const bool have_mask = relu_mask != nullptr;
