@@ -67,8 +67,8 @@ class LaunchScratch:
             if (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()) \
                     or torch.is_inference_mode_enabled():
                 return None
-            if len(self._bufs) > 16:
-                self._bufs.clear()
+            # never evicted: a captured CUDA graph holds the buffer's ADDRESS, not a reference (callers only ask for
+            # small buffers: a few words per call site, <= 8 MB per distinct batch size)
             t = self._bufs[key] = make()
         return t
 
@@ -130,7 +130,7 @@ class _FieldHeadFn(torch.autograd.Function):
         # dz1_ray: accumulated into by the head kernel; with the table path a persistent buffer that tn_embed_bwd clears
         key = ("dz1", str(h.device), rays)
         keep = ctx.scratch.get(key, lambda: torch.zeros((rays, 64), device=h.device)) \
-            if (want_table and ctx.scratch is not None) else None
+            if (want_table and ctx.scratch is not None and rays <= 32768) else None
         if keep is not None:
             if key in ctx.scratch.dirty:
                 keep.zero_()

@@ -152,17 +152,18 @@ class NearFarCollider(nn.Module):
     def forward(self, ray_bundle: RayBundle) -> RayBundle:
         near_plane = self.near_plane if (self.training or not self.reset_near_plane) else 0
         o = ray_bundle.origins
-        # constants: built once per (batch shape, device, planes) instead of ones_like + two multiplies per call
+        # constants: built once per (batch shape, device, planes) instead of ones_like + two multiplies per call.
+        # Entries are never evicted -- a captured CUDA graph reads them by ADDRESS, it holds no reference -- so only
+        # training-sized batches are kept (<= 65536 rays = 0.5 MB per entry); frames and sweeps build theirs per call.
         key = (tuple(o.shape[:-1]), str(o.device), o.dtype, float(near_plane), float(self.far_plane))
         planes = self._planes.get(key)
         if planes is None:
             planes = (torch.full((*o.shape[:-1], 1), float(near_plane), device=o.device, dtype=o.dtype),
                       torch.full((*o.shape[:-1], 1), float(self.far_plane), device=o.device, dtype=o.dtype))
-            # (a tensor first made while a CUDA graph is being captured only holds its values after a replay)
-            # (nor is an inference-mode tensor kept: a later training forward could not use it under autograd)
-            if not (o.is_cuda and torch.cuda.is_current_stream_capturing()) and not torch.is_inference_mode_enabled():
-                if len(self._planes) > 8:
-                    self._planes.clear()
+            # (a tensor first made while a CUDA graph is being captured only holds its values after a replay, and an
+            # inference-mode tensor could not be used by a later training forward under autograd)
+            if planes[0].numel() <= 65536 and not (o.is_cuda and torch.cuda.is_current_stream_capturing()) \
+                    and not torch.is_inference_mode_enabled():
                 self._planes[key] = planes
         ray_bundle.nears, ray_bundle.fars = planes
         return ray_bundle
