@@ -197,3 +197,44 @@ def test_lazy_jitter_matches_reference_rng_order(golden):
                                               g["camera_indices"], training=True)
     close(out["rgb"], g["train/rgb"])
     close(out["rgb_thermal"], g["train/rgb_thermal"])
+
+
+def test_interlevel_hinge_sends_exact_zeros_to_bounded_rays():
+    """Premise of the proposal backward's early-out (csrc/tn_prop.cu): the interlevel loss is a hinge
+    (model_components/losses.py:87-103), so a ray whose proposal histogram bounds the fine weights everywhere sends
+    EXACTLY zero to its proposal densities; only rays that violate the bound carry a gradient."""
+    from oracle import model as om
+    from oracle import sampling as osamp
+    torch.manual_seed(0)
+    R, Sp, Sf = 2, 32, 12
+    o, d = torch.zeros(R, 3), torch.nn.functional.normalize(torch.randn(R, 3), dim=-1)
+    nears, fars = torch.full((R, 1), 0.05), torch.full((R, 1), 1000.0)
+    prop = osamp.initial_samples(o, d, None, nears, fars, Sp, None)
+    sigma = torch.full((R, Sp, 1), 0.3, requires_grad=True)
+    w_prop = osamp.sample_weights(prop.deltas, sigma)
+    fine = osamp.pdf_resample(prop, w_prop.detach(), Sf, None)
+    # ray 0: fine weights far below the proposal mass they sit in (bounded); ray 1: above it (the hinge is active)
+    w_fine = torch.stack([torch.full((Sf, 1), 1e-4), torch.full((Sf, 1), 0.9)])
+    loss = om.interlevel_loss([w_prop, w_fine], [prop, fine])
+    loss.backward()
+    assert torch.count_nonzero(sigma.grad[0]) == 0
+    assert torch.count_nonzero(sigma.grad[1]) > 0
+
+
+def test_rgb_loss_sends_exact_zeros_to_rays_of_thermal_cameras():
+    """Premise of the colour-head backward's tile skip (csrc/tn_mlp_tc.cu): the RGB loss is masked to the rays of RGB
+    cameras (models/thermal_nerfacto.py:315-318), so the rendered RGB of a thermal camera's ray gets an exactly zero
+    gradient -- while the thermal prediction gets one on every ray (thermal MSE on thermal rays, pixel TV and
+    cross-channel terms on RGB rays)."""
+    import oracle
+    torch.manual_seed(1)
+    R = 16
+    is_thermal = (torch.arange(R) >= R // 2).float()
+    rgb = torch.rand(R, 3, requires_grad=True)
+    th = torch.rand(R, 1, requires_grad=True)
+    cfg = oracle.OracleConfig(density_mode="shared")
+    losses = oracle.thermal_nerfacto_losses({}, cfg, {"rgb": rgb, "rgb_thermal": th}, torch.rand(R, 3), is_thermal,
+                                            training=False)
+    sum(losses.values()).backward()
+    assert torch.count_nonzero(rgb.grad[R // 2:]) == 0 and torch.count_nonzero(rgb.grad[:R // 2]) > 0
+    assert torch.count_nonzero(th.grad[R // 2:]) > 0 and torch.count_nonzero(th.grad[:R // 2]) > 0
